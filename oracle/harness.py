@@ -1,0 +1,109 @@
+"""CPU ORACLE harness -- TEST INFRASTRUCTURE ONLY (see oracle/rmp_oracle.py header).
+
+Runs the restated reference on the workloads of ``riemannian_motion_policies_b200.scenarios``:
+  * ``evaluate_loop``  one environment per ``RmpCore.evaluate`` call in a Python loop -- the way the
+    reference itself runs (one env, eager autodiff per leaf); this is the timed CPU baseline;
+  * ``evaluate_vmap``  the same single-environment function under ``torch.func.vmap`` -- identical
+    arithmetic, used by the parity tests to check thousands of environments in seconds.
+"""
+import functools
+import types
+
+import numpy as np
+import torch
+from torch.func import vmap
+
+from . import rmp_oracle as O
+from riemannian_motion_policies_b200 import scenarios as S
+
+
+def namespace(dtype=torch.float32):
+    """The oracle's classes under the reference's names, bound to one dtype."""
+    ns = types.SimpleNamespace(**{k: v for k, v in vars(O).items() if not k.startswith("_")})
+    ns.RmpCore = functools.partial(O.RmpCore, dtype=dtype)
+    ns.UrdfForwardKinematic = functools.partial(O.UrdfForwardKinematic, dtype=dtype)
+    return ns
+
+
+def make_fkine(n, dtype=torch.float32):
+    if n == 2:
+        return O.UrdfForwardKinematic(S.TWO_JOINT_URDF, S.TWO_JOINT_ORDER, dtype=dtype)
+    if n == 7:
+        return O.UrdfForwardKinematic(S.PANDA_WO_TOOL_URDF, S.PANDA_ORDER_7, dtype=dtype)
+    if n == 9:
+        return O.UrdfForwardKinematic(S.PANDA_URDF, S.PANDA_ORDER_9, dtype=dtype)
+    raise ValueError(n)
+
+
+def frame_origins(fkine, q, frames):
+    """[K,3] origins of ``frames`` at configuration q [n] (what the simulator would report as
+    pos_on_link for a control point at the frame origin)."""
+    return torch.stack([fkine.forward(q[None], fr)[0, :3, 3] for fr in frames])
+
+
+def _single_env_fn(config, n, fkine, dtype, combine=False):
+    ns = namespace(dtype)
+    frames = S.collision_frames(fkine)
+
+    def one(q, qd, goal, spheres):
+        q, qd, goal = q.to(dtype), qd.to(dtype), goal.to(dtype)
+        if config == 1:
+            core = S.build_config1(ns, fkine, goal)
+        elif config == 2:
+            core = S.build_config2(ns, fkine, goal, n)
+        else:
+            sph = spheres.to(dtype)
+            origins = frame_origins(fkine, q, frames)                      # [K,3]
+            r = origins[:, None, :] - sph[None, :, :3]
+            on_obst = sph[None, :, :3] + sph[None, :, 3:4] * r / torch.linalg.norm(r, dim=-1, keepdim=True)
+            on_link = origins[:, None, :].expand_as(on_obst)
+            idx = {fr: i for i, fr in enumerate(frames)}
+            tm_for = lambda fr: ns.TaskmapJointFrame4x4ToDistance(on_link[idx[fr]], on_obst[idx[fr]])
+            core = S.BUILDERS[config](ns, fkine, goal, n, tm_for)
+        return core.combine(q, qd) if combine else core.evaluate(q, qd)
+
+    return one
+
+
+def evaluate_loop(config, n, q, qd, goal, spheres=None, dtype=torch.float32, fkine=None):
+    """Reference-style execution: one environment per call.  Inputs are numpy [B,...]."""
+    fkine = fkine or make_fkine(n, dtype)
+    one = _single_env_fn(config, n, fkine, dtype)
+    out = []
+    for b in range(q.shape[0]):
+        sph = torch.as_tensor(spheres[b]) if spheres is not None else torch.zeros(0, 4)
+        out.append(one(torch.as_tensor(q[b]), torch.as_tensor(qd[b]), torch.as_tensor(goal[b]), sph))
+    return torch.stack(out).numpy()
+
+
+def evaluate_vmap(config, n, q, qd, goal, spheres=None, dtype=torch.float32, chunk=1024, fkine=None):
+    """Same arithmetic, vectorised over environments with torch.func.vmap."""
+    fkine = fkine or make_fkine(n, dtype)
+    one = _single_env_fn(config, n, fkine, dtype)
+    B = q.shape[0]
+    if spheres is None:
+        spheres = np.zeros((B, 1, 4), dtype=np.float32)
+    outs = []
+    for s in range(0, B, chunk):
+        sl = slice(s, min(B, s + chunk))
+        outs.append(vmap(one)(torch.as_tensor(q[sl]), torch.as_tensor(qd[sl]), torch.as_tensor(goal[sl]),
+                              torch.as_tensor(spheres[sl])))
+    return torch.cat(outs).numpy()
+
+
+def combined_vmap(config, n, q, qd, goal, spheres=None, dtype=torch.float64, chunk=1024):
+    """(f [B,n], M [B,n,n]) before the resolve -- lets tests measure cond(M) and the singular-value
+    gap around the pinv cutoff (SURVEY.md section 8c guards)."""
+    fkine = make_fkine(n, dtype)
+    one = _single_env_fn(config, n, fkine, dtype, combine=True)
+    B = q.shape[0]
+    if spheres is None:
+        spheres = np.zeros((B, 1, 4), dtype=np.float32)
+    fs, Ms = [], []
+    for s in range(0, B, chunk):
+        sl = slice(s, min(B, s + chunk))
+        f, M = vmap(one)(torch.as_tensor(q[sl]), torch.as_tensor(qd[sl]), torch.as_tensor(goal[sl]),
+                         torch.as_tensor(spheres[sl]))
+        fs.append(f)
+        Ms.append(M)
+    return torch.cat(fs).numpy(), torch.cat(Ms).numpy()

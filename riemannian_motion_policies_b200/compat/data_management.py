@@ -1,0 +1,3 @@
+"""Drop-in shim: lets the reference's experiment scripts keep ``from data_management import ...``.
+Put this directory on sys.path ahead of the reference checkout."""
+from riemannian_motion_policies_b200.data_management import *  # noqa: F401,F403

@@ -1,0 +1,649 @@
+// C ABI of rmp2_b200 (declared in include/rmp2_b200.h): handle lifetime, tree compilation
+// (host only), argument checking, kernel launches, the host-buffer pipeline.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "rmp2_launch.h"
+#include "rmp2_leaves.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(RMP2_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+}  // namespace
+
+struct rmp2_robot {
+  int F = 0, n = 0;
+  std::vector<float> T_const;   // [F][16]
+  std::vector<float> axis;      // [F][3]
+  std::vector<int8_t> jtype;
+  std::vector<int32_t> parent, qidx;
+};
+
+struct HostStage {                // device staging for rmp2_step_host, one per pipeline slot
+  float* buf = nullptr;
+  size_t floats = 0;
+  cudaStream_t stream = nullptr;
+};
+
+struct rmp2_tree {
+  StepTables tab;
+  std::vector<rmp2_leaf_desc> leaves;     // as given, tree order
+  std::vector<int> table_index;           // tree order -> index in tab.leaves
+  int n_pair_sets = 0;
+  int n_goal_slots_used = 0;
+  HostStage stage[3];
+};
+
+// ------------------------------------------------------------------------------ parameter derivation
+// Raw constructor arguments (layout in include/rmp2_b200.h) -> kernel parameters (rmp2_leaves.cuh).
+// Python evaluates these expressions in double before they meet a float32 tensor, so they are
+// evaluated in double here and rounded once.
+static int derive_leaf_params(const rmp2_leaf_desc& d, int n, LeafTab& L, float* vec, int* vec_len) {
+  const float* r = d.params;
+  for (int i = 0; i < RMP2_LEAF_PARAMS; ++i) L.p[i] = 0.f;
+  *vec_len = 0;
+  const int dim = (d.space == RMP2_SPACE_CONFIG) ? n : 3;
+  switch (d.type) {
+    case RMP2_LEAF_TARGET_POLICY:
+      L.p[TP_ALPHA] = r[0];
+      L.p[TP_BETA] = r[1];
+      L.p[TP_C] = r[2];
+      L.p[TP_INV_C] = (float)(1.0 / (double)r[2]);
+      for (int i = 0; i < dim; ++i) vec[i] = d.vec[i];
+      *vec_len = dim;
+      break;
+    case RMP2_LEAF_CONFIG_BIASING:
+      L.p[CB_GAMMA_P] = r[0];
+      L.p[CB_GAMMA_D] = r[1];
+      L.p[CB_W] = r[2];
+      for (int i = 0; i < n; ++i) vec[i] = d.vec[i];
+      *vec_len = n;
+      break;
+    case RMP2_LEAF_JOINT_LIMIT: {
+      const double rr = 0.15;                                   // rmp.py:364
+      L.p[JL_GAMMA_P] = r[0];
+      L.p[JL_GAMMA_D] = r[1];
+      L.p[JL_C3] = (float)(2.0 / (rr * rr * rr));
+      L.p[JL_C2] = (float)(-3.0 / (rr * rr));
+      L.p[JL_R] = (float)rr;
+      L.p[JL_INV_QDMAX] = (float)(1.0 / (20.0 * (2.0 * M_PI) / 60.0));   // rmp.py:374
+      L.p[JL_BETA] = 0.9f;                                               // rmp.py:376
+      L.p[JL_C] = 5.f;
+      L.p[JL_INV_C] = 0.2f;
+      for (int i = 0; i < n; ++i) {
+        vec[i] = d.vec[i];
+        vec[n + i] = d.vec[n + i];
+        vec[2 * n + i] = 1.f / (d.vec[n + i] - d.vec[i]);
+      }
+      *vec_len = 3 * n;
+      break;
+    }
+    case RMP2_LEAF_TARGET_ATTRACTOR:
+      L.p[TA_PGAIN] = r[0];
+      L.p[TA_DGAIN] = r[1];
+      L.p[TA_EPS] = r[2];
+      L.p[TA_EPS10] = (float)((double)r[2] / 10.0);
+      L.p[TA_INV_ALEN] = (float)(1.0 / (double)r[3]);
+      L.p[TA_MIN_ALPHA] = r[4];
+      L.p[TA_SMAX] = r[5];
+      L.p[TA_SMIN] = r[6];
+      L.p[TA_BOOST] = r[7];
+      L.p[TA_INV_BLEN] = (float)(1.0 / (double)r[8]);
+      for (int i = 0; i < 3; ++i) vec[i] = d.vec[i];
+      *vec_len = 3;
+      break;
+    case RMP2_LEAF_VELOCITY_CAP:
+      L.p[VC_CUTOFF] = (float)((double)r[0] - (double)r[1]);   // rmp2.py:97
+      L.p[VC_GAIN] = r[2];
+      L.p[VC_CLIP] = (float)((double)r[1] - 1e-6);             // rmp2.py:104
+      L.p[VC_INV_REGION] = (float)(1.0 / (double)r[1]);
+      L.p[VC_WEIGHT] = r[3];
+      break;
+    case RMP2_LEAF_JOINT_DAMPING:
+      L.p[JD_GAIN] = r[0];
+      L.p[JD_SCALAR] = r[1];
+      L.p[JD_INERTIA] = r[2];
+      break;
+    case RMP2_LEAF_OBSTACLE_AVOIDANCE:
+      L.p[OA_MARGIN] = r[0];
+      L.p[OA_DGAIN] = r[1];
+      L.p[OA_INV_DSTD] = (float)(1.0 / (double)r[2]);
+      L.p[OA_DEPS] = r[3];
+      L.p[OA_INV_VLEN] = (float)(1.0 / (double)r[4]);
+      L.p[OA_RGAIN] = r[5];
+      L.p[OA_INV_RSTD] = (float)(1.0 / (double)r[6]);
+      L.p[OA_R] = r[7];
+      L.p[OA_INV_R] = (float)(1.0 / (double)r[7]);
+      L.p[OA_MSCALAR] = r[8];
+      L.p[OA_INV_ESTD] = (float)(1.0 / (double)r[9]);
+      L.p[OA_EEPS] = r[10];
+      break;
+    case RMP2_LEAF_CSPACE_BIASING:
+      L.p[CS_METRIC] = (float)((double)r[0] + (double)r[4]);   // rmp2.py:224
+      L.p[CS_PGAIN] = r[1];
+      L.p[CS_DGAIN] = r[2];
+      L.p[CS_THRESH] = r[3];
+      for (int i = 0; i < n; ++i) vec[i] = d.vec[i];
+      *vec_len = n;
+      break;
+    default:
+      return fail(RMP2_ERR_INVALID, "unknown leaf type " + std::to_string(d.type));
+  }
+  return RMP2_OK;
+}
+
+static int check_leaf(const rmp2_leaf_desc& d, int F, int idx) {
+  const std::string at = "leaf " + std::to_string(idx) + ": ";
+  const bool config_leaf = d.type == RMP2_LEAF_CONFIG_BIASING || d.type == RMP2_LEAF_JOINT_LIMIT ||
+                           d.type == RMP2_LEAF_VELOCITY_CAP || d.type == RMP2_LEAF_JOINT_DAMPING ||
+                           d.type == RMP2_LEAF_CSPACE_BIASING;
+  switch (d.space) {
+    case RMP2_SPACE_CONFIG:
+      if (!config_leaf && d.type != RMP2_LEAF_TARGET_POLICY)
+        return fail(RMP2_ERR_UNSUPPORTED, at + "this leaf type is not implemented on the identity task map");
+      if (d.goal_slot >= 0) return fail(RMP2_ERR_UNSUPPORTED, at + "per-environment goals need a frame-position task map");
+      break;
+    case RMP2_SPACE_FRAME_POSITION:
+      if (d.type != RMP2_LEAF_TARGET_POLICY && d.type != RMP2_LEAF_TARGET_ATTRACTOR)
+        return fail(RMP2_ERR_UNSUPPORTED, at + "only TargetPolicy / TargetAttractor live on a frame position");
+      break;
+    case RMP2_SPACE_FRAME_DISTANCE_SPHERES:
+    case RMP2_SPACE_FRAME_DISTANCE_PAIRS:
+      if (d.type != RMP2_LEAF_OBSTACLE_AVOIDANCE)
+        return fail(RMP2_ERR_UNSUPPORTED, at + "only ObstacleAvoidance lives on a distance task map");
+      break;
+    default:
+      return fail(RMP2_ERR_INVALID, at + "unknown space " + std::to_string(d.space));
+  }
+  if (d.space != RMP2_SPACE_CONFIG && (d.frame < 0 || d.frame >= F))
+    return fail(RMP2_ERR_INVALID, at + "frame index out of range");
+  if (d.goal_slot >= RMP2_MAX_GOAL_SLOTS) return fail(RMP2_ERR_INVALID, at + "goal_slot out of range");
+  return RMP2_OK;
+}
+
+// Path base -> frame as a serial table (used by rmp2_fk and as a building block below).
+static void fill_frame(const rmp2_robot& rb, int k, FrameTab& ft) {
+  const float* T = &rb.T_const[(size_t)k * 16];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) ft.R[3 * r + c] = T[4 * r + c];
+    ft.t[r] = T[4 * r + 3];
+    ft.axis[r] = rb.axis[(size_t)k * 3 + r];
+  }
+  ft.type = rb.jtype[k];
+  ft.qidx = (rb.qidx[k] >= 0 && rb.qidx[k] < rb.n && ft.type != RMP2_JOINT_FIXED) ? rb.qidx[k] : -1;
+  ft.restore_slot = -1;
+  ft.save_slot = -1;
+  ft.anc_mask = 0;
+  ft.leaf_begin = ft.leaf_end = 0;
+  ft.ref_index = k;
+}
+
+static uint32_t ancestor_mask(const rmp2_robot& rb, int k) {
+  uint32_t m = 0;
+  for (int i = k; i >= 0; i = rb.parent[i])
+    if (rb.qidx[i] >= 0 && rb.qidx[i] < rb.n && rb.jtype[i] != RMP2_JOINT_FIXED) m |= 1u << rb.qidx[i];
+  return m;
+}
+
+static uint32_t prismatic_mask(const rmp2_robot& rb) {
+  uint32_t m = 0;
+  for (int i = 0; i < rb.F; ++i)
+    if (rb.jtype[i] == RMP2_JOINT_PRISMATIC && rb.qidx[i] >= 0 && rb.qidx[i] < rb.n) m |= 1u << rb.qidx[i];
+  return m;
+}
+
+extern "C" {
+
+const char* rmp2_last_error(void) { return g_last_error.c_str(); }
+const char* rmp2_version(void) { return "rmp2_b200 0.1 (sm_100a)"; }
+int64_t rmp2_launch_count(void) { return g_launches.load(); }
+
+int rmp2_robot_create(const float* T_const, const float* axis, const int8_t* jtype, const int32_t* parent,
+                      const int32_t* qidx, int32_t F, int32_t n, rmp2_robot** out) {
+  if (!T_const || !axis || !jtype || !parent || !qidx || !out) return fail(RMP2_ERR_INVALID, "null argument");
+  if (F <= 0 || F > RMP2_MAX_FRAMES) return fail(RMP2_ERR_UNSUPPORTED, "frame count must be in 1.." + std::to_string(RMP2_MAX_FRAMES));
+  if (n <= 0 || n > RMP2_MAX_JOINTS) return fail(RMP2_ERR_UNSUPPORTED, "joint count must be in 1.." + std::to_string(RMP2_MAX_JOINTS));
+  for (int k = 0; k < F; ++k) {
+    if (parent[k] >= k || parent[k] < -1) return fail(RMP2_ERR_INVALID, "parent[" + std::to_string(k) + "] must be -1 or an earlier frame");
+    if (jtype[k] < 0 || jtype[k] > 2) return fail(RMP2_ERR_INVALID, "jtype[" + std::to_string(k) + "] unknown");
+    if (jtype[k] == RMP2_JOINT_REVOLUTE) {
+      const float* a = axis + 3 * k;
+      const double len = sqrt((double)a[0] * a[0] + (double)a[1] * a[1] + (double)a[2] * a[2]);
+      if (fabs(len - 1.0) > 1e-4)
+        return fail(RMP2_ERR_UNSUPPORTED, "revolute axis of frame " + std::to_string(k) + " is not unit length");
+    }
+    if (qidx[k] >= n) return fail(RMP2_ERR_INVALID, "qidx[" + std::to_string(k) + "] out of range");
+  }
+  rmp2_robot* rb = new rmp2_robot;
+  rb->F = F;
+  rb->n = n;
+  rb->T_const.assign(T_const, T_const + (size_t)F * 16);
+  rb->axis.assign(axis, axis + (size_t)F * 3);
+  rb->jtype.assign(jtype, jtype + F);
+  rb->parent.assign(parent, parent + F);
+  rb->qidx.assign(qidx, qidx + F);
+  *out = rb;
+  return RMP2_OK;
+}
+
+void rmp2_robot_destroy(rmp2_robot* robot) { delete robot; }
+
+int rmp2_tree_create(const rmp2_robot* rb, const rmp2_leaf_desc* leaves, int32_t n_leaves, rmp2_tree** out) {
+  if (!rb || !out || (n_leaves > 0 && !leaves)) return fail(RMP2_ERR_INVALID, "null argument");
+  if (n_leaves < 0 || n_leaves > RMP2_MAX_LEAVES)
+    return fail(RMP2_ERR_UNSUPPORTED, "at most " + std::to_string(RMP2_MAX_LEAVES) + " leaves per tree");
+  for (int i = 0; i < n_leaves; ++i) {
+    int rc = check_leaf(leaves[i], rb->F, i);
+    if (rc != RMP2_OK) return rc;
+  }
+  rmp2_tree* tr = new rmp2_tree;
+  memset(&tr->tab, 0, sizeof(StepTables));
+  StepTables& T = tr->tab;
+  T.n = rb->n;
+  T.rcond = (float)(10.0 * rb->n * 1.1920928955078125e-07);   // 10 * max(rows, cols) * eps(float32)
+  T.prismatic_mask = prismatic_mask(*rb);
+  tr->leaves.assign(leaves, leaves + n_leaves);
+  tr->table_index.assign(n_leaves, -1);
+
+  // frames that carry a leaf, and everything between them and the base
+  std::vector<char> needed(rb->F, 0);
+  for (int i = 0; i < n_leaves; ++i)
+    if (leaves[i].space != RMP2_SPACE_CONFIG)
+      for (int k = leaves[i].frame; k >= 0; k = rb->parent[k]) needed[k] = 1;
+  std::vector<std::vector<int>> children(rb->F + 1);          // index F = base
+  for (int k = 0; k < rb->F; ++k)
+    if (needed[k]) children[rb->parent[k] < 0 ? rb->F : rb->parent[k]].push_back(k);
+
+  // leaf bookkeeping shared by frame-attached and configuration-space leaves
+  int leaf_cursor = 0, pair_sets = 0, goal_slots = 0, vec_cursor = 0;
+  std::vector<int> pair_set_of(n_leaves, -1);
+  for (int i = 0; i < n_leaves; ++i) {
+    if (leaves[i].space == RMP2_SPACE_FRAME_DISTANCE_PAIRS) pair_set_of[i] = pair_sets++;
+    if (leaves[i].goal_slot >= 0) goal_slots = std::max(goal_slots, leaves[i].goal_slot + 1);
+    if (leaves[i].space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) T.uses_spheres = 1;
+  }
+  if (pair_sets > RMP2_MAX_PAIR_SETS) { delete tr; return fail(RMP2_ERR_UNSUPPORTED, "too many explicit-pair leaves"); }
+  tr->n_pair_sets = pair_sets;
+  tr->n_goal_slots_used = goal_slots;
+  auto add_leaf = [&](int i) -> int {
+    LeafTab& L = T.leaves[leaf_cursor];
+    L.type = leaves[i].type;
+    L.space = leaves[i].space;
+    L.goal_slot = leaves[i].goal_slot;
+    L.pair_set = pair_set_of[i];
+    float vec[3 * RMP2_MAX_JOINTS];
+    int vlen = 0;
+    int rc = derive_leaf_params(leaves[i], rb->n, L, vec, &vlen);
+    if (rc != RMP2_OK) return rc;
+    if (vec_cursor + vlen > RMP2_VECPOOL) return fail(RMP2_ERR_UNSUPPORTED, "vector-parameter pool exhausted");
+    L.vec_off = vec_cursor;
+    for (int j = 0; j < vlen; ++j) T.vecpool[vec_cursor + j] = vec[j];
+    vec_cursor += vlen;
+    tr->table_index[i] = leaf_cursor++;
+    return RMP2_OK;
+  };
+
+  // depth-first execution order.  A frame with several needed children saves its chain state in
+  // slot `depth` (stack discipline: its descendants only use deeper slots); the first child
+  // continues from the live state, later children reload the slot.
+  int n_slots = 0;
+  std::function<int(int, int, int)> visit = [&](int k, int restore, int depth) -> int {
+    if (T.n_frames >= RMP2_MAX_FRAMES) return fail(RMP2_ERR_UNSUPPORTED, "too many frames");
+    FrameTab& ft = T.frames[T.n_frames++];
+    fill_frame(*rb, k, ft);
+    ft.anc_mask = ancestor_mask(*rb, k);
+    ft.restore_slot = restore;
+    ft.leaf_begin = leaf_cursor;
+    for (int i = 0; i < n_leaves; ++i)
+      if (leaves[i].space != RMP2_SPACE_CONFIG && leaves[i].frame == k) {
+        int rc = add_leaf(i);
+        if (rc != RMP2_OK) return rc;
+      }
+    ft.leaf_end = leaf_cursor;
+    const std::vector<int>& ch = children[k];
+    if (ch.size() > 1) {
+      if (depth >= RMP2_MAX_SLOTS) return fail(RMP2_ERR_UNSUPPORTED, "kinematic tree branches too deeply");
+      ft.save_slot = depth;
+      n_slots = std::max(n_slots, depth + 1);
+      for (size_t ci = 0; ci < ch.size(); ++ci) {
+        int rc = visit(ch[ci], ci == 0 ? -1 : depth, depth + 1);
+        if (rc != RMP2_OK) return rc;
+      }
+    } else if (ch.size() == 1) {
+      return visit(ch[0], -1, depth);
+    }
+    return RMP2_OK;
+  };
+  for (int k : children[rb->F]) {
+    int rc = visit(k, RMP2_SLOT_BASE, 0);
+    if (rc != RMP2_OK) { delete tr; return rc; }
+  }
+  T.n_slots = n_slots;
+  T.n_frame_leaves = leaf_cursor;
+  for (int i = 0; i < n_leaves; ++i)
+    if (leaves[i].space == RMP2_SPACE_CONFIG) {
+      int rc = add_leaf(i);
+      if (rc != RMP2_OK) { delete tr; return rc; }
+    }
+  T.n_leaves = leaf_cursor;
+  *out = tr;
+  return RMP2_OK;
+}
+
+void rmp2_tree_destroy(rmp2_tree* tree) {
+  if (!tree) return;
+  for (auto& s : tree->stage) {
+    if (s.buf) cudaFree(s.buf);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  delete tree;
+}
+
+int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* leaf) {
+  if (!tree || !leaf) return fail(RMP2_ERR_INVALID, "null argument");
+  if (index < 0 || index >= (int)tree->leaves.size()) return fail(RMP2_ERR_INVALID, "leaf index out of range");
+  const rmp2_leaf_desc& old = tree->leaves[index];
+  if (old.type != leaf->type || old.space != leaf->space || old.frame != leaf->frame || old.goal_slot != leaf->goal_slot)
+    return fail(RMP2_ERR_INVALID, "update_leaf may change params/vec only; rebuild the tree to change its structure");
+  LeafTab& L = tree->tab.leaves[tree->table_index[index]];
+  float vec[3 * RMP2_MAX_JOINTS];
+  int vlen = 0;
+  int rc = derive_leaf_params(*leaf, tree->tab.n, L, vec, &vlen);
+  if (rc != RMP2_OK) return rc;
+  for (int j = 0; j < vlen; ++j) tree->tab.vecpool[L.vec_off + j] = vec[j];
+  tree->leaves[index] = *leaf;
+  return RMP2_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------ step launch
+namespace {
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (PFN_tmapEncodeTiled)p;
+  }();
+  return fn;
+}
+
+struct LaunchPlan {
+  bool use_tma = false;
+  int block = RMP2_BLOCK_THREADS;
+  size_t smem = 0;
+  CUtensorMap tmap;
+};
+
+int plan_step(const StepTables& T, const StepArgs& A, LaunchPlan& P) {
+  memset(&P.tmap, 0, sizeof(P.tmap));
+  const long long B = A.B;
+  P.block = (B >= 148LL * 4 * 128) ? 128 : (B >= 148LL * 4 * 64 ? 64 : 32);
+  const int O = A.n_spheres;
+  P.use_tma = T.uses_spheres && O > 0 && (O % 8) == 0 && A.spheres != nullptr &&
+              ((uintptr_t)A.spheres % 16) == 0 && B < (1LL << 31);
+  if (getenv("RMP2_DISABLE_TMA")) P.use_tma = false;
+  if (P.use_tma) {
+    PFN_tmapEncodeTiled enc = get_encode_fn();
+    if (!enc) return fail(RMP2_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const cuuint64_t gdim[2] = {(cuuint64_t)O * 4, (cuuint64_t)B};
+    const cuuint64_t gstride[1] = {(cuuint64_t)O * 16};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estride[2] = {1, 1};
+    CUresult r = enc(&P.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A.spheres), gdim, gstride, box,
+                     estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RMP2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  }
+  const int warps = P.block / 32;
+  const int boxes = P.use_tma ? std::min(4, (O + 7) / 8) : 0;
+  P.smem = 1024 + (size_t)warps * boxes * 4096 + (size_t)warps * 8 +
+           (size_t)T.n_slots * RMP2_CHAIN_FLOATS * P.block * sizeof(float);
+  return RMP2_OK;
+}
+
+int build_args(const rmp2_tree* tree, const rmp2_step_io* io, StepArgs& A) {
+  if (!tree || !io) return fail(RMP2_ERR_INVALID, "null argument");
+  if (io->B < 0) return fail(RMP2_ERR_INVALID, "B must be >= 0");
+  if (io->B > 0 && (!io->q || !io->qd || !io->qdd)) return fail(RMP2_ERR_INVALID, "q, qd and qdd are required");
+  memset(&A, 0, sizeof(A));
+  A.B = io->B;
+  A.q = io->q;
+  A.qd = io->qd;
+  A.qdd = io->qdd;
+  A.goals = io->goals;
+  A.n_goal_slots = io->n_goal_slots;
+  A.spheres = io->spheres;
+  A.n_spheres = io->spheres ? io->n_spheres : 0;
+  A.pairs = io->pairs;
+  if (tree->n_goal_slots_used > 0 && (!io->goals || io->n_goal_slots < tree->n_goal_slots_used))
+    return fail(RMP2_ERR_INVALID, "tree has per-environment goals: io.goals with n_goal_slots >= " +
+                                      std::to_string(tree->n_goal_slots_used) + " is required");
+  if (tree->tab.uses_spheres && io->n_spheres > 0 && !io->spheres)
+    return fail(RMP2_ERR_INVALID, "n_spheres > 0 but spheres is NULL");
+  if (io->n_spheres < 0) return fail(RMP2_ERR_INVALID, "n_spheres must be >= 0");
+  if (io->n_pair_sets != tree->n_pair_sets)
+    return fail(RMP2_ERR_INVALID, "io.n_pair_sets (" + std::to_string(io->n_pair_sets) + ") != explicit-pair leaves of the tree (" +
+                                      std::to_string(tree->n_pair_sets) + ")");
+  int total = 0;
+  for (int i = 0; i < tree->n_pair_sets; ++i) {
+    if (io->pair_counts[i] < 0) return fail(RMP2_ERR_INVALID, "negative pair count");
+    A.pair_off[i] = total;
+    total += io->pair_counts[i];
+  }
+  A.pair_off[tree->n_pair_sets] = total;
+  A.pair_total = total;
+  if (total > 0 && !io->pairs) return fail(RMP2_ERR_INVALID, "pair counts > 0 but pairs is NULL");
+  return RMP2_OK;
+}
+
+int launch(const rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
+  if (A.B == 0) return RMP2_OK;
+  LaunchPlan P;
+  int rc = plan_step(tree->tab, A, P);
+  if (rc != RMP2_OK) return rc;
+  cudaError_t e = rmp2_launch_step(tree->tab, A, &P.tmap, P.use_tma, P.block, P.smem, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "rmp2_step launch");
+  g_launches.fetch_add(1);
+  return RMP2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rmp2_step(const rmp2_tree* tree, const rmp2_step_io* io, void* stream) {
+  StepArgs A;
+  int rc = build_args(tree, io, A);
+  if (rc != RMP2_OK) return rc;
+  return launch(tree, A, (cudaStream_t)stream);
+}
+
+int rmp2_rollout(const rmp2_tree* tree, const rmp2_step_io* io, float* q_inout, float* qd_inout, float dt,
+                 int32_t n_steps, int32_t control_every, void* stream) {
+  if (!q_inout || !qd_inout) return fail(RMP2_ERR_INVALID, "q_inout and qd_inout are required");
+  if (n_steps <= 0 || control_every <= 0) return fail(RMP2_ERR_INVALID, "n_steps and control_every must be positive");
+  rmp2_step_io tmp = *io;
+  tmp.q = q_inout;
+  tmp.qd = qd_inout;
+  StepArgs A;
+  int rc = build_args(tree, &tmp, A);
+  if (rc != RMP2_OK) return rc;
+  A.q_rw = q_inout;
+  A.qd_rw = qd_inout;
+  A.dt = dt;
+  A.n_sim_steps = n_steps;
+  A.control_every = control_every;
+  return launch(tree, A, (cudaStream_t)stream);
+}
+
+int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io) {
+  StepArgs A0;
+  int rc = build_args(tree, io, A0);
+  if (rc != RMP2_OK) return rc;
+  const long long B = io->B;
+  if (B == 0) return RMP2_OK;
+  const int n = tree->tab.n;
+  const int G = io->goals ? io->n_goal_slots : 0;
+  const int O = A0.n_spheres;
+  const int K = A0.pair_total;
+  // floats per environment, each section padded to 4 floats so every section stays 16-byte aligned
+  auto pad4 = [](size_t v) { return (v + 3) & ~size_t(3); };
+  const long long chunk = std::min<long long>(B, 65536);
+  const size_t off_q = 0;
+  const size_t off_qd = off_q + pad4((size_t)chunk * n);
+  const size_t off_qdd = off_qd + pad4((size_t)chunk * n);
+  const size_t off_goal = off_qdd + pad4((size_t)chunk * n);
+  const size_t off_sph = off_goal + pad4((size_t)chunk * G * 3);
+  const size_t off_pair = off_sph + pad4((size_t)chunk * O * 4);
+  const size_t total = off_pair + pad4((size_t)chunk * K * 6);
+  for (auto& s : tree->stage) {
+    if (!s.stream) {
+      cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreate");
+    }
+    if (s.floats < total) {
+      if (s.buf) cudaFree(s.buf);
+      s.buf = nullptr;
+      s.floats = 0;
+      cudaError_t e = cudaMalloc(&s.buf, total * sizeof(float));
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc staging");
+      s.floats = total;
+    }
+  }
+  int slot = 0;
+  for (long long e0 = 0; e0 < B; e0 += chunk, slot = (slot + 1) % 3) {
+    const long long cb = std::min(chunk, B - e0);
+    HostStage& s = tree->stage[slot];
+    cudaError_t e;
+#define RMP2_H2D(dst, src, count)                                                                         \
+  if ((count) > 0) {                                                                                       \
+    e = cudaMemcpyAsync(s.buf + (dst), (src), (size_t)(count) * sizeof(float), cudaMemcpyHostToDevice, s.stream); \
+    if (e != cudaSuccess) return cuda_fail(e, "H2D copy");                                                  \
+  }
+    RMP2_H2D(off_q, io->q + e0 * n, cb * n);
+    RMP2_H2D(off_qd, io->qd + e0 * n, cb * n);
+    RMP2_H2D(off_goal, io->goals ? io->goals + e0 * G * 3 : nullptr, cb * G * 3);
+    RMP2_H2D(off_sph, io->spheres ? io->spheres + e0 * O * 4 : nullptr, cb * O * 4);
+    RMP2_H2D(off_pair, io->pairs ? io->pairs + e0 * K * 6 : nullptr, cb * K * 6);
+#undef RMP2_H2D
+    StepArgs A = A0;
+    A.B = cb;
+    A.q = s.buf + off_q;
+    A.qd = s.buf + off_qd;
+    A.qdd = s.buf + off_qdd;
+    A.goals = G ? s.buf + off_goal : nullptr;
+    A.spheres = O ? s.buf + off_sph : nullptr;
+    A.pairs = K ? s.buf + off_pair : nullptr;
+    rc = launch(tree, A, s.stream);
+    if (rc != RMP2_OK) return rc;
+    e = cudaMemcpyAsync(io->qdd + e0 * n, s.buf + off_qdd, (size_t)cb * n * sizeof(float), cudaMemcpyDeviceToHost, s.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "D2H copy");
+  }
+  for (auto& s : tree->stage) {
+    cudaError_t e = cudaStreamSynchronize(s.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "rmp2_step_host");
+  }
+  return RMP2_OK;
+}
+
+int rmp2_fk(const rmp2_robot* rb, int32_t frame, int64_t B, const float* q, const float* qd, float* x, float* xd,
+            float* J, float* c, void* stream) {
+  if (!rb || !q || !x) return fail(RMP2_ERR_INVALID, "robot, q and x are required");
+  if (frame < 0 || frame >= rb->F) return fail(RMP2_ERR_INVALID, "frame index out of range");
+  if ((xd || c) && !qd) return fail(RMP2_ERR_INVALID, "xd / c need qd");
+  if (B <= 0) return B == 0 ? RMP2_OK : fail(RMP2_ERR_INVALID, "B must be >= 0");
+  StepTables T;
+  memset(&T, 0, sizeof(T));
+  T.n = rb->n;
+  T.prismatic_mask = prismatic_mask(*rb);
+  std::vector<int> path;
+  for (int k = frame; k >= 0; k = rb->parent[k]) path.push_back(k);
+  std::reverse(path.begin(), path.end());
+  for (int k : path) {
+    FrameTab& ft = T.frames[T.n_frames++];
+    fill_frame(*rb, k, ft);
+    ft.anc_mask = ancestor_mask(*rb, k);
+  }
+  cudaError_t e = rmp2_launch_fk(T, B, q, qd, x, xd, J, c, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "rmp2_fk launch");
+  g_launches.fetch_add(1);
+  return RMP2_OK;
+}
+
+int rmp2_leaf_evaluate(const rmp2_leaf_desc* leaf, int32_t m, int64_t K, const float* x, const float* xd, float* xdd,
+                       float* M, void* stream) {
+  if (!leaf || !x || !xd || !xdd || !M) return fail(RMP2_ERR_INVALID, "null argument");
+  if (m <= 0 || m > RMP2_MAX_JOINTS) return fail(RMP2_ERR_INVALID, "task dimension out of range");
+  if (K <= 0) return K == 0 ? RMP2_OK : fail(RMP2_ERR_INVALID, "K must be >= 0");
+  if (leaf->type == RMP2_LEAF_OBSTACLE_AVOIDANCE && m != 1) return fail(RMP2_ERR_INVALID, "ObstacleAvoidance is one-dimensional");
+  if (leaf->type == RMP2_LEAF_TARGET_ATTRACTOR && m != 3) return fail(RMP2_ERR_INVALID, "TargetAttractor is three-dimensional here");
+  LeafTab L;
+  LeafVec V;
+  memset(&L, 0, sizeof(L));
+  memset(&V, 0, sizeof(V));
+  L.type = leaf->type;
+  L.space = leaf->space;
+  rmp2_leaf_desc d = *leaf;
+  d.space = RMP2_SPACE_CONFIG;                    // vec length follows m
+  int vlen = 0;
+  int rc = derive_leaf_params(d, m, L, V.v, &vlen);
+  if (rc != RMP2_OK) return rc;
+  cudaError_t e = rmp2_launch_leaf(L, V, m, K, x, xd, xdd, M, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "rmp2_leaf_evaluate launch");
+  g_launches.fetch_add(1);
+  return RMP2_OK;
+}
+
+int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t* regs, int32_t* smem_bytes, int32_t* blocks_per_sm,
+                          int32_t* block_threads) {
+  if (!tree) return fail(RMP2_ERR_INVALID, "null argument");
+  StepArgs A;
+  memset(&A, 0, sizeof(A));
+  A.B = 1 << 20;
+  A.n_spheres = tree->tab.uses_spheres ? 64 : 0;
+  const bool use_tma = tree->tab.uses_spheres != 0;
+  const int block = RMP2_BLOCK_THREADS;
+  const int warps = block / 32;
+  const size_t smem = 1024 + (size_t)warps * (use_tma ? 4 : 0) * 4096 + (size_t)warps * 8 +
+                      (size_t)tree->tab.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
+  int r = 0, ss = 0, bps = 0;
+  cudaError_t e = rmp2_step_attributes(tree->tab.n, use_tma, block, smem, &r, &ss, &bps);
+  if (e != cudaSuccess) return cuda_fail(e, "rmp2_tree_kernel_info");
+  if (regs) *regs = r;
+  if (smem_bytes) *smem_bytes = (int)smem + ss;
+  if (blocks_per_sm) *blocks_per_sm = bps;
+  if (block_threads) *block_threads = block;
+  return RMP2_OK;
+}
+
+}  // extern "C"

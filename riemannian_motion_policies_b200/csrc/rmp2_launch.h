@@ -1,0 +1,23 @@
+// Host-callable launchers implemented in rmp2_kernels.cu, used by the C ABI in rmp2_api.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "rmp2_tables.h"
+
+#define RMP2_BLOCK_THREADS 128
+
+struct LeafVec {
+  float v[3 * RMP2_MAX_JOINTS];
+};
+
+int rmp2_pick_width(int n);
+
+cudaError_t rmp2_launch_step(const StepTables& T, const StepArgs& A, const CUtensorMap* tmap, bool use_tma,
+                             int block, size_t smem, cudaStream_t stream);
+cudaError_t rmp2_step_attributes(int n, bool use_tma, int block, size_t smem, int* regs, int* static_smem,
+                                 int* blocks_per_sm);
+cudaError_t rmp2_launch_fk(const StepTables& T, long long B, const float* q, const float* qd, float* x, float* xd,
+                           float* J, float* c, cudaStream_t stream);
+cudaError_t rmp2_launch_leaf(const LeafTab& L, const LeafVec& V, int m, long long K, const float* x, const float* xd,
+                             float* xdd, float* M, cudaStream_t stream);

@@ -1,0 +1,271 @@
+// Leaf policies as device functions (float32).  Each cites the reference lines it restates.
+// The derived parameter layout p[] is produced on the host by derive_leaf_params()
+// (rmp2_api.cu) from the raw constructor arguments documented in include/rmp2_b200.h.
+#pragma once
+#include "rmp2_tables.h"
+
+#define RMP2_DEV __device__ __forceinline__
+
+// ---- derived parameter slots ------------------------------------------------------------------
+// TARGET_POLICY
+#define TP_ALPHA 0
+#define TP_BETA 1
+#define TP_C 2
+#define TP_INV_C 3
+// CONFIG_BIASING
+#define CB_GAMMA_P 0
+#define CB_GAMMA_D 1
+#define CB_W 2
+// JOINT_LIMIT   (vecpool: lower[n], upper[n], 1/(upper-lower)[n])
+#define JL_GAMMA_P 0
+#define JL_GAMMA_D 1
+#define JL_C3 2
+#define JL_C2 3
+#define JL_R 4
+#define JL_INV_QDMAX 5
+#define JL_BETA 6
+#define JL_C 7
+#define JL_INV_C 8
+// TARGET_ATTRACTOR
+#define TA_PGAIN 0
+#define TA_DGAIN 1
+#define TA_EPS 2
+#define TA_EPS10 3
+#define TA_INV_ALEN 4
+#define TA_MIN_ALPHA 5
+#define TA_SMAX 6
+#define TA_SMIN 7
+#define TA_BOOST 8
+#define TA_INV_BLEN 9
+// VELOCITY_CAP
+#define VC_CUTOFF 0
+#define VC_GAIN 1
+#define VC_CLIP 2
+#define VC_INV_REGION 3
+#define VC_WEIGHT 4
+// JOINT_DAMPING
+#define JD_GAIN 0
+#define JD_SCALAR 1
+#define JD_INERTIA 2
+// OBSTACLE_AVOIDANCE
+#define OA_MARGIN 0
+#define OA_R 1
+#define OA_INV_R 2
+#define OA_MSCALAR 3
+#define OA_INV_ESTD 4
+#define OA_EEPS 5
+#define OA_RGAIN 6
+#define OA_INV_RSTD 7
+#define OA_INV_VLEN 8
+#define OA_DGAIN 9
+#define OA_INV_DSTD 10
+#define OA_DEPS 11
+// CSPACE_BIASING
+#define CS_METRIC 0
+#define CS_PGAIN 1
+#define CS_DGAIN 2
+#define CS_THRESH 3
+
+// log(1 + exp(-y)) for y >= 0
+RMP2_DEV float softplus_neg(float y) { return log1pf(expf(-y)); }
+
+// ---- metrics of the form  A = iso * I + dir * zeta zeta^T  ----------------------------------------
+// TargetPolicy  (reference: rmp.py:241-260, helper/rmp_helper.py:62-74)
+template <int D>
+RMP2_DEV void target_policy(const float* __restrict__ p, const float (&x)[D], const float (&xd)[D],
+                            const float (&goal)[D], int dim, float (&xdd)[D], float (&zeta)[D],
+                            float& iso, float& dir) {
+  float v[D];
+  float nv2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    v[i] = (i < dim) ? goal[i] - x[i] : 0.f;
+    nv2 = fmaf(v[i], v[i], nv2);
+  }
+  const float nv = sqrtf(nv2);                                           // tf.norm(v)   rmp.py:243
+  const float c = p[TP_C];
+  const float h = nv + c * log1pf(expf(-2.f * c * nv));                  // c*log(...)   rmp.py:244
+  const float inv_h = 1.f / h;
+  float nx2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    xdd[i] = (i < dim) ? p[TP_ALPHA] * (inv_h * v[i]) - p[TP_BETA] * xd[i] : 0.f;   // rmp.py:245-246
+    nx2 = fmaf(xdd[i], xdd[i], nx2);
+  }
+  const float beta = 1.f - expf(-0.5f * nv2);                            // sigma_H = 1  rmp.py:253
+  const float nx = sqrtf(nx2);
+  const float hh = nx + p[TP_INV_C] * log1pf(expf(-2.f * c * nx));       // soft_norm    rmp_helper.py:64
+  const float inv_hh = 1.f / hh;
+#pragma unroll
+  for (int i = 0; i < D; ++i) zeta[i] = xdd[i] * inv_hh;
+  const float w = expf(-nv * (1.f / 3.f));                               // sigma_w = 3  rmp.py:257
+  iso = w * (1.f - beta);
+  dir = w * beta;
+}
+
+// TargetAttractor  (reference: rmp2.py:52-83)
+RMP2_DEV void target_attractor(const float* __restrict__ p, const float (&x)[3], const float (&xd)[3],
+                               const float (&goal)[3], float (&xdd)[3], float (&zeta)[3], float& iso,
+                               float& dir) {
+  float d[3];
+  float dn2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    d[i] = goal[i] - x[i];
+    dn2 = fmaf(d[i], d[i], dn2);
+  }
+  const float dn = sqrtf(dn2);
+  const float inv_soft = 1.f / fmaxf(dn, p[TA_EPS10]);                   // rmp2.py:68-69
+  const float inv_acc = 1.f / (dn + p[TA_EPS]);                          // rmp2.py:58
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    xdd[i] = p[TA_PGAIN] * d[i] * inv_acc - p[TA_DGAIN] * xd[i];
+    zeta[i] = d[i] * inv_soft;
+  }
+  const float sd = dn * p[TA_INV_ALEN];
+  const float a = (1.f - p[TA_MIN_ALPHA]) * expf(-0.5f * sd * sd) + p[TA_MIN_ALPHA];   // rmp2.py:74
+  const float bd = dn * p[TA_INV_BLEN];
+  const float ba = expf(-0.5f * bd * bd);                                               // rmp2.py:79
+  const float boost = ba * p[TA_BOOST] + (1.f - ba);                                    // rmp2.py:80
+  iso = boost * (a * p[TA_SMAX]);                                                       // rmp2.py:76,82
+  dir = boost * ((1.f - a) * p[TA_SMIN]);
+}
+
+// ---- ObstacleAvoidance on one closest-point pair --------------------------------------------------
+// n = unit vector obstacle -> link, d = distance (the task coordinate x of the reference),
+// inv_d = 1/d.  v, a = velocity and Jdot*qd of the frame origin, vv = |v|^2.
+// Distance map (reference: taskmap.py:120-138 via autodiff): xdot = n.v,
+// c = n.a + (|v|^2 - xdot^2)/d.  Leaf (reference: rmp2.py:184-196).
+// Accumulates S += M n n^T (xx, xy, xz, yy, yz, zz) and g += M (xdd - c) n, which is the
+// per-pair pullback of rmp.py:165-167 onto the frame origin.
+RMP2_DEV void obstacle_pair(const float* __restrict__ p, float nx, float ny, float nz, float d,
+                            float inv_d, const float (&v)[3], const float (&a)[3], float vv,
+                            float (&S)[6], float (&g)[3]) {
+  const float xdot = fmaf(nx, v[0], fmaf(ny, v[1], nz * v[2]));
+  const float curv = fmaf(-xdot, xdot, vv) * inv_d;
+  const float c = fmaf(nx, a[0], fmaf(ny, a[1], fmaf(nz, a[2], curv)));
+  const float x = fmaxf(d - p[OA_MARGIN], 0.f);                          // rmp2.py:185-186
+  const float base = p[OA_MSCALAR] / fmaf(x, p[OA_INV_ESTD], p[OA_EEPS]);   // rmp2.py:187
+  const float gt = fmaf(x, p[OA_INV_R], -1.f);
+  const float gate = gt * gt;                                            // rmp2.py:172
+  const float rep = p[OA_RGAIN] * expf(-x * p[OA_INV_RSTD]);             // rmp2.py:189
+  const float one_minus_sig = 1.f / (1.f + expf(xdot * p[OA_INV_VLEN])); // 1 - sigmoid  rmp2.py:190
+  const float damp = -one_minus_sig * p[OA_DGAIN] * xdot / fmaf(x, p[OA_INV_DSTD], p[OA_DEPS]);  // :191
+  const float acc = rep + damp;
+  const float m = (x > p[OA_R]) ? 0.f : one_minus_sig * base * gate;     // rmp2.py:194
+  const float h = m * (acc - c);
+  const float mx = m * nx, my = m * ny, mz = m * nz;
+  S[0] = fmaf(mx, nx, S[0]);
+  S[1] = fmaf(mx, ny, S[1]);
+  S[2] = fmaf(mx, nz, S[2]);
+  S[3] = fmaf(my, ny, S[3]);
+  S[4] = fmaf(my, nz, S[4]);
+  S[5] = fmaf(mz, nz, S[5]);
+  g[0] = fmaf(h, nx, g[0]);
+  g[1] = fmaf(h, ny, g[1]);
+  g[2] = fmaf(h, nz, g[2]);
+}
+
+// scalar form used by rmp2_leaf_evaluate: x, xd -> xdd, M
+RMP2_DEV void obstacle_scalar(const float* __restrict__ p, float xin, float xdot, float& xdd, float& M) {
+  const float x = fmaxf(xin - p[OA_MARGIN], 0.f);
+  const float base = p[OA_MSCALAR] / fmaf(x, p[OA_INV_ESTD], p[OA_EEPS]);
+  const float gt = fmaf(x, p[OA_INV_R], -1.f);
+  const float rep = p[OA_RGAIN] * expf(-x * p[OA_INV_RSTD]);
+  const float one_minus_sig = 1.f / (1.f + expf(xdot * p[OA_INV_VLEN]));
+  const float damp = -one_minus_sig * p[OA_DGAIN] * xdot / fmaf(x, p[OA_INV_DSTD], p[OA_DEPS]);
+  xdd = rep + damp;
+  M = (x > p[OA_R]) ? 0.f : one_minus_sig * base * (gt * gt);
+}
+
+// ---- configuration-space leaves: add A into the full matrix M and A*xdd into f ---------------------
+// All take q, qd (first n entries valid), M row-major [N][N], f [N].
+template <int N>
+RMP2_DEV void leaf_config_biasing(const float* __restrict__ p, const float* __restrict__ q0, int n,
+                                  const float (&q)[N], const float (&qd)[N], float (&xdd)[N], float& m) {
+  // reference: rmp.py:330-347
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    xdd[i] = (i < n) ? p[CB_GAMMA_P] * (q0[i] - q[i]) - p[CB_GAMMA_D] * qd[i] : 0.f;
+  m = p[CB_W];
+}
+
+template <int N>
+RMP2_DEV void leaf_joint_damping(const float* __restrict__ p, int n, const float (&qd)[N], float (&xdd)[N],
+                                 float& m) {
+  // reference: rmp2.py:127-137
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) s = fmaf(qd[i], qd[i], s);     // entries >= n are zero
+  const float nq = sqrtf(s);
+  const float gain = p[JD_GAIN] * nq;
+#pragma unroll
+  for (int i = 0; i < N; ++i) xdd[i] = -gain * qd[i];
+  m = fmaf(p[JD_SCALAR], nq, p[JD_INERTIA]);
+}
+
+template <int N>
+RMP2_DEV void leaf_cspace_biasing(const float* __restrict__ p, const float* __restrict__ goal, int n,
+                                  const float (&q)[N], const float (&qd)[N], float (&xdd)[N], float& m) {
+  // reference: rmp2.py:212-226
+  float e[N];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    e[i] = (i < n) ? q[i] - goal[i] : 0.f;
+    s = fmaf(e[i], e[i], s);
+  }
+  const float ne = sqrtf(s);
+  const bool near = ne < p[CS_THRESH];
+  const float scale = near ? -p[CS_PGAIN] : -p[CS_THRESH] * p[CS_PGAIN] / ne;
+#pragma unroll
+  for (int i = 0; i < N; ++i) xdd[i] = fmaf(scale, e[i], -p[CS_DGAIN] * qd[i]);
+  m = p[CS_METRIC];
+}
+
+// JointVelocityCap: A_ii = w / (1 - ratio_i^2), A_ij = w  (reference: rmp2.py:100-112)
+template <int N>
+RMP2_DEV void leaf_velocity_cap(const float* __restrict__ p, int n, const float (&qd)[N], float (&xdd)[N],
+                                float (&diag)[N], float& w) {
+  w = p[VC_WEIGHT];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float av = fabsf(qd[i]);
+    const float dv = av - p[VC_CUTOFF];
+    const float sgn = (qd[i] > 0.f) ? 1.f : ((qd[i] < 0.f) ? -1.f : 0.f);
+    const float acc = -fabsf(p[VC_GAIN] * dv) * sgn;
+    xdd[i] = (i < n && !(av < p[VC_CUTOFF])) ? acc : 0.f;
+    const float ratio = fminf(dv, p[VC_CLIP]) * p[VC_INV_REGION];
+    diag[i] = (i < n) ? w / (1.f - ratio * ratio) : 0.f;
+  }
+}
+
+// JointLimitAvoidance: A = (beta zeta zeta^T + (1-beta) I) diag(w)  (reference: rmp.py:357-382)
+template <int N>
+RMP2_DEV void leaf_joint_limit(const float* __restrict__ p, const float* __restrict__ vec, int n,
+                               const float (&q)[N], const float (&qd)[N], float (&xdd)[N], float (&zeta)[N],
+                               float (&w)[N]) {
+  float s = 0.f;
+  float vv[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    if (i < n) {
+      const float lo = vec[i], up = vec[n + i], inv_range = vec[2 * n + i];
+      const float d = fminf((up - q[i]) * inv_range, (q[i] - lo) * inv_range);
+      const float spline = fmaf(p[JL_C3] * d, d * d, fmaf(p[JL_C2] * d, d, 1.f));
+      w[i] = (d > p[JL_R]) ? 0.f : spline;
+      vv[i] = qd[i] * p[JL_INV_QDMAX];
+      xdd[i] = -p[JL_GAMMA_P] * q[i] - p[JL_GAMMA_D] * qd[i];
+    } else {
+      w[i] = 0.f;
+      vv[i] = 0.f;
+      xdd[i] = 0.f;
+    }
+    s = fmaf(vv[i], vv[i], s);
+  }
+  const float nv = sqrtf(s);
+  const float hh = nv + p[JL_INV_C] * log1pf(expf(-2.f * p[JL_C] * nv));
+  const float inv_hh = 1.f / hh;
+#pragma unroll
+  for (int i = 0; i < N; ++i) zeta[i] = vv[i] * inv_hh;
+}

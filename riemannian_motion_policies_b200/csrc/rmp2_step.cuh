@@ -1,0 +1,217 @@
+// Per-environment device code of the control step: kinematic chain recursion with analytic
+// velocity / Jdot*qd, pullback to configuration space, and the truncated-SVD resolve.
+// One thread owns one environment; every array below lives in registers (all indices are
+// compile-time after unrolling).
+#pragma once
+#include "rmp2_leaves.cuh"
+
+// --------------------------------------------------------------------------------------------------
+// Kinematic chain state of the frame most recently visited.
+//   R, p : world rotation and origin            (reference: kinematics.py:235-246, the chain product)
+//   w, v : angular velocity, origin velocity    (xd = J qd,  kinematics.py:265)
+//   al, a: angular / origin acceleration at zero joint acceleration, i.e. Jdot qd (kinematics.py:267)
+// The reference obtains v, J and a by TensorFlow autodiff of the 4x4 product; here they are the
+// closed-form rigid-body recursion (verified against autodiff in tests/test_oracle_kinematics.py).
+// --------------------------------------------------------------------------------------------------
+struct Chain {
+  float R[9], p[3], w[3], v[3], al[3], a[3];
+};
+
+RMP2_DEV void chain_reset(Chain& c) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c.R[i] = (i % 4 == 0) ? 1.f : 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c.p[i] = c.w[i] = c.v[i] = c.al[i] = c.a[i] = 0.f;
+}
+
+RMP2_DEV void cross3(const float* a, const float* b, float* o) {
+  o[0] = fmaf(a[1], b[2], -a[2] * b[1]);
+  o[1] = fmaf(a[2], b[0], -a[0] * b[2]);
+  o[2] = fmaf(a[0], b[1], -a[1] * b[0]);
+}
+
+RMP2_DEV void matvec3(const float* R, const float* x, float* o) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[i] = fmaf(R[3 * i], x[0], fmaf(R[3 * i + 1], x[1], R[3 * i + 2] * x[2]));
+}
+
+RMP2_DEV void matmul3(const float* A, const float* B, float* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      C[3 * i + j] = fmaf(A[3 * i], B[j], fmaf(A[3 * i + 1], B[3 + j], A[3 * i + 2] * B[6 + j]));
+}
+
+// Advance the chain across one URDF joint: T_child = T_parent * T_const * T_var(q_i).
+// z receives the joint axis in world coordinates (valid for movable joints).
+RMP2_DEV void chain_advance(Chain& c, const FrameTab& F, float qi, float qdi, float (&z)[3]) {
+  float rho[3], Rc[9];
+  matvec3(c.R, F.t, rho);                       // offset parent origin -> joint origin, world
+  matmul3(c.R, F.R, Rc);
+  z[0] = z[1] = z[2] = 0.f;
+  if (F.type != RMP2_JOINT_FIXED) matvec3(Rc, F.axis, z);
+  if (F.type == RMP2_JOINT_PRISMATIC) {         // T_var = translation q * axis  (kinematics.py:231-233)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rho[i] = fmaf(z[i], qi, rho[i]);
+  }
+  float wr[3], wwr[3], ar[3];
+  cross3(c.w, rho, wr);
+  cross3(c.w, wr, wwr);
+  cross3(c.al, rho, ar);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    c.p[i] += rho[i];
+    c.v[i] += wr[i];
+    c.a[i] += ar[i] + wwr[i];
+  }
+  if (F.type == RMP2_JOINT_PRISMATIC) {
+    float wz[3];
+    cross3(c.w, z, wz);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      c.v[i] = fmaf(z[i], qdi, c.v[i]);
+      c.a[i] = fmaf(2.f * qdi, wz[i], c.a[i]);
+    }
+  }
+  if (F.type == RMP2_JOINT_REVOLUTE) {          // Rodrigues, unit axis (kinematics.py:99-121)
+    float s, co;
+    sincosf(qi, &s, &co);
+    const float t = 1.f - co;
+    const float ux = F.axis[0], uy = F.axis[1], uz = F.axis[2];
+    float Rv[9];
+    Rv[0] = fmaf(t * ux, ux, co);
+    Rv[1] = fmaf(t * ux, uy, -s * uz);
+    Rv[2] = fmaf(t * ux, uz, s * uy);
+    Rv[3] = fmaf(t * uy, ux, s * uz);
+    Rv[4] = fmaf(t * uy, uy, co);
+    Rv[5] = fmaf(t * uy, uz, -s * ux);
+    Rv[6] = fmaf(t * uz, ux, -s * uy);
+    Rv[7] = fmaf(t * uz, uy, s * ux);
+    Rv[8] = fmaf(t * uz, uz, co);
+    matmul3(Rc, Rv, c.R);
+    float wz[3];
+    cross3(c.w, z, wz);                          // uses the parent's angular velocity
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      c.al[i] = fmaf(wz[i], qdi, c.al[i]);
+      c.w[i] = fmaf(z[i], qdi, c.w[i]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) c.R[i] = Rc[i];
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Pullback of everything attached to one frame origin (reference: rmp.py:165-167, summed over the
+// pairs/leaves of the frame as rmp.py:149-150 does afterwards):
+//   M += J^T S J,   f += J^T g,   J[:, j] = z_j x (p_k - p_j)  (revolute) | z_j (prismatic)
+// S symmetric 3x3 as (xx, xy, xz, yy, yz, zz).  Msym holds the lower triangle, row-major.
+// --------------------------------------------------------------------------------------------------
+template <int N>
+RMP2_DEV void pullback(const float (&zj)[N][3], const float (&pj)[N][3], const float (&pk)[3], uint32_t anc,
+                       uint32_t prismatic, const float (&S)[6], const float (&g)[3],
+                       float (&Msym)[N * (N + 1) / 2], float (&f)[N]) {
+  float col[N][3], u[N][3];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    col[j][0] = col[j][1] = col[j][2] = 0.f;
+    u[j][0] = u[j][1] = u[j][2] = 0.f;
+    if (anc & (1u << j)) {                       // warp-uniform
+      if (prismatic & (1u << j)) {
+        col[j][0] = zj[j][0];
+        col[j][1] = zj[j][1];
+        col[j][2] = zj[j][2];
+      } else {
+        const float r[3] = {pk[0] - pj[j][0], pk[1] - pj[j][1], pk[2] - pj[j][2]};
+        cross3(zj[j], r, col[j]);
+      }
+      u[j][0] = fmaf(S[0], col[j][0], fmaf(S[1], col[j][1], S[2] * col[j][2]));
+      u[j][1] = fmaf(S[1], col[j][0], fmaf(S[3], col[j][1], S[4] * col[j][2]));
+      u[j][2] = fmaf(S[2], col[j][0], fmaf(S[4], col[j][1], S[5] * col[j][2]));
+      f[j] = fmaf(col[j][0], g[0], fmaf(col[j][1], g[1], fmaf(col[j][2], g[2], f[j])));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    if (anc & (1u << i)) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        const int idx = i * (i + 1) / 2 + j;
+        Msym[idx] = fmaf(col[i][0], u[j][0], fmaf(col[i][1], u[j][1], fmaf(col[i][2], u[j][2], Msym[idx])));
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Resolve: x = pinv(M) f with tf.linalg.pinv's default cutoff (reference: rmp.py:153-154;
+// TensorFlow 2.10 linalg_impl.pinv: singular values <= 10*max(rows,cols)*eps * sigma_max are dropped).
+// One-sided Jacobi on the ROWS of the augmented matrix [M | f]:  rotations Q^T are applied from
+// the left until the rows g_i of G = Q^T M are mutually orthogonal; then g_i = sigma_i v_i^T,
+// y = Q^T f, and  pinv(M) f = sum_{sigma_i > cutoff} g_i^T y_i / sigma_i^2.  No U or V is stored.
+// M may be non-symmetric (joint-limit leaf) or indefinite (velocity-cap leaf).
+// --------------------------------------------------------------------------------------------------
+#ifndef RMP2_JACOBI_MAX_SWEEPS
+#define RMP2_JACOBI_MAX_SWEEPS 14
+#endif
+#define RMP2_JACOBI_TOL 2.4e-7f
+
+template <int N>
+RMP2_DEV void resolve_pinv(float (&G)[N][N], float (&y)[N], float rcond, float (&x)[N]) {
+  for (int sweep = 0; sweep < RMP2_JACOBI_MAX_SWEEPS; ++sweep) {
+    bool rotated = false;
+#pragma unroll
+    for (int p = 0; p < N - 1; ++p) {
+#pragma unroll
+      for (int q = p + 1; q < N; ++q) {
+        float a = 0.f, b = 0.f, g = 0.f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          a = fmaf(G[p][j], G[p][j], a);
+          b = fmaf(G[q][j], G[q][j], b);
+          g = fmaf(G[p][j], G[q][j], g);
+        }
+        const bool rot = g * g > (RMP2_JACOBI_TOL * RMP2_JACOBI_TOL) * a * b;
+        rotated |= rot;
+        // tan of the rotation angle: smaller root of t^2 + 2 zeta t - 1 = 0
+        const float zeta = (b - a) / (2.f * g);
+        const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
+        float c = rsqrtf(fmaf(t, t, 1.f));
+        float s = c * t;
+        c = rot ? c : 1.f;
+        s = rot ? s : 0.f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const float gp = G[p][j], gq = G[q][j];
+          G[p][j] = fmaf(c, gp, -s * gq);
+          G[q][j] = fmaf(s, gp, c * gq);
+        }
+        const float yp = y[p], yq = y[q];
+        y[p] = fmaf(c, yp, -s * yq);
+        y[q] = fmaf(s, yp, c * yq);
+      }
+    }
+    if (!__any_sync(__activemask(), rotated)) break;
+  }
+  float sig2[N];
+  float smax = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) a = fmaf(G[i][j], G[i][j], a);
+    sig2[i] = a;
+    smax = fmaxf(smax, a);
+  }
+  const float cut2 = rcond * rcond * smax;
+#pragma unroll
+  for (int j = 0; j < N; ++j) x[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float coef = (sig2[i] > cut2) ? y[i] / sig2[i] : 0.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j] = fmaf(G[i][j], coef, x[j]);
+  }
+}

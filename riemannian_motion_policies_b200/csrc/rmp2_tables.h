@@ -1,0 +1,71 @@
+// Kernel-side tables of one compiled RMP tree.  Built on the host by rmp2_tree_create and
+// passed BY VALUE as a __grid_constant__ kernel parameter, so every field is read through the
+// constant bank (uniform across the warp) and no global state is shared between trees.
+#pragma once
+#include <stdint.h>
+#include "../../include/rmp2_b200.h"
+
+#define RMP2_MAX_SLOTS 4          // saved chain states for branching kinematic trees
+#define RMP2_VECPOOL 160          // floats: goals / q0 / limits of all leaves
+#define RMP2_SLOT_BASE (-2)       // restore_slot value meaning "start from the base link"
+#define RMP2_CHAIN_FLOATS 24      // R(9) p(3) w(3) v(3) alpha(3) a(3)
+#define RMP2_TILE_SPHERES 32      // spheres per shared-memory tile (32 x 16 B = 4 TMA boxes of 128 B)
+
+struct FrameTab {
+  float R[9];            // constant rotation  (reference: kinematics.py:202, R_x R_y R_z order)
+  float t[3];            // constant translation
+  float axis[3];         // joint axis, in the frame after the constant transform
+  int32_t type;          // RMP2_JOINT_*
+  int32_t qidx;          // column of q, -1 = none
+  int32_t restore_slot;  // -1: parent is the previous frame in execution order
+                         // RMP2_SLOT_BASE: parent is the base; >= 0: reload saved chain state
+  int32_t save_slot;     // >= 0: store the chain state after this frame (it has several children)
+  uint32_t anc_mask;     // bit j: joint column j lies on the path base -> this frame
+  int32_t leaf_begin;    // leaves attached to this frame: [leaf_begin, leaf_end)
+  int32_t leaf_end;
+  int32_t ref_index;     // index in the reference's frame order (for diagnostics)
+};
+
+struct LeafTab {
+  int32_t type;          // RMP2_LEAF_*
+  int32_t space;         // RMP2_SPACE_*
+  int32_t goal_slot;     // >= 0: per-environment goal
+  int32_t vec_off;       // offset of this leaf's vector parameters in vecpool
+  int32_t pair_set;      // FRAME_DISTANCE_PAIRS: index into the per-call pair offsets
+  float p[RMP2_LEAF_PARAMS];   // derived parameters, see leaf_params.h
+};
+
+struct StepTables {
+  int32_t n;                    // controllable joints
+  int32_t n_frames;             // frames executed (unused ones pruned), depth-first order
+  int32_t n_frame_leaves;       // leaves [0, n_frame_leaves) hang on frames
+  int32_t n_leaves;             // leaves [n_frame_leaves, n_leaves) are configuration-space
+  int32_t n_slots;
+  int32_t uses_spheres;         // some leaf reads io.spheres
+  uint32_t prismatic_mask;      // bit j: joint column j is prismatic
+  float rcond;                  // 10 * n * eps32 (tf.linalg.pinv default, rmp.py:153)
+  FrameTab frames[RMP2_MAX_FRAMES];
+  LeafTab leaves[RMP2_MAX_LEAVES];
+  float vecpool[RMP2_VECPOOL];
+};
+
+// per-call arguments (device pointers)
+struct StepArgs {
+  long long B;
+  const float* q;
+  const float* qd;
+  float* qdd;
+  const float* goals;
+  const float* spheres;
+  const float* pairs;
+  int32_t n_goal_slots;
+  int32_t n_spheres;
+  int32_t pair_total;
+  int32_t pair_off[RMP2_MAX_PAIR_SETS + 1];
+  // rollout (rmp2_rollout): when n_sim_steps > 0 the kernel integrates in place
+  float* q_rw;
+  float* qd_rw;
+  float dt;
+  int32_t n_sim_steps;
+  int32_t control_every;
+};

@@ -1,0 +1,204 @@
+"""Task maps -- host-side mirror of the reference's ``taskmap.py`` (same names and signatures).
+
+A chain built with ``chain_taskmaps([...])`` remembers its stages, so ``RmpCore`` can recognise
+the closed set of chains the CUDA step kernel implements and compile the
+tree; the kernel then evaluates the whole chain analytically.  The stand-alone ``forward`` /
+``differentiate`` methods below exist for API parity: FK runs in the CUDA FK kernel, and the small
+closed-form maps on top of it run as torch ops on the CUDA tensors it returns.
+"""
+import torch
+
+from ._tensor import like_input, require_cuda, to_device, unwrap
+
+
+class Taskmap:
+    """reference: taskmap.py:6-11."""
+
+    def forward(self, q):
+        raise NotImplementedError
+
+    def differentiate(self, q, qd):
+        raise NotImplementedError
+
+
+class IdentityTaskmap(Taskmap):
+    """x = q (reference: taskmap.py:13-20)."""
+
+    def forward(self, q):
+        return q
+
+    def differentiate(self, q, qd):
+        dev = require_cuda()
+        qt, qdt = to_device(q, dev), to_device(qd, dev)
+        J = torch.eye(qt.shape[-1], device=dev).expand(qt.shape[0], -1, -1).contiguous()
+        out = (qt, qdt, J, torch.zeros_like(qt))
+        return tuple(like_input(t, q) for t in out)
+
+
+class TaskmapByForwardKinematic(Taskmap):
+    """reference: taskmap.py:22-31."""
+
+    def __init__(self, fkine, frame):
+        self.fkine = fkine
+        self.frame = frame.decode() if isinstance(frame, bytes) else str(frame)
+        fkine.frame_index(self.frame)          # KeyError now rather than at the first step
+
+    def forward(self, q):
+        return self.fkine(q, self.frame)
+
+    def differentiate(self, q, qd):
+        return self.fkine.differentiate(q, qd, self.frame)
+
+
+class TaskmapByFunction(Taskmap):
+    """reference: taskmap.py:33-42.  ``stages`` is set by chain_taskmaps (None for user functions,
+    which the tree compiler rejects: there is no generic-autodiff fallback)."""
+
+    def __init__(self, forward_fn, differentiate_fn, stages=None):
+        self.forward_fn = forward_fn
+        self.differentiate_fn = differentiate_fn
+        self.stages = stages
+
+    def forward(self, q):
+        return self.forward_fn(q)
+
+    def differentiate(self, q, qd):
+        return self.differentiate_fn(q, qd)
+
+
+class TaskmapFrom4x4ToPosition(Taskmap):
+    """pos = T[:3, 3] (reference: taskmap.py:45-54)."""
+
+    def forward(self, input):
+        t = to_device(input)
+        return like_input(t.reshape(-1, 4, 4)[:, :3, 3].contiguous(), input)
+
+    def differentiate(self, q, qd):
+        dev = require_cuda()
+        qt, qdt = to_device(q, dev).reshape(-1, 16), to_device(qd, dev).reshape(-1, 16)
+        rows = torch.tensor([3, 7, 11], device=dev)
+        J = torch.zeros(qt.shape[0], 3, 16, device=dev)
+        J[:, torch.arange(3, device=dev), rows] = 1.0
+        out = (qt[:, rows], qdt[:, rows], J, torch.zeros(qt.shape[0], 3, device=dev))
+        return tuple(like_input(t, q) for t in out)
+
+
+class _DistanceBase(Taskmap):
+    """Closed form of the reference's autodiff through ``norm(p_joint + stop_grad(p_link - p_joint) - p_obs)``."""
+
+    def _points(self, dev):
+        raise NotImplementedError
+
+    def forward(self, input):
+        link, obst = self._points(require_cuda())
+        d = torch.linalg.norm(link - obst, dim=-1)[:, None]
+        return like_input(d, input)
+
+    def differentiate(self, q, qd):
+        dev = require_cuda()
+        link, obst = self._points(dev)
+        K = link.shape[0]
+        qdt = to_device(qd, dev).reshape(-1, 16)
+        r = link - obst
+        d = torch.linalg.norm(r, dim=-1)
+        nhat = r / d[:, None]
+        v = qdt[:, [3, 7, 11]].expand(K, 3)
+        xdot = (nhat * v).sum(-1)
+        J = torch.zeros(K, 1, 16, device=dev)
+        J[:, 0, [3, 7, 11]] = nhat
+        c = ((v * v).sum(-1) - xdot * xdot) / d
+        out = (d[:, None], xdot[:, None], J, c[:, None])
+        return tuple(like_input(t, q) for t in out)
+
+
+class TaskmapJointFrame4x4ToDistance(_DistanceBase):
+    """Distance of K closest-point pairs attached to one frame (reference: taskmap.py:115-138).
+    The two arguments may be tensors/arrays [K,3] or variables that are updated in place
+    (``Datamanager`` entries, data_management.py:8-17); they are read again at every step."""
+
+    def __init__(self, pos_on_link_in_base_frame, pos_on_obstacle_in_base_frame):
+        self.pos_on_link_in_base_frame = pos_on_link_in_base_frame
+        self.pos_on_obstacle_in_base_frame = pos_on_obstacle_in_base_frame
+
+    def _points(self, dev):
+        link = to_device(self.pos_on_link_in_base_frame, dev).reshape(-1, 3)
+        obst = to_device(self.pos_on_obstacle_in_base_frame, dev).reshape(-1, 3)
+        if link.shape != obst.shape:
+            raise ValueError("pos_on_link_in_base_frame and pos_on_obstacle_in_base_frame need the same shape")
+        return link, obst
+
+    def current_pairs(self):
+        """[K,6] = (pos_on_link, pos_on_obstacle), on whatever side the holders live."""
+        link = unwrap(self.pos_on_link_in_base_frame)
+        obst = unwrap(self.pos_on_obstacle_in_base_frame)
+        link = torch.as_tensor(link, dtype=torch.float32).reshape(-1, 3)
+        obst = torch.as_tensor(obst, dtype=torch.float32).reshape(-1, 3)
+        if link.shape != obst.shape:
+            raise ValueError("pos_on_link_in_base_frame and pos_on_obstacle_in_base_frame need the same shape")
+        return torch.cat([link, obst.to(link.device)], dim=1)
+
+
+class TaskmapJointFrame4x4ToSphereDistance(Taskmap):
+    """Additive to the reference: the K pairs of this frame are the O sphere obstacles passed to
+    ``RmpCore.evaluate(..., spheres=[B,O,4])``: pos_on_link = frame origin, pos_on_obstacle = the
+    closest point of the sphere surface.  Only meaningful inside a compiled tree."""
+
+    def forward(self, input):
+        raise NotImplementedError("sphere distances are evaluated inside RmpCore.evaluate(..., spheres=...)")
+
+    differentiate = forward
+
+
+class TaskmapFrom4x4ToEuler(Taskmap):
+    """reference: taskmap.py:57-67 -- orientation task map, not on the control-step path
+    (SURVEY.md section 8f, rank 4)."""
+
+    def forward(self, input):
+        from .kinematics import euler_from_rotation_matrix
+        t = to_device(input)
+        return like_input(euler_from_rotation_matrix(t.reshape(-1, 4, 4)[:, :3, :3]), input)
+
+    def differentiate(self, q, qd):
+        raise NotImplementedError("TaskmapFrom4x4ToEuler.differentiate is outside the accelerated hot path")
+
+
+class TaskmapRelative4x4(Taskmap):
+    """reference: taskmap.py:79-99 -- used only by the v1 CollisionAvoidance path
+    (SURVEY.md section 8f, rank 3)."""
+
+    def __init__(self, relative_pos):
+        self.relative_pos = relative_pos
+
+    def forward(self, input):
+        raise NotImplementedError("TaskmapRelative4x4 is outside the accelerated hot path")
+
+    differentiate = forward
+
+
+def _chain_taskmaps(taskmap_1, taskmap_2):
+    """Chain rule for (x, xd, J, c) (reference: taskmap.py:142-162)."""
+    def combined_forward(q):
+        return taskmap_2.forward(taskmap_1.forward(q))
+
+    def combined_differentiate(q, qd):
+        out_1, dout1_dt, J_1, c_1 = taskmap_1.differentiate(q, qd)
+        out_2, _, J_2, c_2 = taskmap_2.differentiate(out_1, dout1_dt)
+        dev = require_cuda()
+        J_1d, J_2d = to_device(J_1, dev), to_device(J_2, dev)
+        dout_dt = (J_2d @ to_device(dout1_dt, dev)[..., None])[..., 0]
+        J = J_2d @ J_1d
+        c = to_device(c_2, dev) + (J_2d @ to_device(c_1, dev)[..., None])[..., 0]
+        return tuple(like_input(t, q) for t in (to_device(out_2, dev), dout_dt, J, c))
+
+    stages_1 = taskmap_1.stages if isinstance(taskmap_1, TaskmapByFunction) else [taskmap_1]
+    stages_2 = taskmap_2.stages if isinstance(taskmap_2, TaskmapByFunction) else [taskmap_2]
+    stages = None if (stages_1 is None or stages_2 is None) else list(stages_1) + list(stages_2)
+    return TaskmapByFunction(combined_forward, combined_differentiate, stages=stages)
+
+
+def chain_taskmaps(taskmap_list):
+    """Left fold over the list (reference: taskmap.py:164-168)."""
+    chained = taskmap_list[0]
+    for taskmap in taskmap_list[1:]:
+        chained = _chain_taskmaps(chained, taskmap)
+    return chained

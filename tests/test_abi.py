@@ -1,0 +1,116 @@
+"""The C-ABI shared library: builds, loads and exports every symbol include/rmp2_b200.h declares;
+host-only entry points (handle creation, tree compilation, argument checking) work without a GPU.
+No compute call is made here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from riemannian_motion_policies_b200 import _native, scenarios as S
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rmp2_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rmp2_[a-z_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_symbols() == sorted(_native.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    for sym in _declared_symbols():
+        assert hasattr(native_lib, sym), sym
+    assert b"sm_100a" in native_lib.rmp2_version()
+
+
+def test_struct_layouts_match_header():
+    # rmp2_leaf_desc: 4 int32 + 16 float + 24 float ; rmp2_step_io as declared
+    assert ctypes.sizeof(_native.LeafDesc) == 4 * 4 + 4 * _native.RMP2_LEAF_PARAMS + 4 * 2 * _native.RMP2_MAX_JOINTS
+    io = _native.StepIO
+    assert io.B.offset == 0 and io.q.offset == 8 and io.qdd.offset == 24 and io.goals.offset == 32
+    assert io.n_goal_slots.offset == 40 and io.n_spheres.offset == 44 and io.spheres.offset == 48
+    assert io.pairs.offset == 56 and io.n_pair_sets.offset == 64 and io.pair_counts.offset == 68
+
+
+def _robot(native_lib, F=3, n=2, parent=(-1, 0, 1), jtype=(1, 1, 0), axis=None):
+    T = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (F, 1))
+    axis = np.tile(np.array([[0, 0, 1]], np.float32), (F, 1)) if axis is None else np.asarray(axis, np.float32)
+    jt = np.asarray(jtype, np.int8)
+    par = np.asarray(parent, np.int32)
+    qidx = np.array([0, 1, -1][:F], np.int32)
+    h = ctypes.c_void_p()
+    rc = native_lib.rmp2_robot_create(T.ctypes.data, axis.ctypes.data, jt.ctypes.data, par.ctypes.data,
+                                      qidx.ctypes.data, F, n, ctypes.byref(h))
+    return rc, h
+
+
+def test_robot_create_checks_arguments(native_lib):
+    rc, h = _robot(native_lib)
+    assert rc == 0 and h.value
+    native_lib.rmp2_robot_destroy(h)
+    rc, _ = _robot(native_lib, parent=(-1, 2, 1))
+    assert rc == 1 and b"parent" in native_lib.rmp2_last_error()
+    rc, _ = _robot(native_lib, axis=[[0, 0, 2], [0, 0, 1], [0, 0, 0]])
+    assert rc == 3 and b"unit length" in native_lib.rmp2_last_error()
+
+
+def test_tree_create_rejects_unsupported_combinations(native_lib):
+    rc, h = _robot(native_lib)
+    d = _native.LeafDesc()
+    d.type, d.space, d.frame, d.goal_slot = _native.LEAF_OBSTACLE_AVOIDANCE, _native.SPACE_CONFIG, -1, -1
+    t = ctypes.c_void_p()
+    rc = native_lib.rmp2_tree_create(h, ctypes.byref(d), 1, ctypes.byref(t))
+    assert rc == 3
+    d.type, d.space, d.frame = _native.LEAF_TARGET_ATTRACTOR, _native.SPACE_FRAME_POSITION, 7
+    rc = native_lib.rmp2_tree_create(h, ctypes.byref(d), 1, ctypes.byref(t))
+    assert rc == 1 and b"frame index" in native_lib.rmp2_last_error()
+    native_lib.rmp2_robot_destroy(h)
+
+
+def test_python_tree_compiler_on_cpu(native_lib):
+    """Tree compilation is host-only: every workload of BASELINE.json compiles without a GPU, the
+    unsupported chains raise NotImplementedError (no fallback)."""
+    ns = S.product_namespace()
+    fk = ns.UrdfForwardKinematic(S.PANDA_URDF, S.PANDA_ORDER_9)
+    assert fk.frame_names[-1] == "panda_grasptarget_hand"
+    sphere_tm = lambda frame: ns.TaskmapJointFrame4x4ToSphereDistance()
+    for cfg in (3, 4, 5):
+        core = S.BUILDERS[cfg](ns, fk, [0.5, 0.0, 0.5], 9, sphere_tm)
+        tree = core.compile(9, goal_leaves=["attractor"])
+        assert tree.uses_spheres and tree.handle.value
+    core = S.build_config2(ns, fk, [0.5, 0.0, 0.5], 9)
+    assert not core.compile(9).uses_spheres
+    # explicit-pair leaves (Datamanager feed)
+    dm = ns.Datamanager(fk)
+    core = S.build_config3(ns, fk, [0.5, 0, 0.5], 9, lambda fr: ns.TaskmapJointFrame4x4ToDistance(
+        dm[fr]['pos_on_link_in_base_frame'], dm[fr]['pos_on_obstacle_in_base_frame']))
+    assert len(core.compile(9).pair_taskmaps) == 10
+    # a user-defined task map cannot be compiled
+    core = ns.RmpCore()
+    core.add_rmp(ns.TargetPolicy(0.1, 1, 0.1, [0, 0, 0], ns.TaskmapByFunction(lambda q: q, lambda q, qd: None)))
+    with pytest.raises(NotImplementedError):
+        core.compile(9)
+    core = ns.RmpCore()
+    core.add_rmp(ns.CollisionAvoidance(None, None, 1, 1, 1, 1, 1, 1, ns.IdentityTaskmap()))
+    with pytest.raises(NotImplementedError):
+        core.compile(9)
+    with pytest.raises(KeyError):
+        ns.RmpCore().remove_rmp_by_name("missing")
+
+
+def test_compute_fails_loudly_without_cuda(native_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    ns = S.product_namespace()
+    fk = ns.UrdfForwardKinematic(S.TWO_JOINT_URDF, S.TWO_JOINT_ORDER)
+    core = S.build_config1(ns, fk, [1.0, 0.5, 0.1])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        core.evaluate(np.zeros(2, np.float32), np.zeros(2, np.float32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fk.forward(np.zeros((1, 2), np.float32), "link_23")
