@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Benchmark of the RMP2 control-step hot path (contract: see the task brief / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 2|3|4|5] [--envs B]
+
+A "step" = one pass of the hot path (RmpCore.evaluate, reference rmp.py:133-155) over one batch of
+synthetic environments.  Default workload: BASELINE.json configs[3] -- Franka Panda (7 DOF), target +
+joint-limit + 64 dynamic sphere obstacles, 1,048,576 environments per GPU (weak scaling over N GPUs,
+no collective on the step path).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "franka_rmp2_control_steps_per_sec"
+UNIT = "env-steps/s"
+# algorithmic work per environment-step, SURVEY.md section 8d (n = 7, panda_wo_tool)
+FLOPS_PER_ENV = {2: 2704.0, 3: 16222.0, 4: 45147.0, 5: 45406.0}
+BYTES_PER_ENV = {2: 96.0, 3: 352.0, 4: 1120.0, 5: 1120.0}
+WORKLOAD = {
+    2: "franka_panda_7dof_target+cspace_bias (BASELINE configs[1])",
+    3: "franka_panda_7dof_cluttered_16_spheres (BASELINE configs[2])",
+    4: "franka_panda_7dof_target+joint_limits+64_dynamic_spheres (BASELINE configs[3])",
+    5: "franka_panda_7dof_full_tree_64_spheres (BASELINE configs[4])",
+}
+DEFAULT_ENVS = {2: 1 << 20, 3: 1 << 20, 4: 1 << 20, 5: 1 << 20}
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # analytic, at clocks.max.sm
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, power, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    """One host core: restated reference (oracle), one environment per call like the reference."""
+    config, n, seed, n_envs, n_spheres = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle import harness as H
+    from riemannian_motion_policies_b200 import scenarios as S
+    q, qd, goal = S.sample_panda_state(n_envs + 1, n, seed)
+    sph = S.sample_spheres(n_envs + 1, n_spheres, seed) if n_spheres else None
+    fk = H.make_fkine(n)
+    H.evaluate_loop(config, n, q[:1], qd[:1], goal[:1], None if sph is None else sph[:1], fkine=fk)   # warm-up
+    t0 = time.perf_counter()
+    H.evaluate_loop(config, n, q[1:], qd[1:], goal[1:], None if sph is None else sph[1:], fkine=fk)
+    return n_envs, time.perf_counter() - t0
+
+
+def cpu_reference_throughput(config, n, cores, envs_per_core, n_spheres):
+    """env-steps/s of the restated reference on `cores` host processes (1 thread each)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    jobs = [(config, n, 1000 + i, envs_per_core, n_spheres) for i in range(cores)]
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    total = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return total / slowest, total, slowest
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path.  The reference is
+    TensorFlow 2.10 + PyBullet and cannot be installed here (no wheels, no network), so the arm times
+    the oracle port (oracle/rmp_oracle.py: same per-leaf autodiff structure, one env per call) on all
+    host cores.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    config, n = args.config, 7
+    cores = min(host_cores(), 64)
+    per_core = max(2, args.envs_per_core)
+    O_ = {2: 0, 3: 16, 4: 64, 5: 64}[config]
+    values = []
+    for _ in range(max(1, args.steps)):
+        v, total, slowest = cpu_reference_throughput(config, n, cores, per_core, O_)
+        values.append(v)
+    value = float(np.median(values))
+    sample = f"{cores} processes x {per_core} envs per step, one env per RmpCore.evaluate call (autodiff per leaf)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * cores * per_core / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD[config], "envs_per_step": cores * per_core, "spheres_per_env": O_, "dof": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def synth_inputs(ns, fk, n, B, O_, n_buffers, seed, device):
+    """Seeded synthetic environments generated on the device (distribution: SURVEY.md section 8d)."""
+    import torch
+    from riemannian_motion_policies_b200 import scenarios as S
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lo = torch.tensor(S.PANDA_Q_LOW[:n], dtype=torch.float32, device=device)
+    hi = torch.tensor(S.PANDA_Q_HIGH[:n], dtype=torch.float32, device=device)
+    q = lo + (hi - lo) * torch.rand(B, n, generator=g, device=device)
+    qd = -0.3 + 0.6 * torch.rand(B, n, generator=g, device=device)
+    glo = torch.tensor([0.3, -0.7, 0.3], device=device)
+    ghi = torch.tensor([0.7, 0.7, 0.7], device=device)
+    goal = glo + (ghi - glo) * torch.rand(B, 3, generator=g, device=device)
+    spheres = []
+    if O_:
+        frames = S.collision_frames(fk)
+        origins = torch.stack([fk.forward(q, fr)[:, :3, 3] for fr in frames], dim=1)       # [B,K,3] CUDA FK kernel
+        slo = torch.tensor([-0.8, -0.8, 0.0], device=device)
+        shi = torch.tensor([0.8, 0.8, 1.2], device=device)
+
+        def draw(count):
+            c = slo + (shi - slo) * torch.rand(count, 3, generator=g, device=device)
+            r = 0.025 + 0.075 * torch.rand(count, 1, generator=g, device=device)
+            return torch.cat([c, r], dim=-1)
+
+        for _ in range(n_buffers):
+            sph = draw(B * O_).reshape(B, O_, 4)
+            for _round in range(30):
+                bad = torch.zeros(B, O_, dtype=torch.bool, device=device)
+                for k in range(origins.shape[1]):                                         # keeps the temporaries [B,O]
+                    d = torch.linalg.norm(sph[:, :, :3] - origins[:, None, k, :], dim=-1) - sph[:, :, 3]
+                    bad |= d < 0.03
+                nbad = int(bad.sum())
+                if nbad == 0:
+                    break
+                sph[bad] = draw(nbad)
+            spheres.append(sph.contiguous())
+    return q.contiguous(), qd.contiguous(), goal.contiguous(), spheres
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from riemannian_motion_policies_b200 import _native, scenarios as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    config, n = args.config, 7
+    B = args.envs or DEFAULT_ENVS[config]
+    O_ = S.N_SPHERES[config]
+    ns = S.product_namespace()
+    fk = ns.UrdfForwardKinematic(S.PANDA_WO_TOOL_URDF, S.PANDA_ORDER_7)
+    goal0 = [0.5, 0.0, 0.5]
+    sphere_tm = lambda frame: ns.TaskmapJointFrame4x4ToSphereDistance()
+    core = S.build_config2(ns, fk, goal0, n) if config == 2 else S.BUILDERS[config](ns, fk, goal0, n, sphere_tm)
+    goal_leaf = "target" if config == 2 else "attractor"
+    tree = core.compile(n, goal_leaves=[goal_leaf])
+
+    n_buffers = 4 if O_ else 1
+    q, qd, goal, spheres = synth_inputs(ns, fk, n, B, O_, n_buffers, seed=S.SEEDS[config] + 17 * rank, device=device)
+    goals = goal.reshape(B, 1, 3).contiguous()
+    qdd = torch.empty(B, n, device=device)
+
+    def step(i):
+        tree.step(q, qd, qdd, goals=goals, spheres=spheres[i % n_buffers] if O_ else None)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    barrier()
+    launches0 = _native.launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        start.record()
+        for i in range(args.steps):
+            step(i)
+        stop.record()
+        barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    launches = _native.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    per_gpu = B / (ms_per_step * 1e-3)
+
+    # ---- parity spot check on the benchmarked inputs (first 128 envs of rank 0, oracle = checker only)
+    parity = None
+    e2e = None
+    cpu_baseline = None
+    if rank == 0 and not args.skip_checks:
+        from oracle import harness as H
+        sub = slice(0, 128)
+        sph_np = spheres[(args.steps - 1) % n_buffers][sub].cpu().numpy() if O_ else None
+        ref64 = H.evaluate_vmap(config, n, q[sub].cpu().numpy(), qd[sub].cpu().numpy(), goal[sub].cpu().numpy(), sph_np,
+                                dtype=torch.float64)
+        ref32 = H.evaluate_vmap(config, n, q[sub].cpu().numpy(), qd[sub].cpu().numpy(), goal[sub].cpu().numpy(), sph_np,
+                                dtype=torch.float32)
+        got = qdd[sub].cpu().numpy()
+        rel = lambda a, b: np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-30)
+        parity = {"envs": 128, "median_rel_err_vs_oracle_f32": float(np.median(rel(got, ref32))),
+                  "frac_within_1e-5_of_oracle_f32": float((rel(got, ref32) <= 1e-5).mean()),
+                  "median_rel_err_vs_oracle_f64": float(np.median(rel(got, ref64))),
+                  "median_rel_err_oracle_f32_vs_f64": float(np.median(rel(ref32, ref64)))}
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    if not args.skip_e2e:
+        hb = 2 if O_ else 1
+        q_h, qd_h, goals_h = (t.cpu().pin_memory() for t in (q, qd, goals))
+        sph_h = [spheres[i].cpu().pin_memory() for i in range(hb)] if O_ else [None]
+        qdd_h = torch.empty(B, n).pin_memory()
+        e2e_steps = max(2, min(args.steps, 5))
+        tree.step_host(q_h, qd_h, qdd_h, goals=goals_h, spheres=sph_h[0])           # warm-up (allocates staging)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            tree.step_host(q_h, qd_h, qdd_h, goals=goals_h, spheres=sph_h[i % hb])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = B * (2 * n + 3 + 4 * O_) * 4
+        d2h = B * n * 4
+        e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": e2e_steps, "note": "RmpCore -> CompiledTree.step_host -> rmp2_step_host, pinned host tensors, "
+                                           "64k-env chunks pipelined over 3 streams"}
+        same = torch.allclose(qdd_h[:4096], qdd[:4096].cpu(), rtol=0, atol=0) if not O_ else None
+        if same is not None:
+            e2e["matches_device_path"] = bool(same)
+
+    if rank == 0 and not args.skip_checks and world == 1:
+        cores = min(host_cores(), 64)
+        v, total, slowest = cpu_reference_throughput(config, n, cores, args.envs_per_core, O_)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{total} envs of the same workload, {cores} processes x {args.envs_per_core} envs, "
+                                  f"oracle port run one env per call ({slowest:.1f} s)"}
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        info = tree.kernel_info()
+        t_s = ms_per_step * 1e-3
+        gbs = BYTES_PER_ENV[config] * B / t_s / 1e9
+        tflops = FLOPS_PER_ENV[config] * B / t_s / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD[config], "envs_per_gpu": B, "global_envs": world * B, "spheres_per_env": O_,
+                       "dof": n, "parallelism": f"env-sharded x{world}, no step-path collective",
+                       "l2_policy": f"inputs larger than L2: {n_buffers} rotating sphere buffers of "
+                                    f"{B * O_ * 16 / 1e6:.0f} MB each" if O_ else "q/qd/goal re-read each step"},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                         "bytes_per_env_step": BYTES_PER_ENV[config],
+                         "note": "the kernel is FP32/MUFU-issue bound by design (see roofline_fp32); HBM fraction is "
+                                 "reported because the contract's bounds are hbm|tensor"},
+            "roofline_fp32": {"bound": "fp32", "achieved": tflops, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                              "frac": tflops / FP32_PEAK_TFLOPS, "flops_per_env_step": FLOPS_PER_ENV[config],
+                              "peak_source": "analytic 148 SM x 128 lanes x 2 x 1.965 GHz"},
+            "per_gpu_value": per_gpu, "gpu_launches": int(launches), "kernel": info, "clocks": clocks.summary(),
+            "e2e": e2e, "cpu_baseline": cpu_baseline, "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5])
+    ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: 1,048,576)")
+    ap.add_argument("--envs-per-core", type=int, default=6, help="CPU arm: environments per host process per step")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-checks", action="store_true", help="skip the oracle parity spot check and the CPU baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -208,6 +208,8 @@ class CompiledTree:
         """Device tensors in, device tensor out; asynchronous on the current stream."""
         B = q.shape[0]
         self._check(B, q, qd, qdd, goals, spheres, pairs, cuda=True)
+        if B == 0:
+            return qdd
         io = self._io(B, q, qd, qdd, goals, spheres, pairs, pair_counts)
         _native.check(_native.lib().rmp2_step(self.handle, ctypes.byref(io), current_stream_ptr(q.device)))
         return qdd
