@@ -154,34 +154,91 @@ RMP2_DEV void pullback(const float (&zj)[N][3], const float (&pj)[N][3], const f
 // M may be non-symmetric (joint-limit leaf) or indefinite (velocity-cap leaf).
 // --------------------------------------------------------------------------------------------------
 #ifndef RMP2_JACOBI_MAX_SWEEPS
-#define RMP2_JACOBI_MAX_SWEEPS 14
+#define RMP2_JACOBI_MAX_SWEEPS 16
 #endif
-#define RMP2_JACOBI_TOL 2.4e-7f
+#define RMP2_JACOBI_TOL 2.4e-7f          // relative orthogonality |g| <= tol sqrt(a b)  (4 eps32)
+#define RMP2_JACOBI_ANGLE 1e-8f          // see below
+#define RMP2_JACOBI_DROP (1.f / 16.f)    // see below
+
+// Round-robin (circle method) schedule: round r, slot k -> the pair (p, q).  Consecutive slots of a
+// round touch disjoint rows, so the serial scalar part of one rotation overlaps the row updates of
+// the previous one.  MM = N rounded up to even; pairs that involve the dummy row MM-1 >= N are skipped.
+template <int N>
+struct JacobiSchedule {
+  static constexpr int MM = (N % 2 == 0) ? N : N + 1;
+  static constexpr int rounds = MM - 1;
+  static constexpr int slots = MM / 2;
+  __host__ __device__ static constexpr int first(int r, int k) {
+    return k == 0 ? (MM - 1) : (r + k) % (MM - 1);
+  }
+  __host__ __device__ static constexpr int second(int r, int k) {
+    return k == 0 ? r : (r - k + (MM - 1)) % (MM - 1);
+  }
+};
 
 template <int N>
 RMP2_DEV void resolve_pinv(float (&G)[N][N], float (&y)[N], float rcond, float (&x)[N]) {
+  using Sch = JacobiSchedule<N>;
+  float nrm[N];
   for (int sweep = 0; sweep < RMP2_JACOBI_MAX_SWEEPS; ++sweep) {
+    // squared row norms: exact at the start of every sweep, updated in closed form inside it
+    float smax = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int j = 0; j + 1 < N; j += 2) {
+        a0 = fmaf(G[i][j], G[i][j], a0);
+        a1 = fmaf(G[i][j + 1], G[i][j + 1], a1);
+      }
+      if (N % 2) a0 = fmaf(G[i][N - 1], G[i][N - 1], a0);
+      nrm[i] = a0 + a1;
+      smax = fmaxf(smax, nrm[i]);
+    }
+    // A row whose norm is below drop2 ends below the pinv cutoff whatever happens next (the smaller
+    // row of a pair only loses energy), so its own direction is irrelevant.  Such a row is still
+    // rotated against a large row while the rotation angle is visible in y (> RMP2_JACOBI_ANGLE),
+    // but no longer just to keep it orthogonal relative to its own, ever shrinking, norm -- which in
+    // float32 never terminates for exactly rank-deficient M.
+    const float drop2 = rcond * rcond * smax * RMP2_JACOBI_DROP;
     bool rotated = false;
 #pragma unroll
-    for (int p = 0; p < N - 1; ++p) {
+    for (int r = 0; r < Sch::rounds; ++r) {
 #pragma unroll
-      for (int q = p + 1; q < N; ++q) {
-        float a = 0.f, b = 0.f, g = 0.f;
+      for (int k = 0; k < Sch::slots; ++k) {
+        const int p0 = Sch::first(r, k), q0 = Sch::second(r, k);
+        if (p0 >= N || q0 >= N) continue;            // compile-time after unrolling
+        const int p = p0 < q0 ? p0 : q0, q = p0 < q0 ? q0 : p0;
+        float g0 = 0.f, g1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          a = fmaf(G[p][j], G[p][j], a);
-          b = fmaf(G[q][j], G[q][j], b);
-          g = fmaf(G[p][j], G[q][j], g);
+        for (int j = 0; j + 1 < N; j += 2) {
+          g0 = fmaf(G[p][j], G[q][j], g0);
+          g1 = fmaf(G[p][j + 1], G[q][j + 1], g1);
         }
-        const bool rot = g * g > (RMP2_JACOBI_TOL * RMP2_JACOBI_TOL) * a * b;
+        if (N % 2) g0 = fmaf(G[p][N - 1], G[q][N - 1], g0);
+        const float g = g0 + g1;
+        const float a = nrm[p], b = nrm[q];
+        const float g2 = g * g;
+        const float mx = fmaxf(a, b), mn = fminf(a, b);
+        const bool rot = (g2 > (RMP2_JACOBI_TOL * RMP2_JACOBI_TOL) * a * b) &&
+                         (mn >= drop2 || g2 > (RMP2_JACOBI_ANGLE * RMP2_JACOBI_ANGLE) * mx * mx);
+        if (!__any_sync(0xffffffffu, rot)) continue;  // warp-uniform: nobody needs this pair
         rotated |= rot;
-        // tan of the rotation angle: smaller root of t^2 + 2 zeta t - 1 = 0
-        const float zeta = (b - a) / (2.f * g);
-        const float t = copysignf(1.f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.f)));
+        // tan of the rotation angle, smaller root of t^2 + 2 zeta t - 1 = 0 with zeta = (b-a)/(2g):
+        //   t = 2 g sign(b-a) / (|b-a| + sqrt((b-a)^2 + 4 g^2)).
+        // Any (c, s) gives an orthogonal-up-to-scale row transform and the solution below is invariant
+        // to row scaling, so the approximate intrinsics only affect the convergence rate.
+        const float tau = b - a;
+        const float hyp2 = fmaf(tau, tau, 4.f * g2);
+        const float hyp = hyp2 * rsqrtf(fmaxf(hyp2, 1e-37f));
+        const float t = __fdividef((tau < 0.f) ? -2.f * g : 2.f * g, fabsf(tau) + hyp);
         float c = rsqrtf(fmaf(t, t, 1.f));
         float s = c * t;
+        const float tg = rot ? t * g : 0.f;          // sign(t g) = sign(b - a): the larger row gains
         c = rot ? c : 1.f;
         s = rot ? s : 0.f;
+        nrm[p] = a - tg;
+        nrm[q] = b + tg;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
           const float gp = G[p][j], gq = G[q][j];
@@ -193,7 +250,7 @@ RMP2_DEV void resolve_pinv(float (&G)[N][N], float (&y)[N], float rcond, float (
         y[q] = fmaf(s, yp, c * yq);
       }
     }
-    if (!__any_sync(__activemask(), rotated)) break;
+    if (!__any_sync(0xffffffffu, rotated)) break;
   }
   float sig2[N];
   float smax = 0.f;
