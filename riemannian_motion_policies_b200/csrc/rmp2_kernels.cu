@@ -53,6 +53,7 @@ RMP2_DEV void tma_load_2d(void* dst, const CUtensorMap* tmap, int32_t x, int32_t
 // --------------------------------------------------------------------------------- per-env context
 struct WarpTile {
   const char* base;   // this warp's staged spheres: [box][32 rows][128 B], 128B-swizzled
+  uint32_t base32;    // the same, as a shared-window address
   uint64_t* bar;      // this warp's mbarrier
   uint32_t phase;     // parity of the next completion to wait for
   int boxes;          // boxes per tile (<= 4)
@@ -169,24 +170,37 @@ RMP2_DEV void evaluate_env(const StepTables& T, const StepArgs& A, const CUtenso
             wt.phase ^= 1u;
             tile_ready = true;
           }
-          const float* gsph = A.spheres + ((size_t)env * O + tile_first) * 4;
-#pragma unroll 2
-          for (int o = 0; o < tile_count; ++o) {
-            float4 sp;
-            if (kTma) {
-              const uint32_t off = (uint32_t)(o >> 3) * 4096u + lane * 128u + ((((uint32_t)o & 7u) ^ (lane & 7u)) << 4);
-              sp = *reinterpret_cast<const float4*>(wt.base + off);
-            } else {
-              sp = __ldg(reinterpret_cast<const float4*>(gsph) + o);
-            }
+          auto one_sphere = [&](const float4 sp) {
             // pos_on_link = frame origin; pos_on_obstacle = closest surface point of the sphere
             const float rx = ch.p[0] - sp.x, ry = ch.p[1] - sp.y, rz = ch.p[2] - sp.z;
             const float dc2 = fmaxf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)), 1e-24f);
-            const float inv_dc = rsqrtf(dc2);
+            const float inv_dc = fast_rsqrt(dc2);
             const float sd = fmaf(dc2, inv_dc, -sp.w);             // signed surface distance
             const float sgn = (sd < 0.f) ? -inv_dc : inv_dc;
             const float d = fmaxf(fabsf(sd), 1e-12f);
-            obstacle_pair(L.p, rx * sgn, ry * sgn, rz * sgn, d, 1.f / d, ch.v, ch.a, vv, S, g);
+            obstacle_pair(L.p, rx * sgn, ry * sgn, rz * sgn, d, fast_rcp(d), ch.v, ch.a, vv, S, g);
+          };
+          if (kTma) {
+            // row `lane` of each staged box holds 8 spheres of this environment; the 16-byte chunk c
+            // of a row sits at chunk (c ^ (lane & 7)) (128-byte TMA swizzle) -> conflict-free LDS.128
+            const uint32_t row = wt.base32 + lane * 128u;
+            const uint32_t x7 = (lane & 7u) << 4;
+            const int nbox = tile_count >> 3;
+            for (int b = 0; b < nbox; ++b) {
+#pragma unroll
+              for (int c8 = 0; c8 < 8; ++c8) {
+                float4 sp;
+                const uint32_t addr = row + (uint32_t)b * 4096u + (((uint32_t)c8 << 4) ^ x7);
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(sp.x), "=f"(sp.y), "=f"(sp.z), "=f"(sp.w)
+                             : "r"(addr));
+                one_sphere(sp);
+              }
+            }
+          } else {
+            const float4* gsph = reinterpret_cast<const float4*>(A.spheres + ((size_t)env * O + tile_first) * 4);
+#pragma unroll 2
+            for (int o = 0; o < tile_count; ++o) one_sphere(__ldg(gsph + o));
           }
           contrib = true;
         } else {  // RMP2_SPACE_FRAME_DISTANCE_PAIRS: explicit (pos_on_link, pos_on_obstacle) pairs
@@ -198,7 +212,7 @@ RMP2_DEV void evaluate_env(const StepTables& T, const StepArgs& A, const CUtenso
             const float ry = __ldg(pp + 6 * k + 1) - __ldg(pp + 6 * k + 4);
             const float rz = __ldg(pp + 6 * k + 2) - __ldg(pp + 6 * k + 5);
             const float d2 = fmaxf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)), 1e-24f);
-            const float inv_d = rsqrtf(d2);
+            const float inv_d = fast_rsqrt(d2);
             obstacle_pair(L.p, rx * inv_d, ry * inv_d, rz * inv_d, d2 * inv_d, inv_d, ch.v, ch.a, vv, S, g);
           }
           contrib = true;
@@ -306,6 +320,7 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
   const int boxes = kTma ? min(4, (A.n_spheres + 7) >> 3) : 0;
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   wt.base = reinterpret_cast<const char*>(base + (size_t)warp * boxes * 4096);
+  wt.base32 = smem_u32(wt.base);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)warps * boxes * 4096);
   wt.bar = bars + warp;
   wt.phase = 0;

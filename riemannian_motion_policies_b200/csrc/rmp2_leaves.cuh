@@ -66,8 +66,29 @@
 #define CS_DGAIN 2
 #define CS_THRESH 3
 
-// log(1 + exp(-y)) for y >= 0
-RMP2_DEV float softplus_neg(float y) { return log1pf(expf(-y)); }
+// ---- single-instruction special functions (MUFU), used in the per-pair hot loop -----------------
+// Relative error ~1e-7 each (2 ulp); the distance leaf tolerates that: see DESIGN.md "numerics".
+RMP2_DEV float fast_rcp(float x) {                                               // MUFU.RCP, x normal
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+RMP2_DEV float fast_rsqrt(float x) {                                             // MUFU.RSQ, x normal
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+RMP2_DEV float fast_exp2(float x) {                                              // MUFU.EX2
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exp(x) = 2^(x log2e) with the rounding error of the product folded back in (x up to ~ +-90)
+RMP2_DEV float fast_exp(float x) {
+  const float t = x * 1.4426950408889634f;
+  const float e = fmaf(x, 1.4426950408889634f, -t) + x * 1.9259629911266175e-8f;   // low part
+  return fast_exp2(t) * fmaf(e, 0.6931471805599453f, 1.f);
+}
 
 // ---- metrics of the form  A = iso * I + dir * zeta zeta^T  ----------------------------------------
 // TargetPolicy  (reference: rmp.py:241-260, helper/rmp_helper.py:62-74)
@@ -145,12 +166,12 @@ RMP2_DEV void obstacle_pair(const float* __restrict__ p, float nx, float ny, flo
   const float curv = fmaf(-xdot, xdot, vv) * inv_d;
   const float c = fmaf(nx, a[0], fmaf(ny, a[1], fmaf(nz, a[2], curv)));
   const float x = fmaxf(d - p[OA_MARGIN], 0.f);                          // rmp2.py:185-186
-  const float base = p[OA_MSCALAR] / fmaf(x, p[OA_INV_ESTD], p[OA_EEPS]);   // rmp2.py:187
+  const float base = p[OA_MSCALAR] * fast_rcp(fmaf(x, p[OA_INV_ESTD], p[OA_EEPS]));   // rmp2.py:187
   const float gt = fmaf(x, p[OA_INV_R], -1.f);
   const float gate = gt * gt;                                            // rmp2.py:172
-  const float rep = p[OA_RGAIN] * expf(-x * p[OA_INV_RSTD]);             // rmp2.py:189
-  const float one_minus_sig = 1.f / (1.f + expf(xdot * p[OA_INV_VLEN])); // 1 - sigmoid  rmp2.py:190
-  const float damp = -one_minus_sig * p[OA_DGAIN] * xdot / fmaf(x, p[OA_INV_DSTD], p[OA_DEPS]);  // :191
+  const float rep = p[OA_RGAIN] * fast_exp(-x * p[OA_INV_RSTD]);         // rmp2.py:189
+  const float one_minus_sig = fast_rcp(1.f + fast_exp(xdot * p[OA_INV_VLEN]));   // 1 - sigmoid  rmp2.py:190
+  const float damp = -one_minus_sig * p[OA_DGAIN] * xdot * fast_rcp(fmaf(x, p[OA_INV_DSTD], p[OA_DEPS]));  // :191
   const float acc = rep + damp;
   const float m = (x > p[OA_R]) ? 0.f : one_minus_sig * base * gate;     // rmp2.py:194
   const float h = m * (acc - c);

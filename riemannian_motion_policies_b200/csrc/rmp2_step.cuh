@@ -230,9 +230,9 @@ RMP2_DEV void resolve_pinv(float (&G)[N][N], float (&y)[N], float rcond, float (
         // to row scaling, so the approximate intrinsics only affect the convergence rate.
         const float tau = b - a;
         const float hyp2 = fmaf(tau, tau, 4.f * g2);
-        const float hyp = hyp2 * rsqrtf(fmaxf(hyp2, 1e-37f));
-        const float t = __fdividef((tau < 0.f) ? -2.f * g : 2.f * g, fabsf(tau) + hyp);
-        float c = rsqrtf(fmaf(t, t, 1.f));
+        const float hyp = hyp2 * fast_rsqrt(fmaxf(hyp2, 1e-37f));
+        const float t = ((tau < 0.f) ? -2.f * g : 2.f * g) * fast_rcp(fmaxf(fabsf(tau) + hyp, 1e-37f));
+        float c = fast_rsqrt(fmaf(t, t, 1.f));
         float s = c * t;
         const float tg = rot ? t * g : 0.f;          // sign(t g) = sign(b - a): the larger row gains
         c = rot ? c : 1.f;
