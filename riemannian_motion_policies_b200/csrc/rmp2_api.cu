@@ -137,6 +137,8 @@ static int derive_leaf_params(const rmp2_leaf_desc& d, int n, LeafTab& L, float*
       L.p[OA_MSCALAR] = r[8];
       L.p[OA_INV_ESTD] = (float)(1.0 / (double)r[9]);
       L.p[OA_EEPS] = r[10];
+      L.p[OA_K_REP] = (float)(-1.4426950408889634 / (double)r[6]);
+      L.p[OA_K_VEL] = (float)(1.4426950408889634 / (double)r[4]);
       break;
     case RMP2_LEAF_CSPACE_BIASING:
       L.p[CS_METRIC] = (float)((double)r[0] + (double)r[4]);   // rmp2.py:224
@@ -196,6 +198,10 @@ static void fill_frame(const rmp2_robot& rb, int k, FrameTab& ft) {
   ft.anc_mask = 0;
   ft.leaf_begin = ft.leaf_end = 0;
   ft.ref_index = k;
+  bool ident = true;
+  for (int i = 0; i < 9; ++i) ident = ident && (ft.R[i] == ((i % 4 == 0) ? 1.f : 0.f));
+  ft.const_rot_identity = ident ? 1 : 0;
+  ft.axis_is_z = (ft.axis[0] == 0.f && ft.axis[1] == 0.f && ft.axis[2] == 1.f) ? 1 : 0;
 }
 
 static uint32_t ancestor_mask(const rmp2_robot& rb, int k) {

@@ -186,11 +186,12 @@ RMP2_DEV void evaluate_env(const StepTables& T, const StepArgs& A, const CUtenso
             const uint32_t row = wt.base32 + lane * 128u;
             const uint32_t x7 = (lane & 7u) << 4;
             const int nbox = tile_count >> 3;
-            for (int b = 0; b < nbox; ++b) {
-#pragma unroll
-              for (int c8 = 0; c8 < 8; ++c8) {
+            for (int hb = 0; hb < 2 * nbox; ++hb) {          // half a box (4 spheres) per trip: the
+#pragma unroll                                               // unrolled body stays inside the L0 I-cache
+              for (int c4 = 0; c4 < 4; ++c4) {
                 float4 sp;
-                const uint32_t addr = row + (uint32_t)b * 4096u + (((uint32_t)c8 << 4) ^ x7);
+                const uint32_t c8 = (uint32_t)(hb & 1) * 4u + (uint32_t)c4;
+                const uint32_t addr = row + (uint32_t)(hb >> 1) * 4096u + ((c8 << 4) ^ x7);
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                              : "=f"(sp.x), "=f"(sp.y), "=f"(sp.z), "=f"(sp.w)
                              : "r"(addr));
@@ -342,26 +343,28 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
     qdd[j] = 0.f;
   }
 
-  if (A.n_sim_steps <= 0) {
-    evaluate_env<N, kTma>(T, A, &tmap, env, warp_env0, q, qd, slots, wt, qdd);
-  } else {
-    // closed-loop rollout: explicit Euler at dt, control every `control_every` steps
-    for (int step = 0; step < A.n_sim_steps; ++step) {
-      if (step % A.control_every == 0) evaluate_env<N, kTma>(T, A, &tmap, env, warp_env0, q, qd, slots, wt, qdd);
+  // One call site (one inlined copy of the step): a plain step is a rollout of one control step
+  // without integration.  Closed-loop rollout = explicit Euler at dt, control every `control_every`.
+  const bool rollout = A.n_sim_steps > 0;
+  const int n_steps = rollout ? A.n_sim_steps : 1;
+  for (int step = 0; step < n_steps; ++step) {
+    if (!rollout || step % A.control_every == 0)
+      evaluate_env<N, kTma>(T, A, &tmap, env, warp_env0, q, qd, slots, wt, qdd);
+    if (rollout) {
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         qd[j] = fmaf(qdd[j], A.dt, qd[j]);
         q[j] = fmaf(qd[j], A.dt, q[j]);
       }
     }
-    if (active) {
+  }
+  if (rollout && active) {
 #pragma unroll
-      for (int j = 0; j < N; ++j)
-        if (j < n) {
-          A.q_rw[env * n + j] = q[j];
-          A.qd_rw[env * n + j] = qd[j];
-        }
-    }
+    for (int j = 0; j < N; ++j)
+      if (j < n) {
+        A.q_rw[env * n + j] = q[j];
+        A.qd_rw[env * n + j] = qd[j];
+      }
   }
   if (active) {
 #pragma unroll

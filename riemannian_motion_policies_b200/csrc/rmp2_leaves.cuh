@@ -60,6 +60,8 @@
 #define OA_DGAIN 9
 #define OA_INV_DSTD 10
 #define OA_DEPS 11
+#define OA_K_REP 12       // -log2(e) / repulsion_std_dev
+#define OA_K_VEL 13       //  log2(e) / damping_velocity_gate_length_scale
 // CSPACE_BIASING
 #define CS_METRIC 0
 #define CS_PGAIN 1
@@ -169,8 +171,8 @@ RMP2_DEV void obstacle_pair(const float* __restrict__ p, float nx, float ny, flo
   const float base = p[OA_MSCALAR] * fast_rcp(fmaf(x, p[OA_INV_ESTD], p[OA_EEPS]));   // rmp2.py:187
   const float gt = fmaf(x, p[OA_INV_R], -1.f);
   const float gate = gt * gt;                                            // rmp2.py:172
-  const float rep = p[OA_RGAIN] * fast_exp(-x * p[OA_INV_RSTD]);         // rmp2.py:189
-  const float one_minus_sig = fast_rcp(1.f + fast_exp(xdot * p[OA_INV_VLEN]));   // 1 - sigmoid  rmp2.py:190
+  const float rep = p[OA_RGAIN] * fast_exp2(x * p[OA_K_REP]);            // rmp2.py:189
+  const float one_minus_sig = fast_rcp(1.f + fast_exp2(xdot * p[OA_K_VEL]));     // 1 - sigmoid  rmp2.py:190
   const float damp = -one_minus_sig * p[OA_DGAIN] * xdot * fast_rcp(fmaf(x, p[OA_INV_DSTD], p[OA_DEPS]));  // :191
   const float acc = rep + damp;
   const float m = (x > p[OA_R]) ? 0.f : one_minus_sig * base * gate;     // rmp2.py:194
@@ -192,8 +194,8 @@ RMP2_DEV void obstacle_scalar(const float* __restrict__ p, float xin, float xdot
   const float x = fmaxf(xin - p[OA_MARGIN], 0.f);
   const float base = p[OA_MSCALAR] / fmaf(x, p[OA_INV_ESTD], p[OA_EEPS]);
   const float gt = fmaf(x, p[OA_INV_R], -1.f);
-  const float rep = p[OA_RGAIN] * expf(-x * p[OA_INV_RSTD]);
-  const float one_minus_sig = 1.f / (1.f + expf(xdot * p[OA_INV_VLEN]));
+  const float rep = p[OA_RGAIN] * fast_exp2(x * p[OA_K_REP]);
+  const float one_minus_sig = 1.f / (1.f + fast_exp2(xdot * p[OA_K_VEL]));
   const float damp = -one_minus_sig * p[OA_DGAIN] * xdot / fmaf(x, p[OA_INV_DSTD], p[OA_DEPS]);
   xdd = rep + damp;
   M = (x > p[OA_R]) ? 0.f : one_minus_sig * base * (gt * gt);

@@ -48,7 +48,12 @@ RMP2_DEV void matmul3(const float* A, const float* B, float* C) {
 RMP2_DEV void chain_advance(Chain& c, const FrameTab& F, float qi, float qdi, float (&z)[3]) {
   float rho[3], Rc[9];
   matvec3(c.R, F.t, rho);                       // offset parent origin -> joint origin, world
-  matmul3(c.R, F.R, Rc);
+  if (F.const_rot_identity) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rc[i] = c.R[i];
+  } else {
+    matmul3(c.R, F.R, Rc);
+  }
   z[0] = z[1] = z[2] = 0.f;
   if (F.type != RMP2_JOINT_FIXED) matvec3(Rc, F.axis, z);
   if (F.type == RMP2_JOINT_PRISMATIC) {         // T_var = translation q * axis  (kinematics.py:231-233)
@@ -77,19 +82,29 @@ RMP2_DEV void chain_advance(Chain& c, const FrameTab& F, float qi, float qdi, fl
   if (F.type == RMP2_JOINT_REVOLUTE) {          // Rodrigues, unit axis (kinematics.py:99-121)
     float s, co;
     sincosf(qi, &s, &co);
-    const float t = 1.f - co;
-    const float ux = F.axis[0], uy = F.axis[1], uz = F.axis[2];
-    float Rv[9];
-    Rv[0] = fmaf(t * ux, ux, co);
-    Rv[1] = fmaf(t * ux, uy, -s * uz);
-    Rv[2] = fmaf(t * ux, uz, s * uy);
-    Rv[3] = fmaf(t * uy, ux, s * uz);
-    Rv[4] = fmaf(t * uy, uy, co);
-    Rv[5] = fmaf(t * uy, uz, -s * ux);
-    Rv[6] = fmaf(t * uz, ux, -s * uy);
-    Rv[7] = fmaf(t * uz, uy, s * ux);
-    Rv[8] = fmaf(t * uz, uz, co);
-    matmul3(Rc, Rv, c.R);
+    if (F.axis_is_z) {                           // R_new = Rc * R_z(q): mixes columns 0 and 1
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float a0 = Rc[3 * r], a1 = Rc[3 * r + 1];
+        c.R[3 * r] = fmaf(co, a0, s * a1);
+        c.R[3 * r + 1] = fmaf(co, a1, -s * a0);
+        c.R[3 * r + 2] = Rc[3 * r + 2];
+      }
+    } else {
+      const float t = 1.f - co;
+      const float ux = F.axis[0], uy = F.axis[1], uz = F.axis[2];
+      float Rv[9];
+      Rv[0] = fmaf(t * ux, ux, co);
+      Rv[1] = fmaf(t * ux, uy, -s * uz);
+      Rv[2] = fmaf(t * ux, uz, s * uy);
+      Rv[3] = fmaf(t * uy, ux, s * uz);
+      Rv[4] = fmaf(t * uy, uy, co);
+      Rv[5] = fmaf(t * uy, uz, -s * ux);
+      Rv[6] = fmaf(t * uz, ux, -s * uy);
+      Rv[7] = fmaf(t * uz, uy, s * ux);
+      Rv[8] = fmaf(t * uz, uz, co);
+      matmul3(Rc, Rv, c.R);
+    }
     float wz[3];
     cross3(c.w, z, wz);                          // uses the parent's angular velocity
 #pragma unroll

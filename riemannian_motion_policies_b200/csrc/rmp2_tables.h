@@ -24,6 +24,8 @@ struct FrameTab {
   int32_t leaf_begin;    // leaves attached to this frame: [leaf_begin, leaf_end)
   int32_t leaf_end;
   int32_t ref_index;     // index in the reference's frame order (for diagnostics)
+  int32_t const_rot_identity;  // R == I: skip the constant-rotation product
+  int32_t axis_is_z;           // axis == (0,0,1): the joint rotation only mixes two columns
 };
 
 struct LeafTab {
