@@ -249,6 +249,8 @@ def run_b200_arm(args):
     for i in range(max(3, args.warmup)):
         step(i)
     barrier()
+    tree.profile(True)                      # CUDA events around every kernel launch of the timed region
+    tree.profile_read()
     launches0 = _native.launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
@@ -260,6 +262,8 @@ def run_b200_arm(args):
         barrier()
     elapsed_ms = start.elapsed_time(stop)
     launches = _native.launch_count() - launches0
+    kernel_ms = tree.profile_read()         # {kernel: (total ms, launches)} on this rank
+    tree.profile(False)
     if world > 1:
         t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -323,10 +327,24 @@ def run_b200_arm(args):
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
-        info = tree.kernel_info()
+        info = tree.kernel_info(O_ if O_ else 64)
         t_s = ms_per_step * 1e-3
         gbs = BYTES_PER_ENV[config] * B / t_s / 1e9
         tflops = FLOPS_PER_ENV[config] * B / t_s / 1e12
+        # dominant kernel: the obstacle pair loop when the tree has obstacles, else the step kernel
+        dom = "spheres" if O_ else "step"
+        n_slots = len(S.collision_frames(fk)) if O_ else 0
+        dom_ms = kernel_ms[dom][0] / max(1, kernel_ms[dom][1])
+        total_kernel_ms = sum(v[0] for v in kernel_ms.values()) / args.steps
+        # algorithmic bytes / flops of one launch of the dominant kernel
+        if O_:
+            dom_bytes = B * (16.0 * O_ + 2 * 48.0 * n_slots)       # spheres in, frame records in, (S,g) records out
+            dom_flops = B * 76.0 * O_ * n_slots                    # SURVEY.md 8d term C
+        else:
+            dom_bytes = B * BYTES_PER_ENV[config]
+            dom_flops = B * FLOPS_PER_ENV[config]
+        dom_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
+        dom_tflops = dom_flops / (dom_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -335,14 +353,20 @@ def run_b200_arm(args):
                        "dof": n, "parallelism": f"env-sharded x{world}, no step-path collective",
                        "l2_policy": f"inputs larger than L2: {n_buffers} rotating sphere buffers of "
                                     f"{B * O_ * 16 / 1e6:.0f} MB each" if O_ else "q/qd/goal re-read each step"},
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
-                         "bytes_per_env_step": BYTES_PER_ENV[config],
-                         "note": "the kernel is FP32/MUFU-issue bound by design (see roofline_fp32); HBM fraction is "
-                                 "reported because the contract's bounds are hbm|tensor"},
-            "roofline_fp32": {"bound": "fp32", "achieved": tflops, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-                              "frac": tflops / FP32_PEAK_TFLOPS, "flops_per_env_step": FLOPS_PER_ENV[config],
+            "roofline": {"bound": "hbm", "kernel": f"rmp2_{dom}_kernel", "achieved": dom_gbs, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": dom_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                         "kernel_ms_per_launch": dom_ms, "kernel_share_of_step": dom_ms / max(total_kernel_ms, 1e-12),
+                         "algorithmic_bytes_per_launch": dom_bytes,
+                         "note": "this path is FP32/MUFU-issue bound by design, not HBM bound (see roofline_fp32); the "
+                                 "HBM figure is given because the contract's bounds are hbm|tensor"},
+            "roofline_fp32": {"bound": "fp32", "kernel": f"rmp2_{dom}_kernel", "achieved": dom_tflops,
+                              "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": dom_tflops / FP32_PEAK_TFLOPS,
+                              "algorithmic_flops_per_launch": dom_flops,
+                              "whole_step": {"achieved": tflops, "frac": tflops / FP32_PEAK_TFLOPS,
+                                             "flops_per_env_step": FLOPS_PER_ENV[config],
+                                             "hbm_gbs": gbs, "bytes_per_env_step": BYTES_PER_ENV[config]},
                               "peak_source": "analytic 148 SM x 128 lanes x 2 x 1.965 GHz"},
+            "kernel_ms": {k: {"ms_per_step": v[0] / args.steps, "launches": int(v[1])} for k, v in kernel_ms.items()},
             "per_gpu_value": per_gpu, "gpu_launches": int(launches), "kernel": info, "clocks": clocks.summary(),
             "e2e": e2e, "cpu_baseline": cpu_baseline, "parity": parity,
         }

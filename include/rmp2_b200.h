@@ -140,7 +140,11 @@ int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* 
 /* ---- the hot path ------------------------------------------------------------------------ */
 
 /* qdd = pinv(sum_l J_l^T M_l J_l) * sum_l J_l^T M_l (xdd_l - Jdot_l qd) for B environments.
- * Stands in for RmpCore.evaluate (rmp.py:133-155).  All io pointers are device memory. */
+ * Stands in for RmpCore.evaluate (rmp.py:133-155).  All io pointers are device memory.
+ * Launches up to three kernels on `stream` (frames -> spheres -> step).  The tree handle owns a
+ * scratch buffer for the per-(environment, obstacle leaf) records (48 B each, at most 2^20
+ * environments at a time) that is allocated on first use and grown when needed; therefore the steps
+ * of ONE tree must be issued from one thread on one stream at a time. */
 int rmp2_step(const rmp2_tree* tree, const rmp2_step_io* io, void* stream);
 
 /* Same step with HOST buffers: every io pointer is host memory (pinned for full overlap);
@@ -149,7 +153,7 @@ int rmp2_step(const rmp2_tree* tree, const rmp2_step_io* io, void* stream);
 int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io);
 
 /* Closed-loop rollout: `n_steps` simulation steps of explicit Euler
- * (qd += qdd*dt; q += qd*dt), re-evaluating the tree every `control_every` steps
+ * (qd += qdd*dt; q += qd*dt), re-evaluating the tree every `control_every` steps (command held in between)
  * (the 100 Hz / 10 Hz loop of experiments/franka_panda/05_obstacle_avoidance.py:92-97 with
  * simulation.step replaced by an integrator).  q and qd are updated in place; io->qdd receives
  * the last command. */
@@ -174,9 +178,16 @@ const char* rmp2_last_error(void);
 const char* rmp2_version(void);
 /* kernels launched by this library in this process so far (bench.py's gpu_launches) */
 int64_t rmp2_launch_count(void);
-/* registers/thread, static smem and max active blocks/SM of the step kernel the tree uses */
-int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t* regs, int32_t* smem_bytes,
-                          int32_t* blocks_per_sm, int32_t* block_threads);
+/* registers/thread, dynamic shared memory, max resident blocks/SM and block size of one of the
+ * kernels a step launches: which = 0 frames (chain -> frame records), 1 spheres (the obstacle
+ * pair loop; n_spheres selects the staging layout), 2 step (pullback + leaves + resolve). */
+int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_spheres, int32_t* regs,
+                          int32_t* smem_bytes, int32_t* blocks_per_sm, int32_t* block_threads);
+/* Per-kernel device timing with CUDA events on the launching stream (bench.py's roofline leg).
+ * rmp2_tree_profile_read waits for the recorded launches, returns the accumulated milliseconds and
+ * launch counts of {frames, spheres, step} since the last read, and resets them. */
+int rmp2_tree_profile(rmp2_tree* tree, int32_t enable);
+int rmp2_tree_profile_read(rmp2_tree* tree, double* ms /*[3]*/, int64_t* launches /*[3]*/);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,7 @@ EXPORTS = [
     "rmp2_robot_create", "rmp2_robot_destroy", "rmp2_tree_create", "rmp2_tree_destroy",
     "rmp2_tree_update_leaf", "rmp2_step", "rmp2_step_host", "rmp2_rollout", "rmp2_fk",
     "rmp2_leaf_evaluate", "rmp2_last_error", "rmp2_version", "rmp2_launch_count",
-    "rmp2_tree_kernel_info",
+    "rmp2_tree_kernel_info", "rmp2_tree_profile", "rmp2_tree_profile_read",
 ]
 
 
@@ -113,9 +113,13 @@ def lib():
     L.rmp2_version.restype = ctypes.c_char_p
     L.rmp2_launch_count.argtypes = []
     L.rmp2_launch_count.restype = i64
-    L.rmp2_tree_kernel_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32),
+    L.rmp2_tree_kernel_info.argtypes = [vp, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32),
                                         ctypes.POINTER(i32)]
     L.rmp2_tree_kernel_info.restype = ctypes.c_int
+    L.rmp2_tree_profile.argtypes = [vp, i32]
+    L.rmp2_tree_profile.restype = ctypes.c_int
+    L.rmp2_tree_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
+    L.rmp2_tree_profile_read.restype = ctypes.c_int
     _lib = L
     return L
 

@@ -45,14 +45,27 @@ struct HostStage {                // device staging for rmp2_step_host, one per 
   cudaStream_t stream = nullptr;
 };
 
+struct KernelClock {              // optional per-kernel timing (rmp2_tree_profile)
+  std::vector<cudaEvent_t> pending;   // (start, stop) pairs not yet read
+  double ms = 0.0;
+  long long launches = 0;
+};
+
 struct rmp2_tree {
   StepTables tab;
   std::vector<rmp2_leaf_desc> leaves;     // as given, tree order
   std::vector<int> table_index;           // tree order -> index in tab.leaves
   int n_pair_sets = 0;
   int n_goal_slots_used = 0;
+  SphereTables sph;                       // parameters of the sphere-obstacle leaves, by record slot
+  float* rec = nullptr;                   // [chunk][n_sphere_slots][12] scratch of rmp2_step
+  size_t rec_floats = 0;
+  bool profiling = false;
+  KernelClock clock[3];                   // frames, spheres, step
   HostStage stage[3];
 };
+
+#define RMP2_STEP_CHUNK (1LL << 20)       // environments per internal chunk (bounds the scratch)
 
 // ------------------------------------------------------------------------------ parameter derivation
 // Raw constructor arguments (layout in include/rmp2_b200.h) -> kernel parameters (rmp2_leaves.cuh).
@@ -288,6 +301,7 @@ int rmp2_tree_create(const rmp2_robot* rb, const rmp2_leaf_desc* leaves, int32_t
     if (leaves[i].goal_slot >= 0) goal_slots = std::max(goal_slots, leaves[i].goal_slot + 1);
     if (leaves[i].space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) T.uses_spheres = 1;
   }
+  memset(&tr->sph, 0, sizeof(SphereTables));
   if (pair_sets > RMP2_MAX_PAIR_SETS) { delete tr; return fail(RMP2_ERR_UNSUPPORTED, "too many explicit-pair leaves"); }
   tr->n_pair_sets = pair_sets;
   tr->n_goal_slots_used = goal_slots;
@@ -297,10 +311,15 @@ int rmp2_tree_create(const rmp2_robot* rb, const rmp2_leaf_desc* leaves, int32_t
     L.space = leaves[i].space;
     L.goal_slot = leaves[i].goal_slot;
     L.pair_set = pair_set_of[i];
+    L.sphere_slot = -1;
     float vec[3 * RMP2_MAX_JOINTS];
     int vlen = 0;
     int rc = derive_leaf_params(leaves[i], rb->n, L, vec, &vlen);
     if (rc != RMP2_OK) return rc;
+    if (L.space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) {
+      L.sphere_slot = T.n_sphere_slots++;
+      for (int j = 0; j < RMP2_LEAF_PARAMS; ++j) tr->sph.p[L.sphere_slot][j] = L.p[j];
+    }
     if (vec_cursor + vlen > RMP2_VECPOOL) return fail(RMP2_ERR_UNSUPPORTED, "vector-parameter pool exhausted");
     L.vec_off = vec_cursor;
     for (int j = 0; j < vlen; ++j) T.vecpool[vec_cursor + j] = vec[j];
@@ -352,6 +371,13 @@ int rmp2_tree_create(const rmp2_robot* rb, const rmp2_leaf_desc* leaves, int32_t
       if (rc != RMP2_OK) { delete tr; return rc; }
     }
   T.n_leaves = leaf_cursor;
+  tr->sph.n_slots = T.n_sphere_slots;
+  if (T.n_sphere_slots > 0) {
+    // E environments per block: E * L threads <= 128, E <= 32 (box rows), shared memory bounded
+    int E = RMP2_BLOCK_THREADS / T.n_sphere_slots;
+    E = std::max(1, std::min(E, 32));
+    tr->sph.envs_per_block = E;
+  }
   *out = tr;
   return RMP2_OK;
 }
@@ -362,6 +388,9 @@ void rmp2_tree_destroy(rmp2_tree* tree) {
     if (s.buf) cudaFree(s.buf);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
+  if (tree->rec) cudaFree(tree->rec);
+  for (auto& c : tree->clock)
+    for (auto ev : c.pending) cudaEventDestroy(ev);
   delete tree;
 }
 
@@ -377,6 +406,8 @@ int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* 
   int rc = derive_leaf_params(*leaf, tree->tab.n, L, vec, &vlen);
   if (rc != RMP2_OK) return rc;
   for (int j = 0; j < vlen; ++j) tree->tab.vecpool[L.vec_off + j] = vec[j];
+  if (L.sphere_slot >= 0)
+    for (int j = 0; j < RMP2_LEAF_PARAMS; ++j) tree->sph.p[L.sphere_slot][j] = L.p[j];
   tree->leaves[index] = *leaf;
   return RMP2_OK;
 }
@@ -403,39 +434,51 @@ PFN_tmapEncodeTiled get_encode_fn() {
   return fn;
 }
 
-struct LaunchPlan {
-  bool use_tma = false;
-  int block = RMP2_BLOCK_THREADS;
-  size_t smem = 0;
-  CUtensorMap tmap;
-};
+int pick_block(long long B) {
+  return (B >= 148LL * 4 * 128) ? 128 : (B >= 148LL * 4 * 64 ? 64 : 32);
+}
 
-int plan_step(const StepTables& T, const StepArgs& A, LaunchPlan& P) {
-  memset(&P.tmap, 0, sizeof(P.tmap));
-  const long long B = A.B;
-  P.block = (B >= 148LL * 4 * 128) ? 128 : (B >= 148LL * 4 * 64 ? 64 : 32);
+bool tma_eligible(const rmp2_tree* tree, const StepArgs& A) {
   const int O = A.n_spheres;
-  P.use_tma = T.uses_spheres && O > 0 && (O % 8) == 0 && A.spheres != nullptr &&
-              ((uintptr_t)A.spheres % 16) == 0 && B < (1LL << 31);
-  if (getenv("RMP2_DISABLE_TMA")) P.use_tma = false;
-  if (P.use_tma) {
-    PFN_tmapEncodeTiled enc = get_encode_fn();
-    if (!enc) return fail(RMP2_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    const cuuint64_t gdim[2] = {(cuuint64_t)O * 4, (cuuint64_t)B};
-    const cuuint64_t gstride[1] = {(cuuint64_t)O * 16};
-    const cuuint32_t box[2] = {32, 32};
-    const cuuint32_t estride[2] = {1, 1};
-    CUresult r = enc(&P.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A.spheres), gdim, gstride, box,
-                     estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(RMP2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-  }
-  const int warps = P.block / 32;
-  const int boxes = P.use_tma ? std::min(4, (O + 7) / 8) : 0;
-  P.smem = 1024 + (size_t)warps * boxes * 4096 + (size_t)warps * 8 +
-           (size_t)T.n_slots * RMP2_CHAIN_FLOATS * P.block * sizeof(float);
+  if (getenv("RMP2_DISABLE_TMA")) return false;
+  const size_t smem = rmp2_spheres_smem(tree->sph, O, true);
+  return O > 0 && (O % 8) == 0 && A.spheres != nullptr && ((uintptr_t)A.spheres % 16) == 0 &&
+         A.B < (1LL << 31) && smem <= 200 * 1024;
+}
+
+int encode_sphere_map(const rmp2_tree* tree, const StepArgs& A, CUtensorMap* tmap) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  if (!enc) return fail(RMP2_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const int O = A.n_spheres;
+  const cuuint64_t gdim[2] = {(cuuint64_t)O * 4, (cuuint64_t)A.B};
+  const cuuint64_t gstride[1] = {(cuuint64_t)O * 16};
+  const cuuint32_t box[2] = {32, (cuuint32_t)tree->sph.envs_per_block};   // 8 spheres x E environments
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A.spheres), gdim, gstride, box,
+                   estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RMP2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
   return RMP2_OK;
 }
+
+struct ScopedClock {               // brackets one launch with events when profiling is on
+  KernelClock* c = nullptr;
+  cudaStream_t stream;
+  cudaEvent_t stop = nullptr;
+  ScopedClock(rmp2_tree* tree, int which, cudaStream_t s) : stream(s) {
+    if (!tree->profiling) return;
+    c = &tree->clock[which];
+    cudaEvent_t start;
+    cudaEventCreate(&start);
+    cudaEventCreate(&stop);
+    cudaEventRecord(start, stream);
+    c->pending.push_back(start);
+    c->pending.push_back(stop);
+  }
+  ~ScopedClock() {
+    if (c) cudaEventRecord(stop, stream);
+  }
+};
 
 int build_args(const rmp2_tree* tree, const rmp2_step_io* io, StepArgs& A) {
   if (!tree || !io) return fail(RMP2_ERR_INVALID, "null argument");
@@ -472,14 +515,80 @@ int build_args(const rmp2_tree* tree, const rmp2_step_io* io, StepArgs& A) {
   return RMP2_OK;
 }
 
-int launch(const rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
+// One control step over A.B environments on `stream`, with `rec` as scratch for the sphere records.
+int launch_chunk(rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
   if (A.B == 0) return RMP2_OK;
-  LaunchPlan P;
-  int rc = plan_step(tree->tab, A, P);
-  if (rc != RMP2_OK) return rc;
-  cudaError_t e = rmp2_launch_step(tree->tab, A, &P.tmap, P.use_tma, P.block, P.smem, stream);
-  if (e != cudaSuccess) return cuda_fail(e, "rmp2_step launch");
+  const StepTables& T = tree->tab;
+  const int block = pick_block(A.B);
+  cudaError_t e;
+  if (T.n_sphere_slots > 0 && A.n_spheres > 0) {
+    {
+      ScopedClock clk(tree, 0, stream);
+      e = rmp2_launch_frames(T, A, block, stream);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "rmp2_frames_kernel launch");
+    const bool use_tma = tma_eligible(tree, A);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (use_tma) {
+      int rc = encode_sphere_map(tree, A, &tmap);
+      if (rc != RMP2_OK) return rc;
+    }
+    {
+      ScopedClock clk(tree, 1, stream);
+      e = rmp2_launch_spheres(tree->sph, A, &tmap, use_tma, stream);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "rmp2_spheres_kernel launch");
+    g_launches.fetch_add(2);
+  }
+  {
+    ScopedClock clk(tree, 2, stream);
+    e = rmp2_launch_step(T, A, block, stream);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "rmp2_step_kernel launch");
   g_launches.fetch_add(1);
+  return RMP2_OK;
+}
+
+size_t rec_floats_for(const rmp2_tree* tree, long long B, int n_spheres) {
+  if (tree->tab.n_sphere_slots == 0 || n_spheres <= 0) return 0;
+  return (size_t)B * tree->tab.n_sphere_slots * RMP2_REC_FLOATS;
+}
+
+// Device-pointer step, chunked so that the scratch stays bounded.
+int launch(rmp2_tree* tree, const StepArgs& A0, cudaStream_t stream) {
+  const long long B = A0.B;
+  if (B == 0) return RMP2_OK;
+  const long long chunk = std::min<long long>(B, RMP2_STEP_CHUNK);
+  const size_t need = rec_floats_for(tree, chunk, A0.n_spheres);
+  if (need > tree->rec_floats) {
+    if (tree->rec) {
+      cudaError_t e = cudaDeviceSynchronize();      // earlier steps may still use the old scratch
+      if (e != cudaSuccess) return cuda_fail(e, "synchronize before growing the scratch");
+      cudaFree(tree->rec);
+      tree->rec = nullptr;
+      tree->rec_floats = 0;
+    }
+    cudaError_t e = cudaMalloc(&tree->rec, need * sizeof(float));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc of the sphere-record scratch");
+    tree->rec_floats = need;
+  }
+  const int n = tree->tab.n;
+  for (long long e0 = 0; e0 < B; e0 += chunk) {
+    StepArgs A = A0;
+    A.B = std::min(chunk, B - e0);
+    A.q = A0.q + e0 * n;
+    A.qd = A0.qd + e0 * n;
+    A.qdd = A0.qdd + e0 * n;
+    if (A0.q_rw) A.q_rw = A0.q_rw + e0 * n;
+    if (A0.qd_rw) A.qd_rw = A0.qd_rw + e0 * n;
+    if (A0.goals) A.goals = A0.goals + e0 * A0.n_goal_slots * 3;
+    if (A0.spheres) A.spheres = A0.spheres + e0 * (long long)A0.n_spheres * 4;
+    if (A0.pairs) A.pairs = A0.pairs + e0 * (long long)A0.pair_total * 6;
+    A.rec = tree->rec;
+    int rc = launch_chunk(tree, A, stream);
+    if (rc != RMP2_OK) return rc;
+  }
   return RMP2_OK;
 }
 
@@ -491,7 +600,8 @@ int rmp2_step(const rmp2_tree* tree, const rmp2_step_io* io, void* stream) {
   StepArgs A;
   int rc = build_args(tree, io, A);
   if (rc != RMP2_OK) return rc;
-  return launch(tree, A, (cudaStream_t)stream);
+  // the handle owns scratch that grows on demand: steps of one tree are serialised by the caller
+  return launch(const_cast<rmp2_tree*>(tree), A, (cudaStream_t)stream);
 }
 
 int rmp2_rollout(const rmp2_tree* tree, const rmp2_step_io* io, float* q_inout, float* qd_inout, float dt,
@@ -507,9 +617,13 @@ int rmp2_rollout(const rmp2_tree* tree, const rmp2_step_io* io, float* q_inout, 
   A.q_rw = q_inout;
   A.qd_rw = qd_inout;
   A.dt = dt;
-  A.n_sim_steps = n_steps;
-  A.control_every = control_every;
-  return launch(tree, A, (cudaStream_t)stream);
+  // control step + `control_every` held-command Euler sub-steps, repeated; all asynchronous
+  for (int done = 0; done < n_steps; done += control_every) {
+    A.n_sim_steps = std::min(control_every, n_steps - done);
+    rc = launch(const_cast<rmp2_tree*>(tree), A, (cudaStream_t)stream);
+    if (rc != RMP2_OK) return rc;
+  }
+  return RMP2_OK;
 }
 
 int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io) {
@@ -531,7 +645,8 @@ int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io) {
   const size_t off_goal = off_qdd + pad4((size_t)chunk * n);
   const size_t off_sph = off_goal + pad4((size_t)chunk * G * 3);
   const size_t off_pair = off_sph + pad4((size_t)chunk * O * 4);
-  const size_t total = off_pair + pad4((size_t)chunk * K * 6);
+  const size_t off_rec = off_pair + pad4((size_t)chunk * K * 6);
+  const size_t total = off_rec + pad4(rec_floats_for(tree, chunk, O));
   for (auto& s : tree->stage) {
     if (!s.stream) {
       cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
@@ -570,7 +685,8 @@ int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io) {
     A.goals = G ? s.buf + off_goal : nullptr;
     A.spheres = O ? s.buf + off_sph : nullptr;
     A.pairs = K ? s.buf + off_pair : nullptr;
-    rc = launch(tree, A, s.stream);
+    A.rec = s.buf + off_rec;
+    rc = launch_chunk(tree, A, s.stream);
     if (rc != RMP2_OK) return rc;
     e = cudaMemcpyAsync(io->qdd + e0 * n, s.buf + off_qdd, (size_t)cb * n * sizeof(float), cudaMemcpyDeviceToHost, s.stream);
     if (e != cudaSuccess) return cuda_fail(e, "D2H copy");
@@ -630,25 +746,55 @@ int rmp2_leaf_evaluate(const rmp2_leaf_desc* leaf, int32_t m, int64_t K, const f
   return RMP2_OK;
 }
 
-int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t* regs, int32_t* smem_bytes, int32_t* blocks_per_sm,
-                          int32_t* block_threads) {
+int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_spheres, int32_t* regs, int32_t* smem_bytes,
+                          int32_t* blocks_per_sm, int32_t* block_threads) {
   if (!tree) return fail(RMP2_ERR_INVALID, "null argument");
-  StepArgs A;
-  memset(&A, 0, sizeof(A));
-  A.B = 1 << 20;
-  A.n_spheres = tree->tab.uses_spheres ? 64 : 0;
-  const bool use_tma = tree->tab.uses_spheres != 0;
-  const int block = RMP2_BLOCK_THREADS;
-  const int warps = block / 32;
-  const size_t smem = 1024 + (size_t)warps * (use_tma ? 4 : 0) * 4096 + (size_t)warps * 8 +
-                      (size_t)tree->tab.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
-  int r = 0, ss = 0, bps = 0;
-  cudaError_t e = rmp2_step_attributes(tree->tab.n, use_tma, block, smem, &r, &ss, &bps);
+  if (which < 0 || which > 2) return fail(RMP2_ERR_INVALID, "which must be 0 (frames), 1 (spheres) or 2 (step)");
+  int block = RMP2_BLOCK_THREADS;
+  size_t smem = (size_t)tree->tab.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
+  bool use_tma = false;
+  if (which == 1) {
+    if (tree->tab.n_sphere_slots == 0) return fail(RMP2_ERR_INVALID, "tree has no sphere-obstacle leaves");
+    use_tma = n_spheres > 0 && n_spheres % 8 == 0;
+    block = ((tree->sph.envs_per_block * tree->sph.n_slots + 31) / 32) * 32;
+    smem = rmp2_spheres_smem(tree->sph, n_spheres, use_tma);
+  }
+  int r = 0, bps = 0;
+  cudaError_t e = rmp2_kernel_attributes(tree->tab.n, which, use_tma, block, smem, &r, &bps);
   if (e != cudaSuccess) return cuda_fail(e, "rmp2_tree_kernel_info");
   if (regs) *regs = r;
-  if (smem_bytes) *smem_bytes = (int)smem + ss;
+  if (smem_bytes) *smem_bytes = (int)smem;
   if (blocks_per_sm) *blocks_per_sm = bps;
   if (block_threads) *block_threads = block;
+  return RMP2_OK;
+}
+
+int rmp2_tree_profile(rmp2_tree* tree, int32_t enable) {
+  if (!tree) return fail(RMP2_ERR_INVALID, "null argument");
+  tree->profiling = enable != 0;
+  return RMP2_OK;
+}
+
+int rmp2_tree_profile_read(rmp2_tree* tree, double* ms, int64_t* launches) {
+  if (!tree || !ms || !launches) return fail(RMP2_ERR_INVALID, "null argument");
+  for (int k = 0; k < 3; ++k) {
+    KernelClock& c = tree->clock[k];
+    for (size_t i = 0; i + 1 < c.pending.size(); i += 2) {
+      cudaError_t e = cudaEventSynchronize(c.pending[i + 1]);
+      if (e != cudaSuccess) return cuda_fail(e, "rmp2_tree_profile_read");
+      float t = 0.f;
+      cudaEventElapsedTime(&t, c.pending[i], c.pending[i + 1]);
+      c.ms += t;
+      c.launches += 1;
+      cudaEventDestroy(c.pending[i]);
+      cudaEventDestroy(c.pending[i + 1]);
+    }
+    c.pending.clear();
+    ms[k] = c.ms;
+    launches[k] = c.launches;
+    c.ms = 0.0;
+    c.launches = 0;
+  }
   return RMP2_OK;
 }
 

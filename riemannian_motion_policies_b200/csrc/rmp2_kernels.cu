@@ -1,14 +1,24 @@
 // sm_100a kernels of the RMP2 control step.
 //
-//   rmp2_step_kernel<N, kTma>   THE hot path: one thread per environment walks the kinematic tree
-//                               once per sphere tile, evaluates every leaf, pulls back, resolves.
-//                               Sphere obstacles of the 32 environments of a warp are staged into
-//                               shared memory by one TMA 2-D tiled bulk copy per 8 spheres
-//                               (cp.async.bulk.tensor, 128-byte swizzle, warp-private mbarrier),
-//                               so HBM is read once, in full 128-byte lines, and the per-thread
-//                               row reads from shared memory are bank-conflict free.
-//   rmp2_fk_kernel<N>           FK value / velocity / Jacobian / Jdot*qd of one frame (Python API).
-//   rmp2_leaf_kernel            one leaf policy at given task-space points (Python API).
+// One control step = up to three launches on the caller's stream (intermediates stay in L2/HBM, which
+// this FP32-bound path uses at a few per cent of its bandwidth):
+//
+//   rmp2_frames_kernel<N>    thread per environment: kinematic chain -> origin position, velocity and
+//                            Jdot*qd of every frame that carries a sphere-obstacle leaf  (48 B records)
+//   rmp2_spheres_kernel      thread per (environment, obstacle leaf): the O(frames x spheres) pair loop.
+//                            The spheres of the E environments of a block are staged into shared memory
+//                            by TMA 2-D tiled bulk copies (cp.async.bulk.tensor, 128-byte swizzle,
+//                            mbarrier completion): HBM is read once in full 128-byte lines and the
+//                            LDS.128 row reads are bank-conflict free.  Small code, ~60 registers,
+//                            high occupancy -- this kernel carries >= 60 % of the instructions.
+//                            Output: per (env, leaf) the 3x3 metric sum S and the force sum g, written
+//                            over the input record.
+//   rmp2_step_kernel<N>      thread per environment: chain again (cheap), target leaves, pullback of every
+//                            frame's (S, g), configuration-space leaves, truncated-SVD resolve -> qdd;
+//                            optional explicit-Euler sub-steps for closed-loop rollouts.
+//
+//   rmp2_fk_kernel<N>        FK value / velocity / Jacobian / Jdot*qd of one frame (Python API).
+//   rmp2_leaf_kernel         one leaf policy at given task-space points (Python API).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -43,29 +53,195 @@ RMP2_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
-RMP2_DEV void tma_load_2d(void* dst, const CUtensorMap* tmap, int32_t x, int32_t y, uint64_t* bar) {
+RMP2_DEV void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int32_t x, int32_t y, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+      ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
 
-// --------------------------------------------------------------------------------- per-env context
-struct WarpTile {
-  const char* base;   // this warp's staged spheres: [box][32 rows][128 B], 128B-swizzled
-  uint32_t base32;    // the same, as a shared-window address
-  uint64_t* bar;      // this warp's mbarrier
-  uint32_t phase;     // parity of the next completion to wait for
-  int boxes;          // boxes per tile (<= 4)
-};
+// ------------------------------------------------------------------------------ chain walking
+// Visit frame `fi` of the depth-first execution list: restore / advance / save the chain state and,
+// when kCols, record the world axis and origin of the joint column the frame drives.
+template <int N, bool kCols>
+RMP2_DEV void visit_frame(const StepTables& T, int fi, const float (&q)[N], const float (&qd)[N], Chain& ch,
+                          float (&zj)[N][3], float (&pj)[N][3], float* slots) {
+  const FrameTab& F = T.frames[fi];
+  if (F.restore_slot == RMP2_SLOT_BASE) {
+    chain_reset(ch);
+  } else if (F.restore_slot >= 0) {
+    const float* s = slots + (size_t)F.restore_slot * RMP2_CHAIN_FLOATS * blockDim.x + threadIdx.x;
+    float* cf = reinterpret_cast<float*>(&ch);
+#pragma unroll
+    for (int i = 0; i < RMP2_CHAIN_FLOATS; ++i) cf[i] = s[i * blockDim.x];
+  }
+  float qi = 0.f, qdi = 0.f;
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+    if (j == F.qidx) {
+      qi = q[j];
+      qdi = qd[j];
+    }
+  float z[3];
+  chain_advance(ch, F, qi, qdi, z);
+  if (kCols) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (j == F.qidx) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          zj[j][i] = z[i];
+          pj[j][i] = ch.p[i];
+        }
+      }
+  }
+  if (F.save_slot >= 0) {
+    float* s = slots + (size_t)F.save_slot * RMP2_CHAIN_FLOATS * blockDim.x + threadIdx.x;
+    const float* cf = reinterpret_cast<const float*>(&ch);
+#pragma unroll
+    for (int i = 0; i < RMP2_CHAIN_FLOATS; ++i) s[i * blockDim.x] = cf[i];
+  }
+}
 
-// One environment, one control step: q, qd -> qdd.
-template <int N, bool kTma>
-RMP2_DEV void evaluate_env(const StepTables& T, const StepArgs& A, const CUtensorMap* tmap, long long env,
-                           long long warp_env0, const float (&q)[N], const float (&qd)[N], float* slots,
-                           WarpTile& wt, float (&qdd)[N]) {
+// ------------------------------------------------------------------------------- frames kernel
+// rec[env][slot] = (p, v, a, |v|^2, 0, 0) for every sphere-obstacle leaf slot.
+template <int N>
+__global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
+    rmp2_frames_kernel(const __grid_constant__ StepTables T, const __grid_constant__ StepArgs A) {
+  extern __shared__ float slots[];
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= A.B) return;
   const int n = T.n;
-  const uint32_t lane = threadIdx.x & 31u;
+  float q[N], qd[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    q[j] = (j < n) ? A.q[env * n + j] : 0.f;
+    qd[j] = (j < n) ? A.qd[env * n + j] : 0.f;
+  }
+  float zj[N][3], pj[N][3];   // unused (kCols = false), optimised away
+  Chain ch;
+  chain_reset(ch);
+  float4* rec = reinterpret_cast<float4*>(A.rec) + (size_t)env * T.n_sphere_slots * 3;
+  for (int fi = 0; fi < T.n_frames; ++fi) {
+    visit_frame<N, false>(T, fi, q, qd, ch, zj, pj, slots);
+    const FrameTab& F = T.frames[fi];
+    for (int li = F.leaf_begin; li < F.leaf_end; ++li) {
+      const LeafTab& L = T.leaves[li];
+      if (L.space != RMP2_SPACE_FRAME_DISTANCE_SPHERES) continue;
+      const float vv = fmaf(ch.v[0], ch.v[0], fmaf(ch.v[1], ch.v[1], ch.v[2] * ch.v[2]));
+      float4* r = rec + L.sphere_slot * 3;
+      r[0] = make_float4(ch.p[0], ch.p[1], ch.p[2], ch.v[0]);
+      r[1] = make_float4(ch.v[1], ch.v[2], ch.a[0], ch.a[1]);
+      r[2] = make_float4(ch.a[2], vv, 0.f, 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ spheres kernel
+// Thread t of a block <-> (local environment t / L, obstacle-leaf slot t % L); the block owns E
+// consecutive environments.  Staged layout: box b (8 spheres) = E rows of 128 B, box stride padded to
+// 1024 B so that the 128-byte TMA swizzle (16-byte chunk index XOR row & 7) is row-relative.
+template <bool kTma>
+__global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
+    rmp2_spheres_kernel(const __grid_constant__ SphereTables ST, const __grid_constant__ StepArgs A,
+                        const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int L = ST.n_slots, E = ST.envs_per_block;
+  const int t = threadIdx.x;
+  const int e_local = t / L, slot = t - e_local * L;
+  const long long env0 = (long long)blockIdx.x * E;
+  const long long env = env0 + e_local;
+  const int O = A.n_spheres;
+  const bool active = (e_local < E) && (env < A.B);
+
+  uint32_t tiles = 0;
+  if (kTma) {
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t box_stride = ((uint32_t)E * 128u + 1023u) & ~1023u;
+    const int nbox = O >> 3;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + (size_t)nbox * box_stride);
+    tiles = smem_u32(base);
+    if (t == 0) {
+      mbar_init(bar, 1);
+      mbar_expect_tx(bar, (uint32_t)nbox * (uint32_t)E * 128u);
+      for (int b = 0; b < nbox; ++b) tma_load_2d(tiles + b * box_stride, &tmap, b * 32, (int32_t)env0, bar);
+    }
+    __syncthreads();                              // barrier initialised before anyone polls it
+    if (!active) return;
+    mbar_wait(bar, 0);
+    tiles += (uint32_t)e_local * 128u;
+  } else {
+    if (!active) return;
+  }
+
+  // this thread's frame record and leaf parameters
+  float4* rec = reinterpret_cast<float4*>(A.rec) + ((size_t)env * L + slot) * 3;
+  const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2];
+  const float px = r0.x, py = r0.y, pz = r0.z;
+  const float v[3] = {r0.w, r1.x, r1.y};
+  const float a[3] = {r1.z, r1.w, r2.x};
+  const float vv = r2.y;
+  float p[RMP2_LEAF_PARAMS];
+#pragma unroll
+  for (int i = 0; i < RMP2_LEAF_PARAMS; ++i) p[i] = ST.p[slot][i];
+
+  float S[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float g[3] = {0.f, 0.f, 0.f};
+  auto one_sphere = [&](const float4 sp) {
+    // pos_on_link = frame origin; pos_on_obstacle = closest surface point of the sphere
+    const float rx = px - sp.x, ry = py - sp.y, rz = pz - sp.z;
+    const float dc2 = fmaxf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)), 1e-24f);
+    const float inv_dc = fast_rsqrt(dc2);
+    const float sd = fmaf(dc2, inv_dc, -sp.w);               // signed surface distance
+    const float sgn = (sd < 0.f) ? -inv_dc : inv_dc;
+    const float d = fmaxf(fabsf(sd), 1e-12f);
+    obstacle_pair(p, rx * sgn, ry * sgn, rz * sgn, d, fast_rcp(d), v, a, vv, S, g);
+  };
+  if (kTma) {
+    const uint32_t x7 = ((uint32_t)e_local & 7u) << 4;
+    const uint32_t box_stride = ((uint32_t)E * 128u + 1023u) & ~1023u;
+    for (int hb = 0; hb < (O >> 2); ++hb) {                   // half a box (4 spheres) per trip
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        float4 sp;
+        const uint32_t c8 = (uint32_t)(hb & 1) * 4u + (uint32_t)c4;
+        const uint32_t addr = tiles + (uint32_t)(hb >> 1) * box_stride + ((c8 << 4) ^ x7);
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(sp.x), "=f"(sp.y), "=f"(sp.z), "=f"(sp.w)
+                     : "r"(addr));
+        one_sphere(sp);
+      }
+    }
+  } else {
+    const float4* gs = reinterpret_cast<const float4*>(A.spheres) + (size_t)env * O;
+#pragma unroll 4
+    for (int o = 0; o < O; ++o) one_sphere(__ldg(gs + o));
+  }
+  rec[0] = make_float4(S[0], S[1], S[2], S[3]);
+  rec[1] = make_float4(S[4], S[5], g[0], g[1]);
+  rec[2] = make_float4(g[2], 0.f, 0.f, 0.f);
+}
+
+// --------------------------------------------------------------------------------- step kernel
+template <int N>
+__global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
+    rmp2_step_kernel(const __grid_constant__ StepTables T, const __grid_constant__ StepArgs A) {
+  extern __shared__ float slots[];
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // no early return: the resolve uses full-warp votes; out-of-range lanes redo the last environment
+  const bool active = env < A.B;
+  const long long e = active ? env : A.B - 1;
+  const int n = T.n;
+  const bool rollout = A.n_sim_steps > 0;
+
+  float q[N], qd[N], qdd[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const bool in = j < n;
+    q[j] = in ? (rollout ? A.q_rw : A.q)[e * n + j] : 0.f;
+    qd[j] = in ? (rollout ? A.qd_rw : A.qd)[e * n + j] : 0.f;
+  }
+
   float Msym[N * (N + 1) / 2];
   float f[N];
 #pragma unroll
@@ -73,86 +249,34 @@ RMP2_DEV void evaluate_env(const StepTables& T, const StepArgs& A, const CUtenso
 #pragma unroll
   for (int i = 0; i < N; ++i) f[i] = 0.f;
 
-  const int O = A.n_spheres;
-  const int n_tiles = (T.uses_spheres && O > 0) ? (O + RMP2_TILE_SPHERES - 1) / RMP2_TILE_SPHERES : 1;
-
-  for (int tile = 0; tile < n_tiles; ++tile) {
-    const int tile_first = tile * RMP2_TILE_SPHERES;
-    const int tile_count = T.uses_spheres ? min(RMP2_TILE_SPHERES, O - tile_first) : 0;
-    bool tile_ready = !kTma;
-    if (kTma && tile_count > 0) {
-      __syncwarp();                              // every lane is done reading the previous tile
-      if (lane == 0) {
-        const int boxes = (tile_count + 7) >> 3;
-        mbar_expect_tx(wt.bar, static_cast<uint32_t>(boxes) * 4096u);
-        for (int b = 0; b < boxes; ++b)
-          tma_load_2d(const_cast<char*>(wt.base) + b * 4096, tmap, (tile_first + 8 * b) * 4,
-                      static_cast<int32_t>(warp_env0), wt.bar);
-      }
-    }
-
+  {
     float zj[N][3], pj[N][3];
 #pragma unroll
     for (int j = 0; j < N; ++j) zj[j][0] = zj[j][1] = zj[j][2] = pj[j][0] = pj[j][1] = pj[j][2] = 0.f;
     Chain ch;
     chain_reset(ch);
-
     for (int fi = 0; fi < T.n_frames; ++fi) {
+      visit_frame<N, true>(T, fi, q, qd, ch, zj, pj, slots);
       const FrameTab& F = T.frames[fi];
-      if (F.restore_slot == RMP2_SLOT_BASE) {
-        chain_reset(ch);
-      } else if (F.restore_slot >= 0) {
-        const float* s = slots + (size_t)F.restore_slot * RMP2_CHAIN_FLOATS * blockDim.x + threadIdx.x;
-        float* cf = reinterpret_cast<float*>(&ch);
-#pragma unroll
-        for (int i = 0; i < RMP2_CHAIN_FLOATS; ++i) cf[i] = s[i * blockDim.x];
-      }
-      float qi = 0.f, qdi = 0.f;
-#pragma unroll
-      for (int j = 0; j < N; ++j)
-        if (j == F.qidx) {
-          qi = q[j];
-          qdi = qd[j];
-        }
-      float z[3];
-      chain_advance(ch, F, qi, qdi, z);
-#pragma unroll
-      for (int j = 0; j < N; ++j)
-        if (j == F.qidx) {
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            zj[j][i] = z[i];
-            pj[j][i] = ch.p[i];
-          }
-        }
-      if (F.save_slot >= 0) {
-        float* s = slots + (size_t)F.save_slot * RMP2_CHAIN_FLOATS * blockDim.x + threadIdx.x;
-        const float* cf = reinterpret_cast<const float*>(&ch);
-#pragma unroll
-        for (int i = 0; i < RMP2_CHAIN_FLOATS; ++i) s[i * blockDim.x] = cf[i];
-      }
       if (F.leaf_begin >= F.leaf_end) continue;
 
       float S[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       float g[3] = {0.f, 0.f, 0.f};
       bool contrib = false;
-      const float vv = fmaf(ch.v[0], ch.v[0], fmaf(ch.v[1], ch.v[1], ch.v[2] * ch.v[2]));
-
       for (int li = F.leaf_begin; li < F.leaf_end; ++li) {
         const LeafTab& L = T.leaves[li];
         if (L.space == RMP2_SPACE_FRAME_POSITION) {
-          if (tile != 0) continue;
           float goal[3], xdd[3], zeta[3], iso, dir;
 #pragma unroll
           for (int i = 0; i < 3; ++i)
-            goal[i] = (L.goal_slot >= 0) ? __ldg(A.goals + (env * A.n_goal_slots + L.goal_slot) * 3 + i)
+            goal[i] = (L.goal_slot >= 0) ? __ldg(A.goals + (e * A.n_goal_slots + L.goal_slot) * 3 + i)
                                          : T.vecpool[L.vec_off + i];
           if (L.type == RMP2_LEAF_TARGET_POLICY)
             target_policy<3>(L.p, ch.p, ch.v, goal, 3, xdd, zeta, iso, dir);
           else
             target_attractor(L.p, ch.p, ch.v, goal, xdd, zeta, iso, dir);
-          const float e[3] = {xdd[0] - ch.a[0], xdd[1] - ch.a[1], xdd[2] - ch.a[2]};
-          const float ze = dir * fmaf(zeta[0], e[0], fmaf(zeta[1], e[1], zeta[2] * e[2]));
+          const float er[3] = {xdd[0] - ch.a[0], xdd[1] - ch.a[1], xdd[2] - ch.a[2]};
+          const float ze = dir * fmaf(zeta[0], er[0], fmaf(zeta[1], er[1], zeta[2] * er[2]));
           const float dz[3] = {dir * zeta[0], dir * zeta[1], dir * zeta[2]};
           S[0] += fmaf(dz[0], zeta[0], iso);
           S[1] = fmaf(dz[0], zeta[1], S[1]);
@@ -161,53 +285,27 @@ RMP2_DEV void evaluate_env(const StepTables& T, const StepArgs& A, const CUtenso
           S[4] = fmaf(dz[1], zeta[2], S[4]);
           S[5] += fmaf(dz[2], zeta[2], iso);
 #pragma unroll
-          for (int i = 0; i < 3; ++i) g[i] += fmaf(iso, e[i], ze * zeta[i]);
+          for (int i = 0; i < 3; ++i) g[i] += fmaf(iso, er[i], ze * zeta[i]);
           contrib = true;
         } else if (L.space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) {
-          if (tile_count <= 0) continue;
-          if (kTma && !tile_ready) {
-            mbar_wait(wt.bar, wt.phase);
-            wt.phase ^= 1u;
-            tile_ready = true;
-          }
-          auto one_sphere = [&](const float4 sp) {
-            // pos_on_link = frame origin; pos_on_obstacle = closest surface point of the sphere
-            const float rx = ch.p[0] - sp.x, ry = ch.p[1] - sp.y, rz = ch.p[2] - sp.z;
-            const float dc2 = fmaxf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)), 1e-24f);
-            const float inv_dc = fast_rsqrt(dc2);
-            const float sd = fmaf(dc2, inv_dc, -sp.w);             // signed surface distance
-            const float sgn = (sd < 0.f) ? -inv_dc : inv_dc;
-            const float d = fmaxf(fabsf(sd), 1e-12f);
-            obstacle_pair(L.p, rx * sgn, ry * sgn, rz * sgn, d, fast_rcp(d), ch.v, ch.a, vv, S, g);
-          };
-          if (kTma) {
-            // row `lane` of each staged box holds 8 spheres of this environment; the 16-byte chunk c
-            // of a row sits at chunk (c ^ (lane & 7)) (128-byte TMA swizzle) -> conflict-free LDS.128
-            const uint32_t row = wt.base32 + lane * 128u;
-            const uint32_t x7 = (lane & 7u) << 4;
-            const int nbox = tile_count >> 3;
-            for (int hb = 0; hb < 2 * nbox; ++hb) {          // half a box (4 spheres) per trip: the
-#pragma unroll                                               // unrolled body stays inside the L0 I-cache
-              for (int c4 = 0; c4 < 4; ++c4) {
-                float4 sp;
-                const uint32_t c8 = (uint32_t)(hb & 1) * 4u + (uint32_t)c4;
-                const uint32_t addr = row + (uint32_t)(hb >> 1) * 4096u + ((c8 << 4) ^ x7);
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(sp.x), "=f"(sp.y), "=f"(sp.z), "=f"(sp.w)
-                             : "r"(addr));
-                one_sphere(sp);
-              }
-            }
-          } else {
-            const float4* gsph = reinterpret_cast<const float4*>(A.spheres + ((size_t)env * O + tile_first) * 4);
-#pragma unroll 2
-            for (int o = 0; o < tile_count; ++o) one_sphere(__ldg(gsph + o));
-          }
+          if (A.n_spheres <= 0) continue;
+          // sums over this leaf's spheres, produced by rmp2_spheres_kernel
+          const float4* r = reinterpret_cast<const float4*>(A.rec) + ((size_t)e * T.n_sphere_slots + L.sphere_slot) * 3;
+          const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
+          S[0] += r0.x;
+          S[1] += r0.y;
+          S[2] += r0.z;
+          S[3] += r0.w;
+          S[4] += r1.x;
+          S[5] += r1.y;
+          g[0] += r1.z;
+          g[1] += r1.w;
+          g[2] += r2.x;
           contrib = true;
         } else {  // RMP2_SPACE_FRAME_DISTANCE_PAIRS: explicit (pos_on_link, pos_on_obstacle) pairs
-          if (tile != 0) continue;
           const int k0 = A.pair_off[L.pair_set], k1 = A.pair_off[L.pair_set + 1];
-          const float* pp = A.pairs + ((size_t)env * A.pair_total + k0) * 6;
+          const float* pp = A.pairs + ((size_t)e * A.pair_total + k0) * 6;
+          const float vv = fmaf(ch.v[0], ch.v[0], fmaf(ch.v[1], ch.v[1], ch.v[2] * ch.v[2]));
           for (int k = 0; k < k1 - k0; ++k) {
             const float rx = __ldg(pp + 6 * k + 0) - __ldg(pp + 6 * k + 3);
             const float ry = __ldg(pp + 6 * k + 1) - __ldg(pp + 6 * k + 4);
@@ -220,10 +318,6 @@ RMP2_DEV void evaluate_env(const StepTables& T, const StepArgs& A, const CUtenso
         }
       }
       if (contrib) pullback<N>(zj, pj, ch.p, F.anc_mask, T.prismatic_mask, S, g, Msym, f);
-    }
-    if (kTma && tile_count > 0 && !tile_ready) {   // tree asked for spheres but no frame consumed them
-      mbar_wait(wt.bar, wt.phase);
-      wt.phase ^= 1u;
     }
   }
 
@@ -271,12 +365,12 @@ RMP2_DEV void evaluate_env(const StepTables& T, const StepArgs& A, const CUtenso
       float zeta[N], w[N];
       leaf_joint_limit<N>(L.p, vec, n, q, qd, xdd, zeta, w);
       const float beta = L.p[JL_BETA];
-      float t = 0.f;
+      float tt = 0.f;
 #pragma unroll
-      for (int j = 0; j < N; ++j) t = fmaf(zeta[j] * w[j], xdd[j], t);
+      for (int j = 0; j < N; ++j) tt = fmaf(zeta[j] * w[j], xdd[j], tt);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        f[i] += fmaf(beta * zeta[i], t, (1.f - beta) * w[i] * xdd[i]);
+        f[i] += fmaf(beta * zeta[i], tt, (1.f - beta) * w[i] * xdd[i]);
 #pragma unroll
         for (int j = 0; j < N; ++j) M[i][j] += fmaf(beta * zeta[i], zeta[j], (i == j) ? (1.f - beta) : 0.f) * w[j];
       }
@@ -298,78 +392,30 @@ RMP2_DEV void evaluate_env(const StepTables& T, const StepArgs& A, const CUtenso
     }
   }
   resolve_pinv<N>(M, f, T.rcond, qdd);
-}
 
-// ------------------------------------------------------------------------------------- step kernel
-template <int N, bool kTma>
-__global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
-    rmp2_step_kernel(const __grid_constant__ StepTables T, const __grid_constant__ StepArgs A,
-                     const __grid_constant__ CUtensorMap tmap) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const int warps = blockDim.x >> 5;
-  const int warp = threadIdx.x >> 5;
-  const uint32_t lane = threadIdx.x & 31u;
-  const long long env_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long warp_env0 = env_raw - lane;
-  if (warp_env0 >= A.B) return;                  // whole warp out of range (uniform per warp)
-  const bool active = env_raw < A.B;
-  const long long env = active ? env_raw : A.B - 1;
-  const int n = T.n;
-
-  // shared memory carve-up: [sphere tiles | mbarriers | chain-state slots]
-  WarpTile wt;
-  const int boxes = kTma ? min(4, (A.n_spheres + 7) >> 3) : 0;
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  wt.base = reinterpret_cast<const char*>(base + (size_t)warp * boxes * 4096);
-  wt.base32 = smem_u32(wt.base);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)warps * boxes * 4096);
-  wt.bar = bars + warp;
-  wt.phase = 0;
-  wt.boxes = boxes;
-  float* slots = reinterpret_cast<float*>(bars + warps);
-  if (kTma) {
-    if (lane == 0) mbar_init(wt.bar, 1);
-    __syncwarp();
-  }
-
-  float q[N], qd[N], qdd[N];
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const bool in = j < n;
-    const float* qs = (A.n_sim_steps > 0) ? A.q_rw : A.q;
-    const float* qds = (A.n_sim_steps > 0) ? A.qd_rw : A.qd;
-    q[j] = in ? qs[env * n + j] : 0.f;
-    qd[j] = in ? qds[env * n + j] : 0.f;
-    qdd[j] = 0.f;
-  }
-
-  // One call site (one inlined copy of the step): a plain step is a rollout of one control step
-  // without integration.  Closed-loop rollout = explicit Euler at dt, control every `control_every`.
-  const bool rollout = A.n_sim_steps > 0;
-  const int n_steps = rollout ? A.n_sim_steps : 1;
-  for (int step = 0; step < n_steps; ++step) {
-    if (!rollout || step % A.control_every == 0)
-      evaluate_env<N, kTma>(T, A, &tmap, env, warp_env0, q, qd, slots, wt, qdd);
-    if (rollout) {
+  if (rollout) {
+    // explicit Euler with the command held for n_sim_steps sub-steps (reference loop: control at
+    // 10 Hz, simulation at 100 Hz -- experiments/franka_panda/05_obstacle_avoidance.py:92-97)
+    for (int s = 0; s < A.n_sim_steps; ++s) {
 #pragma unroll
       for (int j = 0; j < N; ++j) {
         qd[j] = fmaf(qdd[j], A.dt, qd[j]);
         q[j] = fmaf(qd[j], A.dt, q[j]);
       }
     }
-  }
-  if (rollout && active) {
+    if (active) {
 #pragma unroll
-    for (int j = 0; j < N; ++j)
-      if (j < n) {
-        A.q_rw[env * n + j] = q[j];
-        A.qd_rw[env * n + j] = qd[j];
-      }
+      for (int j = 0; j < N; ++j)
+        if (j < n) {
+          A.q_rw[e * n + j] = q[j];
+          A.qd_rw[e * n + j] = qd[j];
+        }
+    }
   }
   if (active) {
 #pragma unroll
     for (int j = 0; j < N; ++j)
-      if (j < n) A.qdd[env * n + j] = qdd[j];
+      if (j < n) A.qdd[e * n + j] = qdd[j];
   }
 }
 
@@ -556,25 +602,6 @@ __global__ void __launch_bounds__(128)
 }
 
 // -------------------------------------------------------------------------------- host launchers
-template <int N>
-static cudaError_t launch_step_n(const StepTables& T, const StepArgs& A, const CUtensorMap* tmap, bool use_tma,
-                                 int block, size_t smem, cudaStream_t stream) {
-  const long long blocks = (A.B + block - 1) / block;
-  if (blocks <= 0) return cudaSuccess;
-  CUtensorMap dummy;
-  memset(&dummy, 0, sizeof(dummy));
-  if (use_tma) {
-    cudaError_t e = cudaFuncSetAttribute(rmp2_step_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    rmp2_step_kernel<N, true><<<(unsigned)blocks, block, smem, stream>>>(T, A, *tmap);
-  } else {
-    cudaError_t e = cudaFuncSetAttribute(rmp2_step_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    rmp2_step_kernel<N, false><<<(unsigned)blocks, block, smem, stream>>>(T, A, dummy);
-  }
-  return cudaGetLastError();
-}
-
 int rmp2_pick_width(int n) {
   if (n <= 2) return 2;
   if (n <= 7) return 7;
@@ -582,41 +609,79 @@ int rmp2_pick_width(int n) {
   return 12;
 }
 
-cudaError_t rmp2_launch_step(const StepTables& T, const StepArgs& A, const CUtensorMap* tmap, bool use_tma,
-                             int block, size_t smem, cudaStream_t stream) {
-  switch (rmp2_pick_width(T.n)) {
-    case 2: return launch_step_n<2>(T, A, tmap, use_tma, block, smem, stream);
-    case 7: return launch_step_n<7>(T, A, tmap, use_tma, block, smem, stream);
-    case 9: return launch_step_n<9>(T, A, tmap, use_tma, block, smem, stream);
-    default: return launch_step_n<12>(T, A, tmap, use_tma, block, smem, stream);
+#define RMP2_DISPATCH_N(n, CALL)            \
+  switch (rmp2_pick_width(n)) {             \
+    case 2: { constexpr int NN = 2; CALL; } break;   \
+    case 7: { constexpr int NN = 7; CALL; } break;   \
+    case 9: { constexpr int NN = 9; CALL; } break;   \
+    default: { constexpr int NN = 12; CALL; } break; \
   }
+
+cudaError_t rmp2_launch_frames(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream) {
+  const long long blocks = (A.B + block - 1) / block;
+  if (blocks <= 0) return cudaSuccess;
+  const size_t smem = (size_t)T.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
+  RMP2_DISPATCH_N(T.n, (rmp2_frames_kernel<NN><<<(unsigned)blocks, block, smem, stream>>>(T, A)));
+  return cudaGetLastError();
 }
 
-template <int N>
-static cudaError_t step_attr_n(bool use_tma, cudaFuncAttributes* attr, int block, size_t smem, int* blocks_per_sm) {
-  const void* fn = use_tma ? (const void*)rmp2_step_kernel<N, true> : (const void*)rmp2_step_kernel<N, false>;
-  cudaError_t e = cudaFuncGetAttributes(attr, fn);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  if (use_tma)
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rmp2_step_kernel<N, true>, block, smem);
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rmp2_step_kernel<N, false>, block, smem);
+size_t rmp2_spheres_smem(const SphereTables& ST, int n_spheres, bool use_tma) {
+  if (!use_tma) return 0;
+  const size_t box_stride = ((size_t)ST.envs_per_block * 128 + 1023) & ~size_t(1023);
+  return 1024 + (size_t)(n_spheres / 8) * box_stride + 16;
 }
 
-cudaError_t rmp2_step_attributes(int n, bool use_tma, int block, size_t smem, int* regs, int* static_smem,
-                                 int* blocks_per_sm) {
+cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, const CUtensorMap* tmap, bool use_tma,
+                                cudaStream_t stream) {
+  const long long blocks = (A.B + ST.envs_per_block - 1) / ST.envs_per_block;
+  if (blocks <= 0) return cudaSuccess;
+  const int threads = ((ST.envs_per_block * ST.n_slots + 31) / 32) * 32;
+  const size_t smem = rmp2_spheres_smem(ST, A.n_spheres, use_tma);
+  if (use_tma) {
+    cudaError_t e = cudaFuncSetAttribute(rmp2_spheres_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rmp2_spheres_kernel<true><<<(unsigned)blocks, threads, smem, stream>>>(ST, A, *tmap);
+  } else {
+    CUtensorMap dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    rmp2_spheres_kernel<false><<<(unsigned)blocks, threads, 0, stream>>>(ST, A, dummy);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t rmp2_launch_step(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream) {
+  const long long blocks = (A.B + block - 1) / block;
+  if (blocks <= 0) return cudaSuccess;
+  const size_t smem = (size_t)T.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
+  RMP2_DISPATCH_N(T.n, (rmp2_step_kernel<NN><<<(unsigned)blocks, block, smem, stream>>>(T, A)));
+  return cudaGetLastError();
+}
+
+cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, size_t smem, int* regs,
+                                   int* blocks_per_sm) {
   cudaFuncAttributes attr;
-  cudaError_t e;
-  switch (rmp2_pick_width(n)) {
-    case 2: e = step_attr_n<2>(use_tma, &attr, block, smem, blocks_per_sm); break;
-    case 7: e = step_attr_n<7>(use_tma, &attr, block, smem, blocks_per_sm); break;
-    case 9: e = step_attr_n<9>(use_tma, &attr, block, smem, blocks_per_sm); break;
-    default: e = step_attr_n<12>(use_tma, &attr, block, smem, blocks_per_sm); break;
+  cudaError_t e = cudaSuccess;
+  if (which == 1) {
+    const void* fn = use_tma ? (const void*)rmp2_spheres_kernel<true> : (const void*)rmp2_spheres_kernel<false>;
+    e = cudaFuncGetAttributes(&attr, fn);
+    if (e != cudaSuccess) return e;
+    if (smem > 0) {
+      e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    e = use_tma ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rmp2_spheres_kernel<true>, block, smem)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rmp2_spheres_kernel<false>, block, smem);
+  } else if (which == 0) {
+    RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_frames_kernel<NN>),
+                        e = (e == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                                                     blocks_per_sm, rmp2_frames_kernel<NN>, block, smem) : e));
+  } else {
+    RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_step_kernel<NN>),
+                        e = (e == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                                                     blocks_per_sm, rmp2_step_kernel<NN>, block, smem) : e));
   }
   if (e != cudaSuccess) return e;
   *regs = attr.numRegs;
-  *static_smem = (int)attr.sharedSizeBytes;
   return cudaSuccess;
 }
 
@@ -624,12 +689,7 @@ cudaError_t rmp2_launch_fk(const StepTables& T, long long B, const float* q, con
                            float* J, float* c, cudaStream_t stream) {
   const long long blocks = (B + 127) / 128;
   if (blocks <= 0) return cudaSuccess;
-  switch (rmp2_pick_width(T.n)) {
-    case 2: rmp2_fk_kernel<2><<<(unsigned)blocks, 128, 0, stream>>>(T, B, q, qd, x, xd, J, c); break;
-    case 7: rmp2_fk_kernel<7><<<(unsigned)blocks, 128, 0, stream>>>(T, B, q, qd, x, xd, J, c); break;
-    case 9: rmp2_fk_kernel<9><<<(unsigned)blocks, 128, 0, stream>>>(T, B, q, qd, x, xd, J, c); break;
-    default: rmp2_fk_kernel<12><<<(unsigned)blocks, 128, 0, stream>>>(T, B, q, qd, x, xd, J, c); break;
-  }
+  RMP2_DISPATCH_N(T.n, (rmp2_fk_kernel<NN><<<(unsigned)blocks, 128, 0, stream>>>(T, B, q, qd, x, xd, J, c)));
   return cudaGetLastError();
 }
 

@@ -13,10 +13,14 @@ struct LeafVec {
 
 int rmp2_pick_width(int n);
 
-cudaError_t rmp2_launch_step(const StepTables& T, const StepArgs& A, const CUtensorMap* tmap, bool use_tma,
-                             int block, size_t smem, cudaStream_t stream);
-cudaError_t rmp2_step_attributes(int n, bool use_tma, int block, size_t smem, int* regs, int* static_smem,
-                                 int* blocks_per_sm);
+cudaError_t rmp2_launch_frames(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);
+size_t rmp2_spheres_smem(const SphereTables& ST, int n_spheres, bool use_tma);
+cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, const CUtensorMap* tmap, bool use_tma,
+                                cudaStream_t stream);
+cudaError_t rmp2_launch_step(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);
+// which: 0 frames, 1 spheres, 2 step
+cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, size_t smem, int* regs,
+                                   int* blocks_per_sm);
 cudaError_t rmp2_launch_fk(const StepTables& T, long long B, const float* q, const float* qd, float* x, float* xd,
                            float* J, float* c, cudaStream_t stream);
 cudaError_t rmp2_launch_leaf(const LeafTab& L, const LeafVec& V, int m, long long K, const float* x, const float* xd,

@@ -9,7 +9,7 @@
 #define RMP2_VECPOOL 160          // floats: goals / q0 / limits of all leaves
 #define RMP2_SLOT_BASE (-2)       // restore_slot value meaning "start from the base link"
 #define RMP2_CHAIN_FLOATS 24      // R(9) p(3) w(3) v(3) alpha(3) a(3)
-#define RMP2_TILE_SPHERES 32      // spheres per shared-memory tile (32 x 16 B = 4 TMA boxes of 128 B)
+#define RMP2_REC_FLOATS 12        // one frame record / one (S, g) record
 
 struct FrameTab {
   float R[9];            // constant rotation  (reference: kinematics.py:202, R_x R_y R_z order)
@@ -34,6 +34,7 @@ struct LeafTab {
   int32_t goal_slot;     // >= 0: per-environment goal
   int32_t vec_off;       // offset of this leaf's vector parameters in vecpool
   int32_t pair_set;      // FRAME_DISTANCE_PAIRS: index into the per-call pair offsets
+  int32_t sphere_slot;   // FRAME_DISTANCE_SPHERES: record slot of this leaf in StepArgs::rec
   float p[RMP2_LEAF_PARAMS];   // derived parameters, see leaf_params.h
 };
 
@@ -44,11 +45,19 @@ struct StepTables {
   int32_t n_leaves;             // leaves [n_frame_leaves, n_leaves) are configuration-space
   int32_t n_slots;
   int32_t uses_spheres;         // some leaf reads io.spheres
+  int32_t n_sphere_slots;       // number of FRAME_DISTANCE_SPHERES leaves (record slots per environment)
   uint32_t prismatic_mask;      // bit j: joint column j is prismatic
   float rcond;                  // 10 * n * eps32 (tf.linalg.pinv default, rmp.py:153)
   FrameTab frames[RMP2_MAX_FRAMES];
   LeafTab leaves[RMP2_MAX_LEAVES];
   float vecpool[RMP2_VECPOOL];
+};
+
+// Parameters of the sphere-obstacle leaves, one row per record slot (rmp2_spheres_kernel).
+struct SphereTables {
+  int32_t n_slots;              // L
+  int32_t envs_per_block;       // E: environments per thread block (E * L <= 128)
+  float p[RMP2_MAX_LEAVES][RMP2_LEAF_PARAMS];
 };
 
 // per-call arguments (device pointers)
@@ -60,11 +69,12 @@ struct StepArgs {
   const float* goals;
   const float* spheres;
   const float* pairs;
+  float* rec;            // [B][n_sphere_slots][12] scratch: frame records in, (S, g) sums out
   int32_t n_goal_slots;
   int32_t n_spheres;
   int32_t pair_total;
   int32_t pair_off[RMP2_MAX_PAIR_SETS + 1];
-  // rollout (rmp2_rollout): when n_sim_steps > 0 the kernel integrates in place
+  // rollout (rmp2_rollout): when n_sim_steps > 0 the step kernel integrates in place afterwards
   float* q_rw;
   float* qd_rw;
   float dt;

@@ -234,11 +234,31 @@ class CompiledTree:
                                                  current_stream_ptr(q.device)))
         return q, qd, qdd
 
-    def kernel_info(self):
-        regs, smem, bps, block = (ctypes.c_int32() for _ in range(4))
-        _native.check(_native.lib().rmp2_tree_kernel_info(self.handle, ctypes.byref(regs), ctypes.byref(smem),
-                                                          ctypes.byref(bps), ctypes.byref(block)))
-        return dict(registers=regs.value, smem_bytes=smem.value, blocks_per_sm=bps.value, block_threads=block.value)
+    KERNELS = ("frames", "spheres", "step")
+
+    def kernel_info(self, n_spheres=64):
+        """registers / shared memory / resident blocks per SM of the kernels one step launches."""
+        out = {}
+        for which, name in enumerate(self.KERNELS):
+            if name != "step" and not self.uses_spheres:
+                continue
+            regs, smem, bps, block = (ctypes.c_int32() for _ in range(4))
+            _native.check(_native.lib().rmp2_tree_kernel_info(self.handle, which, n_spheres, ctypes.byref(regs),
+                                                              ctypes.byref(smem), ctypes.byref(bps), ctypes.byref(block)))
+            out[name] = dict(registers=regs.value, smem_bytes=smem.value, blocks_per_sm=bps.value,
+                             block_threads=block.value, warps_per_sm=bps.value * block.value // 32)
+        return out
+
+    def profile(self, enable=True):
+        """Bracket every kernel launch of this tree with CUDA events (see ``profile_read``)."""
+        _native.check(_native.lib().rmp2_tree_profile(self.handle, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> {kernel: (milliseconds, launches)} accumulated since the last read."""
+        ms = (ctypes.c_double * 3)()
+        launches = (ctypes.c_int64 * 3)()
+        _native.check(_native.lib().rmp2_tree_profile_read(self.handle, ms, launches))
+        return {name: (ms[i], launches[i]) for i, name in enumerate(self.KERNELS)}
 
 
 # =================================================================================================
