@@ -232,6 +232,9 @@ def run_b200_arm(args):
     core = S.build_config2(ns, fk, goal0, n) if config == 2 else S.BUILDERS[config](ns, fk, goal0, n, sphere_tm)
     goal_leaf = "target" if config == 2 else "attractor"
     tree = core.compile(n, goal_leaves=[goal_leaf])
+    # Headline and roofline: every (frame, sphere) pair goes through the full arithmetic.  The exact
+    # early-out of the obstacle kernel (library default) is measured separately below.
+    tree.set_early_out(False)
 
     n_buffers = 4 if O_ else 1
     q, qd, goal, spheres = synth_inputs(ns, fk, n, B, O_, n_buffers, seed=S.SEEDS[config] + 17 * rank, device=device)
@@ -271,6 +274,35 @@ def run_b200_arm(args):
     ms_per_step = elapsed_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
     per_gpu = B / (ms_per_step * 1e-3)
+
+    # ---- same workload with the library default (exact early-out of pairs beyond the metric radius)
+    early = None
+    if O_ and not args.skip_early_out:
+        tree.set_early_out(True)
+        for i in range(3):
+            step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ems], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        sub = slice(0, min(B, 8192))
+        frames = S.collision_frames(fk)
+        origins = torch.stack([fk.forward(q[sub], fr)[:, :3, 3] for fr in frames], dim=1)          # [b,K,3]
+        sp = spheres[0][sub]
+        dist_s = torch.linalg.norm(origins[:, :, None, :] - sp[:, None, :, :3], dim=-1) - sp[:, None, :, 3]
+        early = {"value": world * B / (ems / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ems / args.steps,
+                 "active_pair_fraction": float((dist_s.abs() <= 0.5).float().mean()),
+                 "note": "library default: pairs beyond metric_modulation_radius contribute exactly zero "
+                         "(reference rmp2.py:194) and are skipped; results are identical"}
+        tree.set_early_out(False)
 
     # ---- parity spot check on the benchmarked inputs (first 128 envs of rank 0, oracle = checker only)
     parity = None
@@ -368,7 +400,7 @@ def run_b200_arm(args):
                               "peak_source": "analytic 148 SM x 128 lanes x 2 x 1.965 GHz"},
             "kernel_ms": {k: {"ms_per_step": v[0] / args.steps, "launches": int(v[1])} for k, v in kernel_ms.items()},
             "per_gpu_value": per_gpu, "gpu_launches": int(launches), "kernel": info, "clocks": clocks.summary(),
-            "e2e": e2e, "cpu_baseline": cpu_baseline, "parity": parity,
+            "early_out": early, "e2e": e2e, "cpu_baseline": cpu_baseline, "parity": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -386,6 +418,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: 1,048,576)")
     ap.add_argument("--envs-per-core", type=int, default=6, help="CPU arm: environments per host process per step")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-early-out", action="store_true")
     ap.add_argument("--skip-checks", action="store_true", help="skip the oracle parity spot check and the CPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":

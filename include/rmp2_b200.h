@@ -183,6 +183,13 @@ int64_t rmp2_launch_count(void);
  * pair loop; n_spheres selects the staging layout), 2 step (pullback + leaves + resolve). */
 int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_spheres, int32_t* regs,
                           int32_t* smem_bytes, int32_t* blocks_per_sm, int32_t* block_threads);
+/* Options of a tree.  RMP2_OPT_EARLY_OUT (default 1): the obstacle kernel evaluates only the
+ * (frame, sphere) pairs within the leaf's metric_modulation_radius; the others contribute exactly
+ * zero in the reference as well (rmp2.py:194), so results are unchanged.  Set to 0 to force every
+ * pair through the full arithmetic (used for the roofline measurement). */
+#define RMP2_OPT_EARLY_OUT 0
+int rmp2_tree_set_option(rmp2_tree* tree, int32_t option, int32_t value);
+
 /* Per-kernel device timing with CUDA events on the launching stream (bench.py's roofline leg).
  * rmp2_tree_profile_read waits for the recorded launches, returns the accumulated milliseconds and
  * launch counts of {frames, spheres, step} since the last read, and resets them. */

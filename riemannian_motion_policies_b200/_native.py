@@ -33,12 +33,14 @@ SPACE_FRAME_POSITION = 1
 SPACE_FRAME_DISTANCE_SPHERES = 2
 SPACE_FRAME_DISTANCE_PAIRS = 3
 
+OPT_EARLY_OUT = 0
+
 # every symbol include/rmp2_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "rmp2_robot_create", "rmp2_robot_destroy", "rmp2_tree_create", "rmp2_tree_destroy",
     "rmp2_tree_update_leaf", "rmp2_step", "rmp2_step_host", "rmp2_rollout", "rmp2_fk",
     "rmp2_leaf_evaluate", "rmp2_last_error", "rmp2_version", "rmp2_launch_count",
-    "rmp2_tree_kernel_info", "rmp2_tree_profile", "rmp2_tree_profile_read",
+    "rmp2_tree_kernel_info", "rmp2_tree_profile", "rmp2_tree_profile_read", "rmp2_tree_set_option",
 ]
 
 
@@ -116,6 +118,8 @@ def lib():
     L.rmp2_tree_kernel_info.argtypes = [vp, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32),
                                         ctypes.POINTER(i32)]
     L.rmp2_tree_kernel_info.restype = ctypes.c_int
+    L.rmp2_tree_set_option.argtypes = [vp, i32, i32]
+    L.rmp2_tree_set_option.restype = ctypes.c_int
     L.rmp2_tree_profile.argtypes = [vp, i32]
     L.rmp2_tree_profile.restype = ctypes.c_int
     L.rmp2_tree_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]

@@ -61,6 +61,7 @@ struct rmp2_tree {
   float* rec = nullptr;                   // [chunk][n_sphere_slots][12] scratch of rmp2_step
   size_t rec_floats = 0;
   bool profiling = false;
+  bool early_out = true;                  // RMP2_OPT_EARLY_OUT
   KernelClock clock[3];                   // frames, spheres, step
   HostStage stage[3];
 };
@@ -511,6 +512,7 @@ int build_args(const rmp2_tree* tree, const rmp2_step_io* io, StepArgs& A) {
   }
   A.pair_off[tree->n_pair_sets] = total;
   A.pair_total = total;
+  A.early_out = tree->early_out ? 1 : 0;
   if (total > 0 && !io->pairs) return fail(RMP2_ERR_INVALID, "pair counts > 0 but pairs is NULL");
   return RMP2_OK;
 }
@@ -767,6 +769,15 @@ int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_sphere
   if (blocks_per_sm) *blocks_per_sm = bps;
   if (block_threads) *block_threads = block;
   return RMP2_OK;
+}
+
+int rmp2_tree_set_option(rmp2_tree* tree, int32_t option, int32_t value) {
+  if (!tree) return fail(RMP2_ERR_INVALID, "null argument");
+  if (option == RMP2_OPT_EARLY_OUT) {
+    tree->early_out = value != 0;
+    return RMP2_OK;
+  }
+  return fail(RMP2_ERR_INVALID, "unknown option " + std::to_string(option));
 }
 
 int rmp2_tree_profile(rmp2_tree* tree, int32_t enable) {

@@ -104,7 +104,7 @@ RMP2_DEV void visit_frame(const StepTables& T, int fi, const float (&q)[N], cons
 }
 
 // ------------------------------------------------------------------------------- frames kernel
-// rec[env][slot] = (p, v, a, |v|^2, 0, 0) for every sphere-obstacle leaf slot.
+// rec[field][slot][env] = (p, v, a, |v|^2) for every sphere-obstacle leaf slot (fields 0..9).
 template <int N>
 __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
     rmp2_frames_kernel(const __grid_constant__ StepTables T, const __grid_constant__ StepArgs A) {
@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
   float zj[N][3], pj[N][3];   // unused (kCols = false), optimised away
   Chain ch;
   chain_reset(ch);
-  float4* rec = reinterpret_cast<float4*>(A.rec) + (size_t)env * T.n_sphere_slots * 3;
+  // records are field-major: rec[(field * L + slot) * B + env] -> every store below is one full line
+  float* rec = A.rec + env;
+  const size_t fstride = (size_t)T.n_sphere_slots * A.B;
   for (int fi = 0; fi < T.n_frames; ++fi) {
     visit_frame<N, false>(T, fi, q, qd, ch, zj, pj, slots);
     const FrameTab& F = T.frames[fi];
@@ -129,30 +131,38 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
       const LeafTab& L = T.leaves[li];
       if (L.space != RMP2_SPACE_FRAME_DISTANCE_SPHERES) continue;
       const float vv = fmaf(ch.v[0], ch.v[0], fmaf(ch.v[1], ch.v[1], ch.v[2] * ch.v[2]));
-      float4* r = rec + L.sphere_slot * 3;
-      r[0] = make_float4(ch.p[0], ch.p[1], ch.p[2], ch.v[0]);
-      r[1] = make_float4(ch.v[1], ch.v[2], ch.a[0], ch.a[1]);
-      r[2] = make_float4(ch.a[2], vv, 0.f, 0.f);
+      float* r = rec + (size_t)L.sphere_slot * A.B;
+      r[0 * fstride] = ch.p[0];
+      r[1 * fstride] = ch.p[1];
+      r[2 * fstride] = ch.p[2];
+      r[3 * fstride] = ch.v[0];
+      r[4 * fstride] = ch.v[1];
+      r[5 * fstride] = ch.v[2];
+      r[6 * fstride] = ch.a[0];
+      r[7 * fstride] = ch.a[1];
+      r[8 * fstride] = ch.a[2];
+      r[9 * fstride] = vv;
     }
   }
 }
 
 // ------------------------------------------------------------------------------ spheres kernel
-// Thread t of a block <-> (local environment t / L, obstacle-leaf slot t % L); the block owns E
-// consecutive environments.  Staged layout: box b (8 spheres) = E rows of 128 B, box stride padded to
+// Thread t of a block <-> (obstacle-leaf slot t / E, local environment t % E); the block owns E
+// consecutive environments, so record loads/stores are contiguous across lanes and every quarter
+// warp reads 8 distinct swizzled rows of the staged spheres.  Staged layout: box b (8 spheres) = E rows of 128 B, box stride padded to
 // 1024 B so that the 128-byte TMA swizzle (16-byte chunk index XOR row & 7) is row-relative.
-template <bool kTma>
+template <bool kTma, bool kSkip>
 __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
     rmp2_spheres_kernel(const __grid_constant__ SphereTables ST, const __grid_constant__ StepArgs A,
                         const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int L = ST.n_slots, E = ST.envs_per_block;
   const int t = threadIdx.x;
-  const int e_local = t / L, slot = t - e_local * L;
+  const int slot = t / E, e_local = t - slot * E;   // consecutive lanes = consecutive environments
   const long long env0 = (long long)blockIdx.x * E;
   const long long env = env0 + e_local;
   const int O = A.n_spheres;
-  const bool active = (e_local < E) && (env < A.B);
+  const bool active = (slot < L) && (env < A.B);
 
   uint32_t tiles = 0;
   if (kTma) {
@@ -175,12 +185,12 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
   }
 
   // this thread's frame record and leaf parameters
-  float4* rec = reinterpret_cast<float4*>(A.rec) + ((size_t)env * L + slot) * 3;
-  const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2];
-  const float px = r0.x, py = r0.y, pz = r0.z;
-  const float v[3] = {r0.w, r1.x, r1.y};
-  const float a[3] = {r1.z, r1.w, r2.x};
-  const float vv = r2.y;
+  float* rec = A.rec + (size_t)slot * A.B + env;
+  const size_t fstride = (size_t)L * A.B;
+  const float px = rec[0 * fstride], py = rec[1 * fstride], pz = rec[2 * fstride];
+  const float v[3] = {rec[3 * fstride], rec[4 * fstride], rec[5 * fstride]};
+  const float a[3] = {rec[6 * fstride], rec[7 * fstride], rec[8 * fstride]};
+  const float vv = rec[9 * fstride];
   float p[RMP2_LEAF_PARAMS];
 #pragma unroll
   for (int i = 0; i < RMP2_LEAF_PARAMS; ++i) p[i] = ST.p[slot][i];
@@ -197,29 +207,53 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
     const float d = fmaxf(fabsf(sd), 1e-12f);
     obstacle_pair(p, rx * sgn, ry * sgn, rz * sgn, d, fast_rcp(d), v, a, vv, S, g);
   };
-  if (kTma) {
-    const uint32_t x7 = ((uint32_t)e_local & 7u) << 4;
-    const uint32_t box_stride = ((uint32_t)E * 128u + 1023u) & ~1023u;
-    for (int hb = 0; hb < (O >> 2); ++hb) {                   // half a box (4 spheres) per trip
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        float4 sp;
-        const uint32_t c8 = (uint32_t)(hb & 1) * 4u + (uint32_t)c4;
-        const uint32_t addr = tiles + (uint32_t)(hb >> 1) * box_stride + ((c8 << 4) ^ x7);
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(sp.x), "=f"(sp.y), "=f"(sp.z), "=f"(sp.w)
-                     : "r"(addr));
-        one_sphere(sp);
+  const uint32_t x7 = ((uint32_t)e_local & 7u) << 4;
+  const uint32_t box_stride = ((uint32_t)E * 128u + 1023u) & ~1023u;
+  const float4* gs = reinterpret_cast<const float4*>(A.spheres) + (size_t)env * O;
+  auto load_sphere = [&](int o) -> float4 {
+    float4 sp;
+    if (kTma) {
+      const uint32_t addr = tiles + (uint32_t)(o >> 3) * box_stride + ((((uint32_t)o & 7u) << 4) ^ x7);
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(sp.x), "=f"(sp.y), "=f"(sp.z), "=f"(sp.w)
+                   : "r"(addr));
+    } else {
+      sp = __ldg(gs + o);
+    }
+    return sp;
+  };
+  if (!kSkip) {
+    for (int o4 = 0; o4 < (O & ~3); o4 += 4) {               // 4 spheres per trip: the unrolled body
+#pragma unroll                                                // stays inside the L0 instruction cache
+      for (int c4 = 0; c4 < 4; ++c4) one_sphere(load_sphere(o4 + c4));
+    }
+    for (int o = O & ~3; o < O; ++o) one_sphere(load_sphere(o));
+  } else {
+    // Exact early-out (reference: rmp2.py:194 -- a pair beyond the metric radius has M = 0 and adds
+    // exactly nothing): first a cheap squared-distance test of every sphere into a bit mask, then the
+    // full pair only for the set bits.  The test is conservative (1e-5 wider than the leaf's own test).
+    const float reach = (p[OA_R] + p[OA_MARGIN]) * 1.00001f;
+    for (int o0 = 0; o0 < O; o0 += 64) {
+      unsigned long long mask = 0ull;
+      const int cnt = min(64, O - o0);
+      for (int o = 0; o < cnt; ++o) {
+        const float4 sp = load_sphere(o0 + o);
+        const float rx = px - sp.x, ry = py - sp.y, rz = pz - sp.z;
+        const float dc2 = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+        const float lim = sp.w + reach;
+        mask |= (unsigned long long)(dc2 <= lim * lim) << o;
+      }
+      while (mask) {
+        const int o = __ffsll((long long)mask) - 1;
+        mask &= mask - 1ull;
+        one_sphere(load_sphere(o0 + o));
       }
     }
-  } else {
-    const float4* gs = reinterpret_cast<const float4*>(A.spheres) + (size_t)env * O;
-#pragma unroll 4
-    for (int o = 0; o < O; ++o) one_sphere(__ldg(gs + o));
   }
-  rec[0] = make_float4(S[0], S[1], S[2], S[3]);
-  rec[1] = make_float4(S[4], S[5], g[0], g[1]);
-  rec[2] = make_float4(g[2], 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) rec[i * fstride] = S[i];       // fields 0..5: S, 6..8: g (in place)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) rec[(6 + i) * fstride] = g[i];
 }
 
 // --------------------------------------------------------------------------------- step kernel
@@ -290,17 +324,12 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
         } else if (L.space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) {
           if (A.n_spheres <= 0) continue;
           // sums over this leaf's spheres, produced by rmp2_spheres_kernel
-          const float4* r = reinterpret_cast<const float4*>(A.rec) + ((size_t)e * T.n_sphere_slots + L.sphere_slot) * 3;
-          const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
-          S[0] += r0.x;
-          S[1] += r0.y;
-          S[2] += r0.z;
-          S[3] += r0.w;
-          S[4] += r1.x;
-          S[5] += r1.y;
-          g[0] += r1.z;
-          g[1] += r1.w;
-          g[2] += r2.x;
+          const float* r = A.rec + (size_t)L.sphere_slot * A.B + e;
+          const size_t fstride = (size_t)T.n_sphere_slots * A.B;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) S[i] += __ldg(r + i * fstride);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) g[i] += __ldg(r + (6 + i) * fstride);
           contrib = true;
         } else {  // RMP2_SPACE_FRAME_DISTANCE_PAIRS: explicit (pos_on_link, pos_on_obstacle) pairs
           const int k0 = A.pair_off[L.pair_set], k1 = A.pair_off[L.pair_set + 1];
@@ -637,14 +666,19 @@ cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, const
   if (blocks <= 0) return cudaSuccess;
   const int threads = ((ST.envs_per_block * ST.n_slots + 31) / 32) * 32;
   const size_t smem = rmp2_spheres_smem(ST, A.n_spheres, use_tma);
+  CUtensorMap dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  const CUtensorMap& tm = use_tma ? *tmap : dummy;
+  const unsigned nb = (unsigned)blocks;
   if (use_tma) {
-    cudaError_t e = cudaFuncSetAttribute(rmp2_spheres_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const void* fn = A.early_out ? (const void*)rmp2_spheres_kernel<true, true> : (const void*)rmp2_spheres_kernel<true, false>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rmp2_spheres_kernel<true><<<(unsigned)blocks, threads, smem, stream>>>(ST, A, *tmap);
+    if (A.early_out) rmp2_spheres_kernel<true, true><<<nb, threads, smem, stream>>>(ST, A, tm);
+    else rmp2_spheres_kernel<true, false><<<nb, threads, smem, stream>>>(ST, A, tm);
   } else {
-    CUtensorMap dummy;
-    memset(&dummy, 0, sizeof(dummy));
-    rmp2_spheres_kernel<false><<<(unsigned)blocks, threads, 0, stream>>>(ST, A, dummy);
+    if (A.early_out) rmp2_spheres_kernel<false, true><<<nb, threads, 0, stream>>>(ST, A, tm);
+    else rmp2_spheres_kernel<false, false><<<nb, threads, 0, stream>>>(ST, A, tm);
   }
   return cudaGetLastError();
 }
@@ -662,15 +696,15 @@ cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, si
   cudaFuncAttributes attr;
   cudaError_t e = cudaSuccess;
   if (which == 1) {
-    const void* fn = use_tma ? (const void*)rmp2_spheres_kernel<true> : (const void*)rmp2_spheres_kernel<false>;
+    const void* fn = use_tma ? (const void*)rmp2_spheres_kernel<true, false> : (const void*)rmp2_spheres_kernel<false, false>;
     e = cudaFuncGetAttributes(&attr, fn);
     if (e != cudaSuccess) return e;
     if (smem > 0) {
       e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
     }
-    e = use_tma ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rmp2_spheres_kernel<true>, block, smem)
-                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rmp2_spheres_kernel<false>, block, smem);
+    e = use_tma ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rmp2_spheres_kernel<true, false>, block, smem)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, rmp2_spheres_kernel<false, false>, block, smem);
   } else if (which == 0) {
     RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_frames_kernel<NN>),
                         e = (e == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(

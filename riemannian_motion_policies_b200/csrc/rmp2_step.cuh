@@ -241,17 +241,17 @@ RMP2_DEV void resolve_pinv(float (&G)[N][N], float (&y)[N], float rcond, float (
         rotated |= rot;
         // tan of the rotation angle, smaller root of t^2 + 2 zeta t - 1 = 0 with zeta = (b-a)/(2g):
         //   t = 2 g sign(b-a) / (|b-a| + sqrt((b-a)^2 + 4 g^2)).
-        // Any (c, s) gives an orthogonal-up-to-scale row transform and the solution below is invariant
-        // to row scaling, so the approximate intrinsics only affect the convergence rate.
+        // Lanes that do not rotate use g = 0, which yields t = 0, s = 0 and c ~ 1 by itself.  Any (c, s)
+        // gives an orthogonal-up-to-scale row transform and the solution below is invariant to row
+        // scaling, so the approximate MUFU results only affect the convergence rate.
+        const float ge = rot ? g : 0.f;
         const float tau = b - a;
-        const float hyp2 = fmaf(tau, tau, 4.f * g2);
+        const float hyp2 = fmaf(tau, tau, 4.f * ge * ge);
         const float hyp = hyp2 * fast_rsqrt(fmaxf(hyp2, 1e-37f));
-        const float t = ((tau < 0.f) ? -2.f * g : 2.f * g) * fast_rcp(fmaxf(fabsf(tau) + hyp, 1e-37f));
-        float c = fast_rsqrt(fmaf(t, t, 1.f));
-        float s = c * t;
-        const float tg = rot ? t * g : 0.f;          // sign(t g) = sign(b - a): the larger row gains
-        c = rot ? c : 1.f;
-        s = rot ? s : 0.f;
+        const float t = ((tau < 0.f) ? -2.f * ge : 2.f * ge) * fast_rcp(fmaxf(fabsf(tau) + hyp, 1e-37f));
+        const float c = fast_rsqrt(fmaf(t, t, 1.f));
+        const float s = c * t;
+        const float tg = t * ge;                      // sign(t g) = sign(b - a): the larger row gains
         nrm[p] = a - tg;
         nrm[q] = b + tg;
 #pragma unroll

@@ -9,7 +9,7 @@
 #define RMP2_VECPOOL 160          // floats: goals / q0 / limits of all leaves
 #define RMP2_SLOT_BASE (-2)       // restore_slot value meaning "start from the base link"
 #define RMP2_CHAIN_FLOATS 24      // R(9) p(3) w(3) v(3) alpha(3) a(3)
-#define RMP2_REC_FLOATS 12        // one frame record / one (S, g) record
+#define RMP2_REC_FLOATS 10        // fields of one frame record (p, v, a, |v|^2); (S, g) reuse 9 of them
 
 struct FrameTab {
   float R[9];            // constant rotation  (reference: kinematics.py:202, R_x R_y R_z order)
@@ -69,10 +69,11 @@ struct StepArgs {
   const float* goals;
   const float* spheres;
   const float* pairs;
-  float* rec;            // [B][n_sphere_slots][12] scratch: frame records in, (S, g) sums out
+  float* rec;            // [10][n_sphere_slots][B] scratch, field-major: frame records in, (S, g) sums out
   int32_t n_goal_slots;
   int32_t n_spheres;
   int32_t pair_total;
+  int32_t early_out;     // spheres kernel: skip pairs beyond the metric radius (exact, see rmp2.py:194)
   int32_t pair_off[RMP2_MAX_PAIR_SETS + 1];
   // rollout (rmp2_rollout): when n_sim_steps > 0 the step kernel integrates in place afterwards
   float* q_rw;

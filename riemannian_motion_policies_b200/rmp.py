@@ -249,6 +249,10 @@ class CompiledTree:
                              block_threads=block.value, warps_per_sm=bps.value * block.value // 32)
         return out
 
+    def set_early_out(self, enable=True):
+        """Skip (frame, sphere) pairs beyond the metric radius in the obstacle kernel (exact; default on)."""
+        _native.check(_native.lib().rmp2_tree_set_option(self.handle, _native.OPT_EARLY_OUT, 1 if enable else 0))
+
     def profile(self, enable=True):
         """Bracket every kernel launch of this tree with CUDA events (see ``profile_read``)."""
         _native.check(_native.lib().rmp2_tree_profile(self.handle, 1 if enable else 0))

@@ -152,6 +152,28 @@ def test_tma_and_direct_paths_agree(ns):
     np.testing.assert_array_equal(a, b)
 
 
+def test_early_out_is_exact(ns):
+    """Skipping pairs beyond the metric radius (library default) changes nothing: they contribute
+    exactly zero in the reference (rmp2.py:194)."""
+    n, B = 7, 4096
+    q, qd, goal, sph = make_inputs(5, n, B)
+    fk = product_fkine(ns, n)
+    core = product_core(ns, 5, n, fk)
+    dev = torch.device("cuda")
+    args = [torch.as_tensor(a, device=dev) for a in (q, qd)]
+    goals = torch.as_tensor(goal, device=dev).reshape(B, 1, 3).contiguous()
+    spheres = torch.as_tensor(sph, device=dev)
+    tree = core.compile(n, goal_leaves=["attractor"])
+    out = {}
+    for flag in (True, False):
+        tree.set_early_out(flag)
+        qdd = torch.empty(B, n, device=dev)
+        tree.step(args[0], args[1], qdd, goals=goals, spheres=spheres)
+        out[flag] = qdd.cpu().numpy()
+    tree.set_early_out(True)
+    np.testing.assert_array_equal(out[True], out[False])
+
+
 def test_joint_subset_pads_the_kernel_width(ns):
     """n = 5 controllable joints of the 7-joint arm (kernel instantiated for 7): joints outside `order`
     read q = 0 like the reference (kinematics.py:197,218-219); padded rows/cols stay zero."""
