@@ -257,8 +257,12 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 }
 
 // --------------------------------------------------------------------------------- step kernel
+// resident blocks per SM the register allocation aims at (N <= 7: 128 registers -> 16 warps/SM)
+#ifndef RMP2_STEP_MIN_BLOCKS
+#define RMP2_STEP_MIN_BLOCKS(N) ((N) <= 7 ? 4 : ((N) <= 9 ? 3 : 2))
+#endif
 template <int N>
-__global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
+__global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_STEP_MIN_BLOCKS(N))
     rmp2_step_kernel(const __grid_constant__ StepTables T, const __grid_constant__ StepArgs A) {
   extern __shared__ float slots[];
   const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
