@@ -47,29 +47,67 @@ def measured_peaks():
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """Samples SM clock, power and clock-event (throttle) reasons DURING the timed region: an NVML
+    polling thread (every ~2 ms; the timed region can be shorter than nvidia-smi's fastest period),
+    with an `nvidia-smi -lms` subprocess as fallback."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+        self.samples = []          # (sm_mhz, sm_max_mhz, power_w, reasons bitmask)
+        self.stop_flag = threading.Event()
+        self.nvml = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map through the UUID-free common case
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.nvml = None
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                              "--format=csv,noheader,nounits", "-lms", "100"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=self._read, daemon=True)
+                self.thread.start()
+            except OSError:
+                self.proc = None
         return self
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((float(sm), float(mx), float(pw), int(rs)))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def __exit__(self, *exc):
+        self.stop_flag.set()
+        if self.nvml is not None and self.thread is not None:
+            self.thread.join(timeout=1)
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -79,24 +117,39 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, power, reasons = [], [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for row in self.rows:
-            parts = [p.strip() for p in row.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+        if self.samples:
+            n = self.nvml
+            bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            for a, b, c, r in self.samples:
+                sm.append(a)
+                mx.append(b)
+                power.append(c)
+                for name, bit in bits.items():
+                    if r & bit:
+                        reasons.add(name)
+            source = "nvml"
+        else:
+            source = "nvidia-smi"
+            for row in self.rows:
+                parts = [p.strip() for p in row.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                    power.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(self.NAMES, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": source}
 
 
 # --------------------------------------------------------------------------------------- CPU arm
@@ -166,46 +219,6 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
-def synth_inputs(ns, fk, n, B, O_, n_buffers, seed, device):
-    """Seeded synthetic environments generated on the device (distribution: SURVEY.md section 8d)."""
-    import torch
-    from riemannian_motion_policies_b200 import scenarios as S
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    lo = torch.tensor(S.PANDA_Q_LOW[:n], dtype=torch.float32, device=device)
-    hi = torch.tensor(S.PANDA_Q_HIGH[:n], dtype=torch.float32, device=device)
-    q = lo + (hi - lo) * torch.rand(B, n, generator=g, device=device)
-    qd = -0.3 + 0.6 * torch.rand(B, n, generator=g, device=device)
-    glo = torch.tensor([0.3, -0.7, 0.3], device=device)
-    ghi = torch.tensor([0.7, 0.7, 0.7], device=device)
-    goal = glo + (ghi - glo) * torch.rand(B, 3, generator=g, device=device)
-    spheres = []
-    if O_:
-        frames = S.collision_frames(fk)
-        origins = torch.stack([fk.forward(q, fr)[:, :3, 3] for fr in frames], dim=1)       # [B,K,3] CUDA FK kernel
-        slo = torch.tensor([-0.8, -0.8, 0.0], device=device)
-        shi = torch.tensor([0.8, 0.8, 1.2], device=device)
-
-        def draw(count):
-            c = slo + (shi - slo) * torch.rand(count, 3, generator=g, device=device)
-            r = 0.025 + 0.075 * torch.rand(count, 1, generator=g, device=device)
-            return torch.cat([c, r], dim=-1)
-
-        for _ in range(n_buffers):
-            sph = draw(B * O_).reshape(B, O_, 4)
-            for _round in range(30):
-                bad = torch.zeros(B, O_, dtype=torch.bool, device=device)
-                for k in range(origins.shape[1]):                                         # keeps the temporaries [B,O]
-                    d = torch.linalg.norm(sph[:, :, :3] - origins[:, None, k, :], dim=-1) - sph[:, :, 3]
-                    bad |= d < 0.03
-                nbad = int(bad.sum())
-                if nbad == 0:
-                    break
-                sph[bad] = draw(nbad)
-            spheres.append(sph.contiguous())
-    return q.contiguous(), qd.contiguous(), goal.contiguous(), spheres
-
-
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -237,7 +250,7 @@ def run_b200_arm(args):
     tree.set_early_out(False)
 
     n_buffers = 4 if O_ else 1
-    q, qd, goal, spheres = synth_inputs(ns, fk, n, B, O_, n_buffers, seed=S.SEEDS[config] + 17 * rank, device=device)
+    q, qd, goal, spheres = S.synth_inputs_device(fk, n, B, O_, n_buffers, seed=S.SEEDS[config] + 17 * rank, device=device)
     goals = goal.reshape(B, 1, 3).contiguous()
     qdd = torch.empty(B, n, device=device)
 

@@ -223,11 +223,32 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
     return sp;
   };
   if (!kSkip) {
-    for (int o4 = 0; o4 < (O & ~3); o4 += 4) {               // 4 spheres per trip: the unrolled body
-#pragma unroll                                                // stays inside the L0 instruction cache
-      for (int c4 = 0; c4 < 4; ++c4) one_sphere(load_sphere(o4 + c4));
+    if (kTma) {
+      // 8 swizzled chunk addresses of this thread's row, advanced by one box stride per box;
+      // 4 spheres per trip so that the unrolled body stays inside the L0 instruction cache
+      uint32_t addr[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) addr[c] = tiles + ((((uint32_t)c) << 4) ^ x7);
+      for (int b = 0; b < (O >> 3); ++b) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            float4 sp;
+            const uint32_t ad = (h == 0) ? addr[c4] : addr[4 + c4];
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(sp.x), "=f"(sp.y), "=f"(sp.z), "=f"(sp.w)
+                         : "r"(ad));
+            one_sphere(sp);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) addr[c] += box_stride;
+      }
+    } else {
+#pragma unroll 4
+      for (int o = 0; o < O; ++o) one_sphere(load_sphere(o));
     }
-    for (int o = O & ~3; o < O; ++o) one_sphere(load_sphere(o));
   } else {
     // Exact early-out (reference: rmp2.py:194 -- a pair beyond the metric radius has M = 0 and adds
     // exactly nothing): first a cheap squared-distance test of every sphere into a bit mask, then the

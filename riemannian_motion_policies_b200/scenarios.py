@@ -184,3 +184,42 @@ def closest_points_on_spheres(origins, spheres):
     on_obst = spheres[None, :, :3] + spheres[None, :, 3:4] * r / dist
     on_link = np.broadcast_to(origins[:, None, :], on_obst.shape).copy()
     return on_link.astype(np.float32), on_obst.astype(np.float32)
+
+
+def synth_inputs_device(fk, n, B, O_, n_buffers, seed, device):
+    """Seeded synthetic environments generated on the device (distribution: SURVEY.md section 8d)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lo = torch.tensor(PANDA_Q_LOW[:n], dtype=torch.float32, device=device)
+    hi = torch.tensor(PANDA_Q_HIGH[:n], dtype=torch.float32, device=device)
+    q = lo + (hi - lo) * torch.rand(B, n, generator=g, device=device)
+    qd = -0.3 + 0.6 * torch.rand(B, n, generator=g, device=device)
+    glo = torch.tensor([0.3, -0.7, 0.3], device=device)
+    ghi = torch.tensor([0.7, 0.7, 0.7], device=device)
+    goal = glo + (ghi - glo) * torch.rand(B, 3, generator=g, device=device)
+    spheres = []
+    if O_:
+        frames = collision_frames(fk)
+        origins = torch.stack([fk.forward(q, fr)[:, :3, 3] for fr in frames], dim=1)       # [B,K,3] CUDA FK kernel
+        slo = torch.tensor([-0.8, -0.8, 0.0], device=device)
+        shi = torch.tensor([0.8, 0.8, 1.2], device=device)
+
+        def draw(count):
+            c = slo + (shi - slo) * torch.rand(count, 3, generator=g, device=device)
+            r = 0.025 + 0.075 * torch.rand(count, 1, generator=g, device=device)
+            return torch.cat([c, r], dim=-1)
+
+        for _ in range(n_buffers):
+            sph = draw(B * O_).reshape(B, O_, 4)
+            for _round in range(30):
+                bad = torch.zeros(B, O_, dtype=torch.bool, device=device)
+                for k in range(origins.shape[1]):                                         # keeps the temporaries [B,O]
+                    d = torch.linalg.norm(sph[:, :, :3] - origins[:, None, k, :], dim=-1) - sph[:, :, 3]
+                    bad |= d < 0.03
+                nbad = int(bad.sum())
+                if nbad == 0:
+                    break
+                sph[bad] = draw(nbad)
+            spheres.append(sph.contiguous())
+    return q.contiguous(), qd.contiguous(), goal.contiguous(), spheres

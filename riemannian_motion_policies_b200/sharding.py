@@ -1,0 +1,64 @@
+"""Environment-sharded data parallelism: one process per GPU, no collective on the step path.
+
+Environments are independent, so a batch of B environments is cut into `world_size` contiguous
+blocks; every rank runs the same compiled tree on its block.  The only
+communication is an optional all-gather of `qdd` when one host needs all results; it is not part
+of the step and is timed separately.  Works with the `nccl` backend on GPUs and with `gloo` on CPU
+tensors (used by the CPU tests of the partition / collection logic).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(B, world_size, rank):
+    """[lo, hi) of rank's contiguous block; the first B % world_size ranks hold one extra environment."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, extra = divmod(int(B), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard(t, world_size, rank):
+    """This rank's block of a [B, ...] tensor (a view, no copy)."""
+    lo, hi = shard_bounds(t.shape[0], world_size, rank)
+    return t[lo:hi]
+
+
+def gather_environments(local, B, group=None):
+    """All-gather per-rank blocks [b_r, ...] into the full [B, ...] tensor on every rank.
+    Blocks may differ by one row; they are padded to the largest block for the collective."""
+    world = dist.get_world_size(group)
+    sizes = [shard_bounds(B, world, r) for r in range(world)]
+    longest = max(hi - lo for lo, hi in sizes)
+    padded = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    out = torch.empty((world * longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    out = out.reshape((world, longest) + tuple(local.shape[1:]))
+    return torch.cat([out[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+
+
+class ShardedStep:
+    """Runs `step_fn(q, qd, goals, spheres) -> qdd` on this rank's block of every input."""
+
+    def __init__(self, step_fn, group=None):
+        self.step_fn = step_fn
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def local_inputs(self, *tensors):
+        return [None if t is None else shard(t, self.world, self.rank) for t in tensors]
+
+    def step_local(self, q, qd, goals=None, spheres=None):
+        """Inputs are the FULL batch (e.g. generated identically on every rank); only this rank's
+        block is evaluated.  No communication."""
+        ql, qdl, gl, sl = self.local_inputs(q, qd, goals, spheres)
+        return self.step_fn(ql, qdl, gl, sl)
+
+    def step_and_gather(self, q, qd, goals=None, spheres=None):
+        local = self.step_local(q, qd, goals, spheres)
+        if self.world == 1:
+            return local
+        return gather_environments(local, q.shape[0], self.group)

@@ -1,0 +1,111 @@
+"""Full-size checks (BASELINE.json sizes: 1,048,576 environments, 64 spheres) through properties that
+do not need the oracle at that size, plus an oracle spot check on a random subset."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_common import assert_parity
+from oracle import harness as H
+from riemannian_motion_policies_b200 import scenarios as S
+
+pytestmark = pytest.mark.gpu
+
+B_FULL = 1 << 20
+N = 7
+
+
+@pytest.fixture(scope="module")
+def world(native_lib):
+    ns = S.product_namespace()
+    dev = torch.device("cuda")
+    fk = ns.UrdfForwardKinematic(S.PANDA_WO_TOOL_URDF, S.PANDA_ORDER_7)
+    core = S.build_config4(ns, fk, [0.5, 0.0, 0.5], N, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance())
+    tree = core.compile(N, goal_leaves=["attractor"])
+    q, qd, goal, spheres = S.synth_inputs_device(fk, N, B_FULL, 64, 1, seed=3, device=dev)
+    goals = goal.reshape(B_FULL, 1, 3).contiguous()
+    qdd = torch.empty(B_FULL, N, device=dev)
+    tree.step(q, qd, qdd, goals=goals, spheres=spheres[0])
+    torch.cuda.synchronize()
+    return dict(ns=ns, fk=fk, core=core, tree=tree, q=q, qd=qd, goals=goals, spheres=spheres[0], qdd=qdd, dev=dev)
+
+
+def test_full_size_output_is_finite_and_deterministic(world):
+    w = world
+    assert torch.isfinite(w["qdd"]).all()
+    again = torch.empty_like(w["qdd"])
+    w["tree"].step(w["q"], w["qd"], again, goals=w["goals"], spheres=w["spheres"])
+    assert torch.equal(again, w["qdd"])
+
+
+def test_environments_are_independent(world):
+    """Permutation equivariance and chunk invariance: an environment's result does not depend on its
+    position in the batch, nor on what else is in the batch (blocks, tails, TMA tiles, chunking)."""
+    w = world
+    g = torch.Generator(device=w["dev"])
+    g.manual_seed(0)
+    perm = torch.randperm(B_FULL, generator=g, device=w["dev"])
+    out = torch.empty_like(w["qdd"])
+    w["tree"].step(w["q"][perm].contiguous(), w["qd"][perm].contiguous(), out, goals=w["goals"][perm].contiguous(),
+                   spheres=w["spheres"][perm].contiguous())
+    assert torch.equal(out, w["qdd"][perm])
+    for lo, hi in ((0, 1), (5, 5 + 33), (1000, 1000 + 65537), (B_FULL - 12345, B_FULL)):
+        part = torch.empty(hi - lo, N, device=w["dev"])
+        w["tree"].step(w["q"][lo:hi].contiguous(), w["qd"][lo:hi].contiguous(), part,
+                       goals=w["goals"][lo:hi].contiguous(), spheres=w["spheres"][lo:hi].contiguous())
+        assert torch.equal(part, w["qdd"][lo:hi])
+
+
+def test_full_size_subset_against_oracle(world):
+    w = world
+    rng = np.random.RandomState(1)
+    idx = torch.as_tensor(np.sort(rng.choice(B_FULL, size=512, replace=False)), device=w["dev"])
+    q, qd = w["q"][idx].cpu().numpy(), w["qd"][idx].cpu().numpy()
+    goal, sph = w["goals"][idx, 0].cpu().numpy(), w["spheres"][idx].cpu().numpy()
+    ref32 = H.evaluate_vmap(4, N, q, qd, goal, sph, dtype=torch.float32)
+    ref64 = H.evaluate_vmap(4, N, q, qd, goal, sph, dtype=torch.float64)
+    _, M64 = H.combined_vmap(4, N, q, qd, goal, sph, dtype=torch.float64)
+    stats = assert_parity(w["qdd"][idx].cpu().numpy(), ref32, ref64, M64, N, label="1M-env subset", max_excluded=0.10)
+    print(stats)
+
+
+def test_host_buffer_path_matches_device_path(world):
+    """rmp2_step_host (pinned host tensors, chunked 3-stream pipeline) == rmp2_step."""
+    w = world
+    Bh = 200_000                         # three 64k chunks + a ragged one
+    pin = lambda t: t[:Bh].cpu().pin_memory()
+    qdd_h = torch.empty(Bh, N).pin_memory()
+    w["tree"].step_host(pin(w["q"]), pin(w["qd"]), qdd_h, goals=pin(w["goals"]), spheres=pin(w["spheres"]))
+    assert torch.equal(qdd_h, w["qdd"][:Bh].cpu())
+    # pageable (non-pinned) host memory also works
+    qdd_p = torch.empty(1000, N)
+    w["tree"].step_host(w["q"][:1000].cpu(), w["qd"][:1000].cpu(), qdd_p, goals=w["goals"][:1000].cpu(),
+                        spheres=w["spheres"][:1000].cpu())
+    assert torch.equal(qdd_p, w["qdd"][:1000].cpu())
+
+
+def test_rollout_equals_stepwise_euler(world):
+    """rmp2_rollout (control every 10 steps, dt = 0.01; the 100 Hz / 10 Hz loop of
+    experiments/franka_panda/05_obstacle_avoidance.py:92-97 with an Euler integrator) equals the same
+    loop written with single steps on the host side."""
+    w = world
+    ns, fk, dev = w["ns"], w["fk"], w["dev"]
+    # the damped full tree (config 5): a closed loop without a damping leaf is not a meaningful rollout
+    core = S.build_config5(ns, fk, [0.5, 0.0, 0.5], N, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance())
+    tree = core.compile(N, goal_leaves=["attractor"])
+    Br, dt, n_steps, every = 4096, 0.01, 30, 10
+    q, qd = w["q"][:Br].clone(), w["qd"][:Br].clone()
+    goals, sph = w["goals"][:Br].contiguous(), w["spheres"][:Br].contiguous()
+    qdd = torch.empty(Br, N, device=dev)
+    tree.rollout(q, qd, qdd, dt, n_steps, every, goals=goals, spheres=sph)
+    q2, qd2 = w["q"][:Br].clone(), w["qd"][:Br].clone()
+    cmd = torch.empty(Br, N, device=dev)
+    for step in range(n_steps):
+        if step % every == 0:
+            tree.step(q2, qd2, cmd, goals=goals, spheres=sph)
+        qd2 = torch.addcmul(qd2, cmd, torch.tensor(dt, device=dev))
+        q2 = torch.addcmul(q2, qd2, torch.tensor(dt, device=dev))
+    assert torch.isfinite(q).all() and torch.isfinite(q2).all()
+    # same arithmetic up to fma contraction of the integrator; chaotic amplification over 3 control
+    # steps stays far below these bounds
+    torch.testing.assert_close(q, q2, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(qd, qd2, rtol=1e-3, atol=1e-4)
