@@ -383,7 +383,7 @@ def run_b200_arm(args):
         total_kernel_ms = sum(v[0] for v in kernel_ms.values()) / args.steps
         # algorithmic bytes / flops of one launch of the dominant kernel
         if O_:
-            dom_bytes = B * (16.0 * O_ + 2 * 48.0 * n_slots)       # spheres in, frame records in, (S,g) records out
+            dom_bytes = B * (16.0 * O_ + 76.0 * n_slots)           # spheres in, 40 B frame record in, 36 B (S,g) out
             dom_flops = B * 76.0 * O_ * n_slots                    # SURVEY.md 8d term C
         else:
             dom_bytes = B * BYTES_PER_ENV[config]
