@@ -141,9 +141,9 @@ int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* 
 
 /* qdd = pinv(sum_l J_l^T M_l J_l) * sum_l J_l^T M_l (xdd_l - Jdot_l qd) for B environments.
  * Stands in for RmpCore.evaluate (rmp.py:133-155).  All io pointers are device memory.
- * Launches up to three kernels on `stream` (frames -> spheres -> step).  The tree handle owns a
- * scratch buffer for the per-(environment, obstacle leaf) records (48 B each, at most 2^20
- * environments at a time) that is allocated on first use and grown when needed; therefore the steps
+ * Launches up to four kernels on `stream` (frames -> spheres -> step -> resolve).  The tree handle owns
+ * scratch buffers for the per-(environment, obstacle leaf) records (40 B each) and the combined metric
+ * (at most 2^20 environments at a time), allocated on first use and grown when needed; therefore the steps
  * of ONE tree must be issued from one thread on one stream at a time. */
 int rmp2_step(const rmp2_tree* tree, const rmp2_step_io* io, void* stream);
 
@@ -180,7 +180,8 @@ const char* rmp2_version(void);
 int64_t rmp2_launch_count(void);
 /* registers/thread, dynamic shared memory, max resident blocks/SM and block size of one of the
  * kernels a step launches: which = 0 frames (chain -> frame records), 1 spheres (the obstacle
- * pair loop; n_spheres selects the staging layout), 2 step (pullback + leaves + resolve). */
+ * pair loop; n_spheres selects the staging layout), 2 step with the resolve fused (small batches),
+ * 3 step without it and 4 the stand-alone resolve kernel (large batches). */
 int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_spheres, int32_t* regs,
                           int32_t* smem_bytes, int32_t* blocks_per_sm, int32_t* block_threads);
 /* Options of a tree.  RMP2_OPT_EARLY_OUT (default 1): the obstacle kernel evaluates only the
@@ -192,9 +193,9 @@ int rmp2_tree_set_option(rmp2_tree* tree, int32_t option, int32_t value);
 
 /* Per-kernel device timing with CUDA events on the launching stream (bench.py's roofline leg).
  * rmp2_tree_profile_read waits for the recorded launches, returns the accumulated milliseconds and
- * launch counts of {frames, spheres, step} since the last read, and resets them. */
+ * launch counts of {frames, spheres, step, resolve} since the last read, and resets them. */
 int rmp2_tree_profile(rmp2_tree* tree, int32_t enable);
-int rmp2_tree_profile_read(rmp2_tree* tree, double* ms /*[3]*/, int64_t* launches /*[3]*/);
+int rmp2_tree_profile_read(rmp2_tree* tree, double* ms /*[4]*/, int64_t* launches /*[4]*/);
 
 #ifdef __cplusplus
 }

@@ -58,11 +58,13 @@ struct rmp2_tree {
   int n_pair_sets = 0;
   int n_goal_slots_used = 0;
   SphereTables sph;                       // parameters of the sphere-obstacle leaves, by record slot
-  float* rec = nullptr;                   // [chunk][n_sphere_slots][12] scratch of rmp2_step
+  float* rec = nullptr;                   // sphere-record scratch of rmp2_step (field-major, see rmp2_tables.h)
   size_t rec_floats = 0;
+  float* mf = nullptr;                    // combined (M, f) scratch when the resolve runs as its own kernel
+  size_t mf_floats = 0;
   bool profiling = false;
   bool early_out = true;                  // RMP2_OPT_EARLY_OUT
-  KernelClock clock[3];                   // frames, spheres, step
+  KernelClock clock[4];                   // frames, spheres, step, resolve
   HostStage stage[3];
 };
 
@@ -390,6 +392,7 @@ void rmp2_tree_destroy(rmp2_tree* tree) {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   if (tree->rec) cudaFree(tree->rec);
+  if (tree->mf) cudaFree(tree->mf);
   for (auto& c : tree->clock)
     for (auto ev : c.pending) cudaEventDestroy(ev);
   delete tree;
@@ -549,7 +552,28 @@ int launch_chunk(rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
   }
   if (e != cudaSuccess) return cuda_fail(e, "rmp2_step_kernel launch");
   g_launches.fetch_add(1);
+  if (A.mf) {
+    {
+      ScopedClock clk(tree, 3, stream);
+      e = rmp2_launch_resolve(T, A, block, stream);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "rmp2_resolve_kernel launch");
+    g_launches.fetch_add(1);
+  }
   return RMP2_OK;
+}
+
+// Large batches run the resolve as its own kernel (smaller code and register footprint for both
+// halves); small ones keep it fused (one launch less, latency).  RMP2_SPLIT_RESOLVE=0/1 overrides.
+bool split_resolve(long long B) {
+  const char* v = getenv("RMP2_SPLIT_RESOLVE");
+  if (v) return v[0] == '1';
+  return B >= 32768;
+}
+
+size_t mf_floats_for(const rmp2_tree* tree, long long B) {
+  const int N = rmp2_pick_width(tree->tab.n);
+  return (size_t)B * (N * N + N);
 }
 
 size_t rec_floats_for(const rmp2_tree* tree, long long B, int n_spheres) {
@@ -575,6 +599,20 @@ int launch(rmp2_tree* tree, const StepArgs& A0, cudaStream_t stream) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc of the sphere-record scratch");
     tree->rec_floats = need;
   }
+  const bool split = split_resolve(chunk);
+  const size_t need_mf = split ? mf_floats_for(tree, chunk) : 0;
+  if (need_mf > tree->mf_floats) {
+    if (tree->mf) {
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) return cuda_fail(e, "synchronize before growing the scratch");
+      cudaFree(tree->mf);
+      tree->mf = nullptr;
+      tree->mf_floats = 0;
+    }
+    cudaError_t e = cudaMalloc(&tree->mf, need_mf * sizeof(float));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc of the (M, f) scratch");
+    tree->mf_floats = need_mf;
+  }
   const int n = tree->tab.n;
   for (long long e0 = 0; e0 < B; e0 += chunk) {
     StepArgs A = A0;
@@ -588,6 +626,7 @@ int launch(rmp2_tree* tree, const StepArgs& A0, cudaStream_t stream) {
     if (A0.spheres) A.spheres = A0.spheres + e0 * (long long)A0.n_spheres * 4;
     if (A0.pairs) A.pairs = A0.pairs + e0 * (long long)A0.pair_total * 6;
     A.rec = tree->rec;
+    A.mf = split ? tree->mf : nullptr;
     int rc = launch_chunk(tree, A, stream);
     if (rc != RMP2_OK) return rc;
   }
@@ -648,7 +687,9 @@ int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io) {
   const size_t off_sph = off_goal + pad4((size_t)chunk * G * 3);
   const size_t off_pair = off_sph + pad4((size_t)chunk * O * 4);
   const size_t off_rec = off_pair + pad4((size_t)chunk * K * 6);
-  const size_t total = off_rec + pad4(rec_floats_for(tree, chunk, O));
+  const size_t off_mf = off_rec + pad4(rec_floats_for(tree, chunk, O));
+  const bool split = split_resolve(chunk);
+  const size_t total = off_mf + (split ? pad4(mf_floats_for(tree, chunk)) : 0);
   for (auto& s : tree->stage) {
     if (!s.stream) {
       cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
@@ -688,6 +729,7 @@ int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io) {
     A.spheres = O ? s.buf + off_sph : nullptr;
     A.pairs = K ? s.buf + off_pair : nullptr;
     A.rec = s.buf + off_rec;
+    A.mf = split ? s.buf + off_mf : nullptr;
     rc = launch_chunk(tree, A, s.stream);
     if (rc != RMP2_OK) return rc;
     e = cudaMemcpyAsync(io->qdd + e0 * n, s.buf + off_qdd, (size_t)cb * n * sizeof(float), cudaMemcpyDeviceToHost, s.stream);
@@ -751,9 +793,10 @@ int rmp2_leaf_evaluate(const rmp2_leaf_desc* leaf, int32_t m, int64_t K, const f
 int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_spheres, int32_t* regs, int32_t* smem_bytes,
                           int32_t* blocks_per_sm, int32_t* block_threads) {
   if (!tree) return fail(RMP2_ERR_INVALID, "null argument");
-  if (which < 0 || which > 2) return fail(RMP2_ERR_INVALID, "which must be 0 (frames), 1 (spheres) or 2 (step)");
+  if (which < 0 || which > 4)
+    return fail(RMP2_ERR_INVALID, "which must be 0 (frames), 1 (spheres), 2 (step, fused), 3 (step, split) or 4 (resolve)");
   int block = RMP2_BLOCK_THREADS;
-  size_t smem = (size_t)tree->tab.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
+  size_t smem = (which == 4) ? 0 : (size_t)tree->tab.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
   bool use_tma = false;
   if (which == 1) {
     if (tree->tab.n_sphere_slots == 0) return fail(RMP2_ERR_INVALID, "tree has no sphere-obstacle leaves");
@@ -788,7 +831,7 @@ int rmp2_tree_profile(rmp2_tree* tree, int32_t enable) {
 
 int rmp2_tree_profile_read(rmp2_tree* tree, double* ms, int64_t* launches) {
   if (!tree || !ms || !launches) return fail(RMP2_ERR_INVALID, "null argument");
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < 4; ++k) {
     KernelClock& c = tree->clock[k];
     for (size_t i = 0; i + 1 < c.pending.size(); i += 2) {
       cudaError_t e = cudaEventSynchronize(c.pending[i + 1]);

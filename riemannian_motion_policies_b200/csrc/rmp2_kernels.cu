@@ -278,12 +278,50 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 }
 
 // --------------------------------------------------------------------------------- step kernel
+// Tail shared by the fused step kernel and the resolve kernel: optional explicit-Euler sub-steps with
+// the command held (reference loop: control at 10 Hz, simulation at 100 Hz --
+// experiments/franka_panda/05_obstacle_avoidance.py:92-97), then the stores.
+template <int N>
+RMP2_DEV void finish_step(const StepArgs& A, int n, long long e, bool active, bool rollout, float (&q)[N],
+                          float (&qd)[N], const float (&qdd)[N]) {
+  if (rollout) {
+    for (int s = 0; s < A.n_sim_steps; ++s) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        qd[j] = fmaf(qdd[j], A.dt, qd[j]);
+        q[j] = fmaf(qd[j], A.dt, q[j]);
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        if (j < n) {
+          A.q_rw[e * n + j] = q[j];
+          A.qd_rw[e * n + j] = qd[j];
+        }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (j < n) A.qdd[e * n + j] = qdd[j];
+  }
+}
+
+#ifndef RMP2_RESOLVE_MIN_BLOCKS
+#define RMP2_RESOLVE_MIN_BLOCKS(N) ((N) <= 7 ? 6 : ((N) <= 9 ? 3 : 2))
+#endif
+#ifndef RMP2_SPLIT_MIN_BLOCKS
+#define RMP2_SPLIT_MIN_BLOCKS(N) ((N) <= 7 ? 4 : ((N) <= 9 ? 3 : 2))
+#endif
 // resident blocks per SM the register allocation aims at (N <= 7: 128 registers -> 16 warps/SM)
 #ifndef RMP2_STEP_MIN_BLOCKS
 #define RMP2_STEP_MIN_BLOCKS(N) ((N) <= 7 ? 4 : ((N) <= 9 ? 3 : 2))
 #endif
-template <int N>
-__global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_STEP_MIN_BLOCKS(N))
+// kSplit: stop after the combined (M, f) and hand them to rmp2_resolve_kernel through A.mf
+// (field-major [N*N + N][B]); used for large batches, where two small kernels beat one big one.
+template <int N, bool kSplit>
+__global__ void __launch_bounds__(RMP2_BLOCK_THREADS, kSplit ? RMP2_SPLIT_MIN_BLOCKS(N) : RMP2_STEP_MIN_BLOCKS(N))
     rmp2_step_kernel(const __grid_constant__ StepTables T, const __grid_constant__ StepArgs A) {
   extern __shared__ float slots[];
   const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,32 +483,47 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_STEP_MIN_BLOCKS(N))
         }
     }
   }
-  resolve_pinv<N>(M, f, T.rcond, qdd);
-
-  if (rollout) {
-    // explicit Euler with the command held for n_sim_steps sub-steps (reference loop: control at
-    // 10 Hz, simulation at 100 Hz -- experiments/franka_panda/05_obstacle_avoidance.py:92-97)
-    for (int s = 0; s < A.n_sim_steps; ++s) {
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        qd[j] = fmaf(qdd[j], A.dt, qd[j]);
-        q[j] = fmaf(qd[j], A.dt, q[j]);
-      }
-    }
+  if (kSplit) {
     if (active) {
+      float* o = A.mf + e;
 #pragma unroll
-      for (int j = 0; j < N; ++j)
-        if (j < n) {
-          A.q_rw[e * n + j] = q[j];
-          A.qd_rw[e * n + j] = qd[j];
-        }
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) o[(size_t)(i * N + j) * A.B] = M[i][j];
+#pragma unroll
+      for (int i = 0; i < N; ++i) o[(size_t)(N * N + i) * A.B] = f[i];
     }
+    return;
   }
-  if (active) {
+  resolve_pinv<N>(M, f, T.rcond, qdd);
+  finish_step<N>(A, n, e, active, rollout, q, qd, qdd);
+}
+
+// -------------------------------------------------------------------------------- resolve kernel
+template <int N>
+__global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_RESOLVE_MIN_BLOCKS(N))
+    rmp2_resolve_kernel(const __grid_constant__ ResolveArgs R, const __grid_constant__ StepArgs A) {
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = env < A.B;                 // full-warp votes inside: no early return
+  const long long e = active ? env : A.B - 1;
+  const int n = R.n;
+  const bool rollout = A.n_sim_steps > 0;
+  float M[N][N], f[N], qdd[N];
+  const float* in = A.mf + e;
 #pragma unroll
-    for (int j = 0; j < N; ++j)
-      if (j < n) A.qdd[e * n + j] = qdd[j];
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j) M[i][j] = __ldg(in + (size_t)(i * N + j) * A.B);
+#pragma unroll
+  for (int i = 0; i < N; ++i) f[i] = __ldg(in + (size_t)(N * N + i) * A.B);
+  resolve_pinv<N>(M, f, R.rcond, qdd);
+  float q[N], qd[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    q[j] = (rollout && j < n) ? A.q_rw[e * n + j] : 0.f;
+    qd[j] = (rollout && j < n) ? A.qd_rw[e * n + j] : 0.f;
   }
+  finish_step<N>(A, n, e, active, rollout, q, qd, qdd);
 }
 
 // --------------------------------------------------------------------------------------- FK kernel
@@ -712,7 +765,21 @@ cudaError_t rmp2_launch_step(const StepTables& T, const StepArgs& A, int block, 
   const long long blocks = (A.B + block - 1) / block;
   if (blocks <= 0) return cudaSuccess;
   const size_t smem = (size_t)T.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
-  RMP2_DISPATCH_N(T.n, (rmp2_step_kernel<NN><<<(unsigned)blocks, block, smem, stream>>>(T, A)));
+  if (A.mf) {
+    RMP2_DISPATCH_N(T.n, (rmp2_step_kernel<NN, true><<<(unsigned)blocks, block, smem, stream>>>(T, A)));
+  } else {
+    RMP2_DISPATCH_N(T.n, (rmp2_step_kernel<NN, false><<<(unsigned)blocks, block, smem, stream>>>(T, A)));
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t rmp2_launch_resolve(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream) {
+  const long long blocks = (A.B + block - 1) / block;
+  if (blocks <= 0) return cudaSuccess;
+  ResolveArgs R;
+  R.n = T.n;
+  R.rcond = T.rcond;
+  RMP2_DISPATCH_N(T.n, (rmp2_resolve_kernel<NN><<<(unsigned)blocks, block, 0, stream>>>(R, A)));
   return cudaGetLastError();
 }
 
@@ -734,10 +801,18 @@ cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, si
     RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_frames_kernel<NN>),
                         e = (e == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                                                      blocks_per_sm, rmp2_frames_kernel<NN>, block, smem) : e));
-  } else {
-    RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_step_kernel<NN>),
+  } else if (which == 2) {
+    RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_step_kernel<NN, false>),
                         e = (e == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                                                     blocks_per_sm, rmp2_step_kernel<NN>, block, smem) : e));
+                                                     blocks_per_sm, rmp2_step_kernel<NN, false>, block, smem) : e));
+  } else if (which == 3) {
+    RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_step_kernel<NN, true>),
+                        e = (e == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                                                     blocks_per_sm, rmp2_step_kernel<NN, true>, block, smem) : e));
+  } else {
+    RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_resolve_kernel<NN>),
+                        e = (e == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                                                     blocks_per_sm, rmp2_resolve_kernel<NN>, block, 0) : e));
   }
   if (e != cudaSuccess) return e;
   *regs = attr.numRegs;

@@ -18,7 +18,8 @@ size_t rmp2_spheres_smem(const SphereTables& ST, int n_spheres, bool use_tma);
 cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, const CUtensorMap* tmap, bool use_tma,
                                 cudaStream_t stream);
 cudaError_t rmp2_launch_step(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);
-// which: 0 frames, 1 spheres, 2 step
+cudaError_t rmp2_launch_resolve(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);
+// which: 0 frames, 1 spheres, 2 step (fused resolve), 3 step (split), 4 resolve
 cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, size_t smem, int* regs,
                                    int* blocks_per_sm);
 cudaError_t rmp2_launch_fk(const StepTables& T, long long B, const float* q, const float* qd, float* x, float* xd,

@@ -60,6 +60,11 @@ struct SphereTables {
   float p[RMP2_MAX_LEAVES][RMP2_LEAF_PARAMS];
 };
 
+struct ResolveArgs {
+  int32_t n;
+  float rcond;
+};
+
 // per-call arguments (device pointers)
 struct StepArgs {
   long long B;
@@ -70,6 +75,7 @@ struct StepArgs {
   const float* spheres;
   const float* pairs;
   float* rec;            // [10][n_sphere_slots][B] scratch, field-major: frame records in, (S, g) sums out
+  float* mf;             // [N*N + N][B] scratch (N = kernel width): combined M and f, or NULL = fused resolve
   int32_t n_goal_slots;
   int32_t n_spheres;
   int32_t pair_total;

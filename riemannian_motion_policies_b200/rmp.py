@@ -234,13 +234,13 @@ class CompiledTree:
                                                  current_stream_ptr(q.device)))
         return q, qd, qdd
 
-    KERNELS = ("frames", "spheres", "step")
+    KERNELS = ("frames", "spheres", "step", "resolve")
 
     def kernel_info(self, n_spheres=64):
-        """registers / shared memory / resident blocks per SM of the kernels one step launches."""
+        """registers / shared memory / resident blocks per SM of the kernels one step can launch."""
         out = {}
-        for which, name in enumerate(self.KERNELS):
-            if name != "step" and not self.uses_spheres:
+        for which, name in enumerate(("frames", "spheres", "step_fused", "step", "resolve")):
+            if name in ("frames", "spheres") and not self.uses_spheres:
                 continue
             regs, smem, bps, block = (ctypes.c_int32() for _ in range(4))
             _native.check(_native.lib().rmp2_tree_kernel_info(self.handle, which, n_spheres, ctypes.byref(regs),
@@ -259,8 +259,8 @@ class CompiledTree:
 
     def profile_read(self):
         """-> {kernel: (milliseconds, launches)} accumulated since the last read."""
-        ms = (ctypes.c_double * 3)()
-        launches = (ctypes.c_int64 * 3)()
+        ms = (ctypes.c_double * 4)()
+        launches = (ctypes.c_int64 * 4)()
         _native.check(_native.lib().rmp2_tree_profile_read(self.handle, ms, launches))
         return {name: (ms[i], launches[i]) for i, name in enumerate(self.KERNELS)}
 
