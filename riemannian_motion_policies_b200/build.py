@@ -26,7 +26,7 @@ def build(force=False, verbose=True):
             print(f"[rmp2_b200] {OUT} is up to date")
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + SOURCES
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("RMP2_NVCC_EXTRA", "").split() + ["-o", OUT] + SOURCES
     if verbose:
         print("[rmp2_b200]", " ".join(cmd))
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)

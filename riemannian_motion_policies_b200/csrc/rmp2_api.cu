@@ -374,6 +374,12 @@ int rmp2_tree_create(const rmp2_robot* rb, const rmp2_leaf_desc* leaves, int32_t
       if (rc != RMP2_OK) { delete tr; return rc; }
     }
   T.n_leaves = leaf_cursor;
+  // leaves whose metric is a positive multiple of the identity keep M well conditioned
+  T.precondition = 1;
+  for (int i = 0; i < n_leaves; ++i) {
+    const int t = leaves[i].type;
+    if (t == RMP2_LEAF_CONFIG_BIASING || t == RMP2_LEAF_JOINT_DAMPING || t == RMP2_LEAF_CSPACE_BIASING) T.precondition = 0;
+  }
   tr->sph.n_slots = T.n_sphere_slots;
   if (T.n_sphere_slots > 0) {
     // E environments per block: E * L threads <= 128, E <= 32 (box rows), shared memory bounded

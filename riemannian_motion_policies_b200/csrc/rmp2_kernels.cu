@@ -495,12 +495,14 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, kSplit ? RMP2_SPLIT_MIN_BL
     }
     return;
   }
-  resolve_pinv<N>(M, f, T.rcond, qdd);
+  resolve_pinv<N, false>(M, f, T.rcond, qdd);
   finish_step<N>(A, n, e, active, rollout, q, qd, qdd);
 }
 
 // -------------------------------------------------------------------------------- resolve kernel
-template <int N>
+// kQr: precondition with a pivoted QR (trees without an isotropic metric leaf, i.e. possibly
+// rank-deficient: fewer Jacobi sweeps); well-conditioned trees skip it.
+template <int N, bool kQr>
 __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_RESOLVE_MIN_BLOCKS(N))
     rmp2_resolve_kernel(const __grid_constant__ ResolveArgs R, const __grid_constant__ StepArgs A) {
   const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -516,7 +518,7 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_RESOLVE_MIN_BLOCKS(N)
     for (int j = 0; j < N; ++j) M[i][j] = __ldg(in + (size_t)(i * N + j) * A.B);
 #pragma unroll
   for (int i = 0; i < N; ++i) f[i] = __ldg(in + (size_t)(N * N + i) * A.B);
-  resolve_pinv<N>(M, f, R.rcond, qdd);
+  resolve_pinv<N, kQr>(M, f, R.rcond, qdd);
   float q[N], qd[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
@@ -779,7 +781,11 @@ cudaError_t rmp2_launch_resolve(const StepTables& T, const StepArgs& A, int bloc
   ResolveArgs R;
   R.n = T.n;
   R.rcond = T.rcond;
-  RMP2_DISPATCH_N(T.n, (rmp2_resolve_kernel<NN><<<(unsigned)blocks, block, 0, stream>>>(R, A)));
+  if (T.precondition) {
+    RMP2_DISPATCH_N(T.n, (rmp2_resolve_kernel<NN, true><<<(unsigned)blocks, block, 0, stream>>>(R, A)));
+  } else {
+    RMP2_DISPATCH_N(T.n, (rmp2_resolve_kernel<NN, false><<<(unsigned)blocks, block, 0, stream>>>(R, A)));
+  }
   return cudaGetLastError();
 }
 
@@ -810,9 +816,9 @@ cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, si
                         e = (e == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                                                      blocks_per_sm, rmp2_step_kernel<NN, true>, block, smem) : e));
   } else {
-    RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_resolve_kernel<NN>),
+    RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_resolve_kernel<NN, true>),
                         e = (e == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                                                     blocks_per_sm, rmp2_resolve_kernel<NN>, block, 0) : e));
+                                                     blocks_per_sm, rmp2_resolve_kernel<NN, true>, block, 0) : e));
   }
   if (e != cudaSuccess) return e;
   *regs = attr.numRegs;

@@ -191,9 +191,88 @@ struct JacobiSchedule {
   }
 };
 
+// Householder QR with column pivoting, in place on the augmented matrix:  [G | y] <- [R | Q^T y],
+// columns of G permuted so that |R_11| >= |R_22| >= ...;  perm[j] = original column now at position j.
+// Purpose: preconditioner.  The rows of R are graded and R R^T is far closer to diagonal than M M^T,
+// which cuts the Jacobi sweeps on rank-deficient trees from ~7 to ~4 (Drmac & Veselic, SIMAX 2008, use
+// the same device).  pinv(M) f = P pinv(R) Q^T f, so the truncation rule is unchanged.
 template <int N>
+RMP2_DEV void qr_column_pivoting(float (&G)[N][N], float (&y)[N], int (&perm)[N]) {
+  float cn[N];                                   // squared norms of the trailing part of each column
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    perm[j] = j;
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) a = fmaf(G[i][j], G[i][j], a);
+    cn[j] = a;
+  }
+#pragma unroll
+  for (int k = 0; k < N - 1; ++k) {
+    int piv = k;
+    float best = cn[k];
+#pragma unroll
+    for (int j = k + 1; j < N; ++j)
+      if (cn[j] > best) {
+        best = cn[j];
+        piv = j;
+      }
+#pragma unroll
+    for (int j = k + 1; j < N; ++j) {
+      const bool sw = (piv == j);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const float a = G[i][k], b = G[i][j];
+        G[i][k] = sw ? b : a;
+        G[i][j] = sw ? a : b;
+      }
+      const float ca = cn[k], cb = cn[j];
+      cn[k] = sw ? cb : ca;
+      cn[j] = sw ? ca : cb;
+      const int pa = perm[k], pb = perm[j];
+      perm[k] = sw ? pb : pa;
+      perm[j] = sw ? pa : pb;
+    }
+    float nrm2 = 0.f;
+#pragma unroll
+    for (int i = k; i < N; ++i) nrm2 = fmaf(G[i][k], G[i][k], nrm2);
+    const float nrm = sqrtf(nrm2);
+    const float x0 = G[k][k];
+    const float alpha = (x0 > 0.f) ? -nrm : nrm;             // R_kk
+    const float v0 = x0 - alpha;                              // v = x - alpha e_k (no cancellation)
+    const float denom = nrm2 - alpha * x0;                    // = v^T v / 2
+    const float beta = (denom > 0.f) ? 1.f / denom : 0.f;     // H = I - beta v v^T
+#pragma unroll
+    for (int j = k + 1; j < N; ++j) {
+      float d = v0 * G[k][j];
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) d = fmaf(G[i][k], G[i][j], d);
+      d *= beta;
+      G[k][j] = fmaf(-d, v0, G[k][j]);
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) G[i][j] = fmaf(-d, G[i][k], G[i][j]);
+      cn[j] = fmaxf(cn[j] - G[k][j] * G[k][j], 0.f);
+    }
+    {
+      float d = v0 * y[k];
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) d = fmaf(G[i][k], y[i], d);
+      d *= beta;
+      y[k] = fmaf(-d, v0, y[k]);
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) y[i] = fmaf(-d, G[i][k], y[i]);
+    }
+    G[k][k] = (denom > 0.f) ? alpha : x0;
+#pragma unroll
+    for (int i = k + 1; i < N; ++i) G[i][k] = 0.f;
+  }
+}
+
+template <int N, bool kQr>
 RMP2_DEV void resolve_pinv(float (&G)[N][N], float (&y)[N], float rcond, float (&x)[N]) {
   using Sch = JacobiSchedule<N>;
+  int perm[N];
+  if (kQr) qr_column_pivoting<N>(G, y, perm);
   float nrm[N];
   for (int sweep = 0; sweep < RMP2_JACOBI_MAX_SWEEPS; ++sweep) {
     // squared row norms: exact at the start of every sweep, updated in closed form inside it
@@ -278,12 +357,24 @@ RMP2_DEV void resolve_pinv(float (&G)[N][N], float (&y)[N], float rcond, float (
     smax = fmaxf(smax, a);
   }
   const float cut2 = rcond * rcond * smax;
+  float xp[N];                                   // solution (in pivoted column order with QRCP)
 #pragma unroll
-  for (int j = 0; j < N; ++j) x[j] = 0.f;
+  for (int j = 0; j < N; ++j) xp[j] = 0.f;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const float coef = (sig2[i] > cut2) ? y[i] / sig2[i] : 0.f;
 #pragma unroll
-    for (int j = 0; j < N; ++j) x[j] = fmaf(G[i][j], coef, x[j]);
+    for (int j = 0; j < N; ++j) xp[j] = fmaf(G[i][j], coef, xp[j]);
+  }
+  if (kQr) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {                // x[perm[k]] = xp[k]
+      x[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < N; ++k) x[j] = (perm[k] == j) ? xp[k] : x[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j] = xp[j];
   }
 }

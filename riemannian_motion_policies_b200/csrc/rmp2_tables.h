@@ -46,6 +46,8 @@ struct StepTables {
   int32_t n_slots;
   int32_t uses_spheres;         // some leaf reads io.spheres
   int32_t n_sphere_slots;       // number of FRAME_DISTANCE_SPHERES leaves (record slots per environment)
+  int32_t precondition;         // no leaf adds a positive multiple of I: M may be rank deficient -> pivoted-QR
+                                // preconditioning of the Jacobi resolve pays off
   uint32_t prismatic_mask;      // bit j: joint column j is prismatic
   float rcond;                  // 10 * n * eps32 (tf.linalg.pinv default, rmp.py:153)
   FrameTab frames[RMP2_MAX_FRAMES];
