@@ -495,7 +495,10 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, kSplit ? RMP2_SPLIT_MIN_BL
     }
     return;
   }
-  resolve_pinv<N, false>(M, f, T.rcond, qdd);
+  if (T.precondition)                            // same arithmetic as the stand-alone resolve kernel
+    resolve_pinv<N, true>(M, f, T.rcond, qdd);
+  else
+    resolve_pinv<N, false>(M, f, T.rcond, qdd);
   finish_step<N>(A, n, e, active, rollout, q, qd, qdd);
 }
 
