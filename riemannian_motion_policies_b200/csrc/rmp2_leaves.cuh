@@ -168,12 +168,18 @@ RMP2_DEV void obstacle_pair(const float* __restrict__ p, float nx, float ny, flo
   const float curv = fmaf(-xdot, xdot, vv) * inv_d;
   const float c = fmaf(nx, a[0], fmaf(ny, a[1], fmaf(nz, a[2], curv)));
   const float x = fmaxf(d - p[OA_MARGIN], 0.f);                          // rmp2.py:185-186
-  const float base = p[OA_MSCALAR] * fast_rcp(fmaf(x, p[OA_INV_ESTD], p[OA_EEPS]));   // rmp2.py:187
+  // one reciprocal for the two leaf denominators (MUFU is the co-limiting pipe of the pair loop):
+  // 1/den1 = den2 / (den1 den2), 1/den2 = den1 / (den1 den2)
+  const float den1 = fmaf(x, p[OA_INV_ESTD], p[OA_EEPS]);
+  const float den2 = fmaf(x, p[OA_INV_DSTD], p[OA_DEPS]);
+  const float r12 = fast_rcp(den1 * den2);
+  const float inv1 = r12 * den2, inv2 = r12 * den1;
+  const float base = p[OA_MSCALAR] * inv1;                               // rmp2.py:187
   const float gt = fmaf(x, p[OA_INV_R], -1.f);
   const float gate = gt * gt;                                            // rmp2.py:172
   const float rep = p[OA_RGAIN] * fast_exp2(x * p[OA_K_REP]);            // rmp2.py:189
   const float one_minus_sig = fast_rcp(1.f + fast_exp2(xdot * p[OA_K_VEL]));     // 1 - sigmoid  rmp2.py:190
-  const float damp = -one_minus_sig * p[OA_DGAIN] * xdot * fast_rcp(fmaf(x, p[OA_INV_DSTD], p[OA_DEPS]));  // :191
+  const float damp = -one_minus_sig * p[OA_DGAIN] * xdot * inv2;         // rmp2.py:191
   const float acc = rep + damp;
   const float m = (x > p[OA_R]) ? 0.f : one_minus_sig * base * gate;     // rmp2.py:194
   const float h = m * (acc - c);
