@@ -67,7 +67,10 @@ enum {
   RMP2_LEAF_OBSTACLE_AVOIDANCE = 7,
   /* rmp2.py:198-226 CSpaceBiasing: params = {metric_scalar, position_gain, damping_gain,
    *                 robust_position_term_thresh, inertia}; vec = goal[n]                     */
-  RMP2_LEAF_CSPACE_BIASING = 8
+  RMP2_LEAF_CSPACE_BIASING = 8,
+  /* rmp.py:264-315  CollisionAvoidance (v1): params = {eta_rep, nu_rep, eta_damp, nu_damp, r, c};
+   *                 distance d and unit normal vec of every pair come with the pair rows             */
+  RMP2_LEAF_COLLISION_AVOIDANCE = 9
 };
 
 /* task map a leaf lives on (the closed set of chains the reference's experiments build) */
@@ -80,8 +83,12 @@ enum {
    * O spheres of rmp2_step_io.spheres: pos_on_link = frame origin, pos_on_obstacle = closest
    * point of the sphere surface to it                                                         */
   RMP2_SPACE_FRAME_DISTANCE_SPHERES = 2,
-  /* same chain, the K pairs given explicitly (the Datamanager feed, data_management.py:22-37) */
-  RMP2_SPACE_FRAME_DISTANCE_PAIRS = 3
+  /* same chain, the K pairs given explicitly (the Datamanager feed, data_management.py:22-37);
+   * pair row = (pos_on_link xyz, pos_on_obstacle xyz, 0, 0)                                    */
+  RMP2_SPACE_FRAME_DISTANCE_PAIRS = 3,
+  /* taskmap.py:79-99   chain [FK(frame), TaskmapRelative4x4(relative_pos), TaskmapFrom4x4ToPosition]:
+   * K points fixed in the frame; pair row = (relative_pos xyz, distance, normal_vec xyz, 0)     */
+  RMP2_SPACE_FRAME_POINTS = 4
 };
 
 typedef struct rmp2_robot rmp2_robot; /* constant kinematic tables of one URDF              */
@@ -109,8 +116,8 @@ typedef struct rmp2_step_io {
   int32_t n_goal_slots;
   int32_t n_spheres;      /* O, spheres per environment                                      */
   const float* spheres;   /* [B][O][4] = (cx, cy, cz, radius) or NULL                        */
-  const float* pairs;     /* [B][K_total][6] = (pos_on_link xyz, pos_on_obstacle xyz) or NULL */
-  int32_t n_pair_sets;    /* number of FRAME_DISTANCE_PAIRS leaves, in tree order             */
+  const float* pairs;     /* [B][K_total][8] pair rows (layout per space, see above) or NULL   */
+  int32_t n_pair_sets;    /* number of FRAME_DISTANCE_PAIRS / FRAME_POINTS leaves, tree order  */
   int32_t pair_counts[RMP2_MAX_PAIR_SETS]; /* K of each such leaf; K_total = their sum        */
 } rmp2_step_io;
 
@@ -169,9 +176,11 @@ int rmp2_fk(const rmp2_robot* robot, int32_t frame, int64_t B, const float* q, c
             float* x, float* xd, float* J, float* c, void* stream);
 
 /* xdd [K][m], M [K][m][m] of one leaf at task-space points x, xd [K][m].
- * Stands in for RiemannianMotionPolicy.evaluate (rmp.py:202-206, rmp2.py:25-29). */
+ * Stands in for RiemannianMotionPolicy.evaluate (rmp.py:202-206, rmp2.py:25-29).
+ * aux: only for RMP2_LEAF_COLLISION_AVOIDANCE, [K][4] = (distance, normal_vec xyz) -- the data the
+ * reference leaf holds as self.d / self.vec (rmp.py:269-270); NULL otherwise. */
 int rmp2_leaf_evaluate(const rmp2_leaf_desc* leaf, int32_t m, int64_t K, const float* x,
-                       const float* xd, float* xdd, float* M, void* stream);
+                       const float* xd, const float* aux, float* xdd, float* M, void* stream);
 
 /* ---- introspection ----------------------------------------------------------------------- */
 const char* rmp2_last_error(void);

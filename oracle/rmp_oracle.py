@@ -452,6 +452,34 @@ class TargetPolicy(RiemannianMotionPolicy):
         return w * H
 
 
+class CollisionAvoidance(RiemannianMotionPolicy):
+    """reference: rmp.py:264-315 (v1 obstacle leaf; d [K] and vec [K,3] are external data)."""
+    def __init__(self, d, vec, eta_rep, nu_rep, eta_damp, nu_damp, r, c, taskmap, name="collision_avoidance"):
+        super().__init__(name, taskmap)
+        self.d, self.vec = d, vec
+        self.eta_rep, self.nu_rep, self.eta_damp, self.nu_damp, self.r, self.c = eta_rep, nu_rep, eta_damp, nu_damp, r, c
+
+    def _motion_command(self, x, xd):
+        d, vec = torch.as_tensor(self.d).to(x.dtype), torch.as_tensor(self.vec).to(x.dtype)
+        alpha_rep = self.eta_rep * torch.exp(-d / self.nu_rep)
+        f_rep = alpha_rep[:, None] * vec
+        epsilon = 1e-6
+        alpha_damp = self.eta_damp / (d / self.nu_damp + epsilon)
+        scaling = torch.clamp((-xd * vec).sum(-1), min=0.)
+        P_obs = scaling[:, None, None] * vec[:, :, None] * vec[:, None, :]
+        f_damp = alpha_damp[:, None] * (P_obs @ xd[..., None])[..., 0]
+        return f_rep - f_damp
+
+    def _metric(self, x, xd):
+        d = torch.as_tensor(self.d).to(x.dtype)
+        c_0, c_1, c_2, c_3 = 1, 0, -3 / self.r ** 2, 2 / self.r ** 3
+        spline = c_3 * d ** 3 + c_2 * d ** 2 + c_1 * d + c_0
+        w = torch.where(d > self.r, torch.zeros_like(spline), spline)
+        f_obs = self._motion_command(x, xd)
+        H = directionally_stretched_metric(v=f_obs, c=self.c, beta=0)
+        return w[:, None, None] * H
+
+
 class ConfigurationSpaceBiasing(RiemannianMotionPolicy):
     """reference: rmp.py:318-347."""
     def __init__(self, gamma_p, gamma_d, q0, name, w=0.05):

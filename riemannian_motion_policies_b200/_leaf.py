@@ -49,6 +49,10 @@ class RiemannianMotionPolicy:
             d.vec[i] = v
         return d
 
+    def _aux(self, K, dev):
+        """Extra per-row data a leaf holds itself (only the v1 CollisionAvoidance: distance, normal)."""
+        return None
+
     # -- stand-alone evaluation, same signature as the reference --------------------------------
     def evaluate(self, x, xd, *args, **kwargs):
         """x, xd [K,m] -> xdd [K,m], M [K,m,m] through the CUDA leaf kernel
@@ -61,6 +65,8 @@ class RiemannianMotionPolicy:
         desc = self.leaf_desc(m)
         xdd = torch.empty(K, m, device=dev)
         M = torch.empty(K, m, m, device=dev)
-        _native.check(_native.lib().rmp2_leaf_evaluate(desc, m, K, xt.data_ptr(), xdt.data_ptr(), xdd.data_ptr(),
+        aux = self._aux(K, dev)
+        _native.check(_native.lib().rmp2_leaf_evaluate(desc, m, K, xt.data_ptr(), xdt.data_ptr(),
+                                                       None if aux is None else aux.data_ptr(), xdd.data_ptr(),
                                                        M.data_ptr(), current_stream_ptr(dev)))
         return like_input(xdd, x), like_input(M, x)

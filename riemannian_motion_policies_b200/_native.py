@@ -27,11 +27,14 @@ LEAF_VELOCITY_CAP = 5
 LEAF_JOINT_DAMPING = 6
 LEAF_OBSTACLE_AVOIDANCE = 7
 LEAF_CSPACE_BIASING = 8
+LEAF_COLLISION_AVOIDANCE = 9
 
 SPACE_CONFIG = 0
 SPACE_FRAME_POSITION = 1
 SPACE_FRAME_DISTANCE_SPHERES = 2
 SPACE_FRAME_DISTANCE_PAIRS = 3
+SPACE_FRAME_POINTS = 4
+PAIR_FLOATS = 8
 
 OPT_EARLY_OUT = 0
 
@@ -107,7 +110,7 @@ def lib():
     L.rmp2_rollout.restype = ctypes.c_int
     L.rmp2_fk.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp]
     L.rmp2_fk.restype = ctypes.c_int
-    L.rmp2_leaf_evaluate.argtypes = [ctypes.POINTER(LeafDesc), i32, i64, vp, vp, vp, vp, vp]
+    L.rmp2_leaf_evaluate.argtypes = [ctypes.POINTER(LeafDesc), i32, i64, vp, vp, vp, vp, vp, vp]
     L.rmp2_leaf_evaluate.restype = ctypes.c_int
     L.rmp2_last_error.argtypes = []
     L.rmp2_last_error.restype = ctypes.c_char_p

@@ -156,6 +156,17 @@ static int derive_leaf_params(const rmp2_leaf_desc& d, int n, LeafTab& L, float*
       L.p[OA_K_REP] = (float)(-1.4426950408889634 / (double)r[6]);
       L.p[OA_K_VEL] = (float)(1.4426950408889634 / (double)r[4]);
       break;
+    case RMP2_LEAF_COLLISION_AVOIDANCE: {
+      const double rr = (double)r[4];
+      L.p[CA_ETA_REP] = r[0];
+      L.p[CA_INV_NU_REP] = (float)(1.0 / (double)r[1]);
+      L.p[CA_ETA_DAMP] = r[2];
+      L.p[CA_INV_NU_DAMP] = (float)(1.0 / (double)r[3]);
+      L.p[CA_R] = r[4];
+      L.p[CA_C3] = (float)(2.0 / (rr * rr * rr));               // rmp.py:303-304
+      L.p[CA_C2] = (float)(-3.0 / (rr * rr));
+      break;
+    }
     case RMP2_LEAF_CSPACE_BIASING:
       L.p[CS_METRIC] = (float)((double)r[0] + (double)r[4]);   // rmp2.py:224
       L.p[CS_PGAIN] = r[1];
@@ -189,6 +200,10 @@ static int check_leaf(const rmp2_leaf_desc& d, int F, int idx) {
     case RMP2_SPACE_FRAME_DISTANCE_PAIRS:
       if (d.type != RMP2_LEAF_OBSTACLE_AVOIDANCE)
         return fail(RMP2_ERR_UNSUPPORTED, at + "only ObstacleAvoidance lives on a distance task map");
+      break;
+    case RMP2_SPACE_FRAME_POINTS:
+      if (d.type != RMP2_LEAF_COLLISION_AVOIDANCE)
+        return fail(RMP2_ERR_UNSUPPORTED, at + "only CollisionAvoidance lives on frame-fixed points");
       break;
     default:
       return fail(RMP2_ERR_INVALID, at + "unknown space " + std::to_string(d.space));
@@ -300,7 +315,8 @@ int rmp2_tree_create(const rmp2_robot* rb, const rmp2_leaf_desc* leaves, int32_t
   int leaf_cursor = 0, pair_sets = 0, goal_slots = 0, vec_cursor = 0;
   std::vector<int> pair_set_of(n_leaves, -1);
   for (int i = 0; i < n_leaves; ++i) {
-    if (leaves[i].space == RMP2_SPACE_FRAME_DISTANCE_PAIRS) pair_set_of[i] = pair_sets++;
+    if (leaves[i].space == RMP2_SPACE_FRAME_DISTANCE_PAIRS || leaves[i].space == RMP2_SPACE_FRAME_POINTS)
+      pair_set_of[i] = pair_sets++;
     if (leaves[i].goal_slot >= 0) goal_slots = std::max(goal_slots, leaves[i].goal_slot + 1);
     if (leaves[i].space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) T.uses_spheres = 1;
   }
@@ -630,7 +646,7 @@ int launch(rmp2_tree* tree, const StepArgs& A0, cudaStream_t stream) {
     if (A0.qd_rw) A.qd_rw = A0.qd_rw + e0 * n;
     if (A0.goals) A.goals = A0.goals + e0 * A0.n_goal_slots * 3;
     if (A0.spheres) A.spheres = A0.spheres + e0 * (long long)A0.n_spheres * 4;
-    if (A0.pairs) A.pairs = A0.pairs + e0 * (long long)A0.pair_total * 6;
+    if (A0.pairs) A.pairs = A0.pairs + e0 * (long long)A0.pair_total * RMP2_PAIR_FLOATS;
     A.rec = tree->rec;
     A.mf = split ? tree->mf : nullptr;
     int rc = launch_chunk(tree, A, stream);
@@ -692,7 +708,7 @@ int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io) {
   const size_t off_goal = off_qdd + pad4((size_t)chunk * n);
   const size_t off_sph = off_goal + pad4((size_t)chunk * G * 3);
   const size_t off_pair = off_sph + pad4((size_t)chunk * O * 4);
-  const size_t off_rec = off_pair + pad4((size_t)chunk * K * 6);
+  const size_t off_rec = off_pair + pad4((size_t)chunk * K * RMP2_PAIR_FLOATS);
   const size_t off_mf = off_rec + pad4(rec_floats_for(tree, chunk, O));
   const bool split = split_resolve(chunk);
   const size_t total = off_mf + (split ? pad4(mf_floats_for(tree, chunk)) : 0);
@@ -724,7 +740,7 @@ int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io) {
     RMP2_H2D(off_qd, io->qd + e0 * n, cb * n);
     RMP2_H2D(off_goal, io->goals ? io->goals + e0 * G * 3 : nullptr, cb * G * 3);
     RMP2_H2D(off_sph, io->spheres ? io->spheres + e0 * O * 4 : nullptr, cb * O * 4);
-    RMP2_H2D(off_pair, io->pairs ? io->pairs + e0 * K * 6 : nullptr, cb * K * 6);
+    RMP2_H2D(off_pair, io->pairs ? io->pairs + e0 * K * RMP2_PAIR_FLOATS : nullptr, cb * K * RMP2_PAIR_FLOATS);
 #undef RMP2_H2D
     StepArgs A = A0;
     A.B = cb;
@@ -772,9 +788,11 @@ int rmp2_fk(const rmp2_robot* rb, int32_t frame, int64_t B, const float* q, cons
   return RMP2_OK;
 }
 
-int rmp2_leaf_evaluate(const rmp2_leaf_desc* leaf, int32_t m, int64_t K, const float* x, const float* xd, float* xdd,
-                       float* M, void* stream) {
+int rmp2_leaf_evaluate(const rmp2_leaf_desc* leaf, int32_t m, int64_t K, const float* x, const float* xd,
+                       const float* aux, float* xdd, float* M, void* stream) {
   if (!leaf || !x || !xd || !xdd || !M) return fail(RMP2_ERR_INVALID, "null argument");
+  if (leaf->type == RMP2_LEAF_COLLISION_AVOIDANCE && (m != 3 || !aux))
+    return fail(RMP2_ERR_INVALID, "CollisionAvoidance is three-dimensional and needs aux = (distance, normal)");
   if (m <= 0 || m > RMP2_MAX_JOINTS) return fail(RMP2_ERR_INVALID, "task dimension out of range");
   if (K <= 0) return K == 0 ? RMP2_OK : fail(RMP2_ERR_INVALID, "K must be >= 0");
   if (leaf->type == RMP2_LEAF_OBSTACLE_AVOIDANCE && m != 1) return fail(RMP2_ERR_INVALID, "ObstacleAvoidance is one-dimensional");
@@ -790,7 +808,7 @@ int rmp2_leaf_evaluate(const rmp2_leaf_desc* leaf, int32_t m, int64_t K, const f
   int vlen = 0;
   int rc = derive_leaf_params(d, m, L, V.v, &vlen);
   if (rc != RMP2_OK) return rc;
-  cudaError_t e = rmp2_launch_leaf(L, V, m, K, x, xd, xdd, M, (cudaStream_t)stream);
+  cudaError_t e = rmp2_launch_leaf(L, V, m, K, x, xd, aux, xdd, M, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "rmp2_leaf_evaluate launch");
   g_launches.fetch_add(1);
   return RMP2_OK;

@@ -394,19 +394,45 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, kSplit ? RMP2_SPLIT_MIN_BL
 #pragma unroll
           for (int i = 0; i < 3; ++i) g[i] += __ldg(r + (6 + i) * fstride);
           contrib = true;
-        } else {  // RMP2_SPACE_FRAME_DISTANCE_PAIRS: explicit (pos_on_link, pos_on_obstacle) pairs
+        } else if (L.space == RMP2_SPACE_FRAME_DISTANCE_PAIRS) {  // explicit (pos_on_link, pos_on_obstacle)
           const int k0 = A.pair_off[L.pair_set], k1 = A.pair_off[L.pair_set + 1];
-          const float* pp = A.pairs + ((size_t)e * A.pair_total + k0) * 6;
+          const float* pp = A.pairs + ((size_t)e * A.pair_total + k0) * RMP2_PAIR_FLOATS;
           const float vv = fmaf(ch.v[0], ch.v[0], fmaf(ch.v[1], ch.v[1], ch.v[2] * ch.v[2]));
           for (int k = 0; k < k1 - k0; ++k) {
-            const float rx = __ldg(pp + 6 * k + 0) - __ldg(pp + 6 * k + 3);
-            const float ry = __ldg(pp + 6 * k + 1) - __ldg(pp + 6 * k + 4);
-            const float rz = __ldg(pp + 6 * k + 2) - __ldg(pp + 6 * k + 5);
+            const float* row = pp + RMP2_PAIR_FLOATS * k;
+            const float rx = __ldg(row + 0) - __ldg(row + 3);
+            const float ry = __ldg(row + 1) - __ldg(row + 4);
+            const float rz = __ldg(row + 2) - __ldg(row + 5);
             const float d2 = fmaxf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)), 1e-24f);
             const float inv_d = fast_rsqrt(d2);
             obstacle_pair(L.p, rx * inv_d, ry * inv_d, rz * inv_d, d2 * inv_d, inv_d, ch.v, ch.a, vv, S, g);
           }
           contrib = true;
+        } else {  // RMP2_SPACE_FRAME_POINTS: points fixed in the frame (v1 CollisionAvoidance)
+          // x = p + R rel;  xd = v + w x rho;  c = a + alpha x rho + w x (w x rho)   (rho = R rel);
+          // the point's Jacobian is the frame-origin Jacobian evaluated at x, so every pair is
+          // pulled back on its own (reference: taskmap.py:83-99 via autodiff).
+          const int k0 = A.pair_off[L.pair_set], k1 = A.pair_off[L.pair_set + 1];
+          const float* pp = A.pairs + ((size_t)e * A.pair_total + k0) * RMP2_PAIR_FLOATS;
+          for (int k = 0; k < k1 - k0; ++k) {
+            const float* row = pp + RMP2_PAIR_FLOATS * k;
+            const float rel[3] = {__ldg(row + 0), __ldg(row + 1), __ldg(row + 2)};
+            const float dist = __ldg(row + 3);
+            const float vec[3] = {__ldg(row + 4), __ldg(row + 5), __ldg(row + 6)};
+            float rho[3], wr[3], wwr[3], ar[3];
+            matvec3(ch.R, rel, rho);
+            cross3(ch.w, rho, wr);
+            cross3(ch.w, wr, wwr);
+            cross3(ch.al, rho, ar);
+            const float xp[3] = {ch.p[0] + rho[0], ch.p[1] + rho[1], ch.p[2] + rho[2]};
+            const float xd[3] = {ch.v[0] + wr[0], ch.v[1] + wr[1], ch.v[2] + wr[2]};
+            const float cp[3] = {ch.a[0] + ar[0] + wwr[0], ch.a[1] + ar[1] + wwr[1], ch.a[2] + ar[2] + wwr[2]};
+            float fl[3], w;
+            collision_avoidance_v1(L.p, dist, vec, xd, fl, w);
+            const float Sp[6] = {w, 0.f, 0.f, w, 0.f, w};
+            const float gp[3] = {w * (fl[0] - cp[0]), w * (fl[1] - cp[1]), w * (fl[2] - cp[2])};
+            pullback<N>(zj, pj, xp, F.anc_mask, T.prismatic_mask, Sp, gp, Msym, f);
+          }
         }
       }
       if (contrib) pullback<N>(zj, pj, ch.p, F.anc_mask, T.prismatic_mask, S, g, Msym, f);
@@ -648,8 +674,8 @@ __global__ void __launch_bounds__(128)
 // One thread per task-space point.  D = RMP2_MAX_JOINTS covers every task dimension in use.
 __global__ void __launch_bounds__(128)
     rmp2_leaf_kernel(const __grid_constant__ LeafTab L, const __grid_constant__ LeafVec V, int m, long long K,
-                     const float* __restrict__ xin, const float* __restrict__ xdin, float* __restrict__ xdd_out,
-                     float* __restrict__ M_out) {
+                     const float* __restrict__ xin, const float* __restrict__ xdin, const float* __restrict__ aux,
+                     float* __restrict__ xdd_out, float* __restrict__ M_out) {
   constexpr int D = RMP2_MAX_JOINTS;
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
@@ -667,6 +693,15 @@ __global__ void __launch_bounds__(128)
     obstacle_scalar(L.p, x[0], xd[0], a, mm);
     xdd[0] = a;
     Mo[0] = mm;
+  } else if (L.type == RMP2_LEAF_COLLISION_AVOIDANCE) {
+    const float vec[3] = {aux[4 * k + 1], aux[4 * k + 2], aux[4 * k + 3]};
+    const float xd3[3] = {xd[0], xd[1], xd[2]};
+    float f3[3], w;
+    collision_avoidance_v1(L.p, aux[4 * k], vec, xd3, f3, w);
+    for (int i = 0; i < 3; ++i) {
+      xdd[i] = f3[i];
+      Mo[4 * i] = w;
+    }
   } else if (L.type == RMP2_LEAF_TARGET_POLICY || L.type == RMP2_LEAF_TARGET_ATTRACTOR) {
     float zeta[D], iso, dir;
 #pragma unroll
@@ -837,9 +872,9 @@ cudaError_t rmp2_launch_fk(const StepTables& T, long long B, const float* q, con
 }
 
 cudaError_t rmp2_launch_leaf(const LeafTab& L, const LeafVec& V, int m, long long K, const float* x, const float* xd,
-                             float* xdd, float* M, cudaStream_t stream) {
+                             const float* aux, float* xdd, float* M, cudaStream_t stream) {
   const long long blocks = (K + 127) / 128;
   if (blocks <= 0) return cudaSuccess;
-  rmp2_leaf_kernel<<<(unsigned)blocks, 128, 0, stream>>>(L, V, m, K, x, xd, xdd, M);
+  rmp2_leaf_kernel<<<(unsigned)blocks, 128, 0, stream>>>(L, V, m, K, x, xd, aux, xdd, M);
   return cudaGetLastError();
 }

@@ -25,4 +25,4 @@ cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, si
 cudaError_t rmp2_launch_fk(const StepTables& T, long long B, const float* q, const float* qd, float* x, float* xd,
                            float* J, float* c, cudaStream_t stream);
 cudaError_t rmp2_launch_leaf(const LeafTab& L, const LeafVec& V, int m, long long K, const float* x, const float* xd,
-                             float* xdd, float* M, cudaStream_t stream);
+                             const float* aux, float* xdd, float* M, cudaStream_t stream);

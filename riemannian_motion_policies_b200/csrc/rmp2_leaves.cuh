@@ -68,6 +68,15 @@
 #define CS_DGAIN 2
 #define CS_THRESH 3
 
+// COLLISION_AVOIDANCE (v1)
+#define CA_ETA_REP 0
+#define CA_INV_NU_REP 1
+#define CA_ETA_DAMP 2
+#define CA_INV_NU_DAMP 3
+#define CA_R 4
+#define CA_C3 5
+#define CA_C2 6
+
 // ---- single-instruction special functions (MUFU), used in the per-pair hot loop -----------------
 // Relative error ~1e-7 each (2 ulp); the distance leaf tolerates that: see DESIGN.md "numerics".
 RMP2_DEV float fast_rcp(float x) {                                               // MUFU.RCP, x normal
@@ -205,6 +214,22 @@ RMP2_DEV void obstacle_scalar(const float* __restrict__ p, float xin, float xdot
   const float damp = -one_minus_sig * p[OA_DGAIN] * xdot / fmaf(x, p[OA_INV_DSTD], p[OA_DEPS]);
   xdd = rep + damp;
   M = (x > p[OA_R]) ? 0.f : one_minus_sig * base * (gt * gt);
+}
+
+// CollisionAvoidance, v1 (reference: rmp.py:283-315).  d, vec = distance and unit normal of the pair
+// (external data), xd = velocity of the point.  The metric's directional stretching is multiplied by
+// beta = 0 (rmp.py:312), so A = w * I exactly.
+RMP2_DEV void collision_avoidance_v1(const float* __restrict__ p, float d, const float (&vec)[3],
+                                     const float (&xd)[3], float (&f)[3], float& w) {
+  const float alpha_rep = p[CA_ETA_REP] * expf(-d * p[CA_INV_NU_REP]);            // rmp.py:285
+  const float alpha_damp = p[CA_ETA_DAMP] / (d * p[CA_INV_NU_DAMP] + 1e-6f);      // rmp.py:289-290
+  const float vx = fmaf(vec[0], xd[0], fmaf(vec[1], xd[1], vec[2] * xd[2]));      // vec . xd
+  const float scaling = fmaxf(0.f, -vx);                                          // rmp.py:291
+  const float damp = alpha_damp * scaling * vx;                                   // P_obs xd = scaling vec (vec.xd)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) f[i] = (alpha_rep - damp) * vec[i];                 // rmp.py:286,293-295
+  const float spline = fmaf(p[CA_C3] * d, d * d, fmaf(p[CA_C2] * d, d, 1.f));     // rmp.py:301-305
+  w = (d > p[CA_R]) ? 0.f : spline;                                               // rmp.py:306
 }
 
 // ---- configuration-space leaves: add A into the full matrix M and A*xdd into f ---------------------

@@ -9,6 +9,7 @@
 #define RMP2_VECPOOL 160          // floats: goals / q0 / limits of all leaves
 #define RMP2_SLOT_BASE (-2)       // restore_slot value meaning "start from the base link"
 #define RMP2_CHAIN_FLOATS 24      // R(9) p(3) w(3) v(3) alpha(3) a(3)
+#define RMP2_PAIR_FLOATS 8        // floats per explicit pair row (rmp2_step_io.pairs)
 #define RMP2_REC_FLOATS 10        // fields of one frame record (p, v, a, |v|^2); (S, g) reuse 9 of them
 
 struct FrameTab {

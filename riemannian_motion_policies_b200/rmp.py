@@ -15,7 +15,7 @@ from . import _native
 from ._leaf import RiemannianMotionPolicy, as_float_list
 from ._tensor import current_stream_ptr, is_device_tensor, require_cuda, to_device, unwrap
 from .taskmap import (IdentityTaskmap, TaskmapByForwardKinematic, TaskmapByFunction, TaskmapFrom4x4ToPosition,
-                      TaskmapJointFrame4x4ToDistance, TaskmapJointFrame4x4ToSphereDistance)
+                      TaskmapJointFrame4x4ToDistance, TaskmapJointFrame4x4ToSphereDistance, TaskmapRelative4x4)
 
 
 # =================================================================================================
@@ -42,15 +42,32 @@ class TargetPolicy(RiemannianMotionPolicy):
 
 
 class CollisionAvoidance(RiemannianMotionPolicy):
-    """reference: rmp.py:264-315.  The v1 obstacle path (with TaskmapRelative4x4) is listed as
-    'next' in SURVEY.md section 8f; the class holds its parameters but cannot be compiled yet."""
-    leaf_type = None
+    """v1 obstacle avoidance (reference: rmp.py:264-315).  ``d`` [K] and ``vec`` [K,3] are the distance and
+    normal of every closest-point pair, typically Datamanager variables that are updated in place."""
+    leaf_type = _native.LEAF_COLLISION_AVOIDANCE
 
     def __init__(self, d, vec, eta_rep, nu_rep, eta_damp, nu_damp, r, c, taskmap, name='collision_avoidance'):
         super().__init__(name, taskmap)
         self.d, self.vec = d, vec
         self.eta_rep, self.nu_rep, self.eta_damp, self.nu_damp = eta_rep, nu_rep, eta_damp, nu_damp
         self.r, self.c = r, c
+
+    def _params(self):
+        return [self.eta_rep, self.nu_rep, self.eta_damp, self.nu_damp, self.r, self.c]
+
+    def current_data(self):
+        """[K,4] = (distance, normal xyz) read from the holders right now."""
+        d = torch.as_tensor(unwrap(self.d), dtype=torch.float32).reshape(-1, 1).cpu()
+        vec = torch.as_tensor(unwrap(self.vec), dtype=torch.float32).reshape(-1, 3).cpu()
+        if d.shape[0] != vec.shape[0]:
+            raise ValueError("CollisionAvoidance: d and vec need the same number of rows")
+        return torch.cat([d, vec], dim=1)
+
+    def _aux(self, K, dev):
+        aux = self.current_data()
+        if aux.shape[0] != K:
+            raise ValueError(f"CollisionAvoidance holds {aux.shape[0]} pairs but x has {K} rows")
+        return aux.to(dev).contiguous()
 
 
 class ConfigurationSpaceBiasing(RiemannianMotionPolicy):
@@ -106,10 +123,13 @@ def classify_taskmap(taskmap):
             return _native.SPACE_FRAME_DISTANCE_SPHERES, fk.fkine, fk.frame, second
         if isinstance(second, TaskmapJointFrame4x4ToDistance):
             return _native.SPACE_FRAME_DISTANCE_PAIRS, fk.fkine, fk.frame, second
+    if (stages is not None and len(stages) == 3 and isinstance(stages[0], TaskmapByForwardKinematic)
+            and isinstance(stages[1], TaskmapRelative4x4) and isinstance(stages[2], TaskmapFrom4x4ToPosition)):
+        return _native.SPACE_FRAME_POINTS, stages[0].fkine, stages[0].frame, stages[1]
     raise NotImplementedError(
         f"task map {type(taskmap).__name__} (stages={[type(s).__name__ for s in stages] if stages else None}) is not "
         "one of the chains the CUDA engine implements: IdentityTaskmap, [FK, 4x4ToPosition], [FK, JointFrame4x4ToDistance], "
-        "[FK, JointFrame4x4ToSphereDistance]")
+        "[FK, JointFrame4x4ToSphereDistance], [FK, Relative4x4, 4x4ToPosition]")
 
 
 class CompiledTree:
@@ -136,7 +156,11 @@ class CompiledTree:
             raise ValueError(f"q has {n} entries but the kinematics was built for {self.fkine.n_joints} joints")
         for e in self.entries:
             e[2] = self.fkine.frame_index(e[2]) if e[2] is not None else -1
-        self.pair_taskmaps = [e[4] for e in self.entries if e[1] == _native.SPACE_FRAME_DISTANCE_PAIRS]
+        # leaves fed with explicit pair rows [K,8], in tree order
+        self.pair_taskmaps = [e[4] for e in self.entries
+                              if e[1] in (_native.SPACE_FRAME_DISTANCE_PAIRS, _native.SPACE_FRAME_POINTS)]
+        self.pair_sources = [self._pair_source(e) for e in self.entries
+                             if e[1] in (_native.SPACE_FRAME_DISTANCE_PAIRS, _native.SPACE_FRAME_POINTS)]
         self.uses_spheres = any(e[1] == _native.SPACE_FRAME_DISTANCE_SPHERES for e in self.entries)
         self._own_robot = None
         if self.fkine is not None:
@@ -152,6 +176,20 @@ class CompiledTree:
         arr = (_native.LeafDesc * max(1, len(self.descs)))(*self.descs)
         self.handle = ctypes.c_void_p()
         _native.check(_native.lib().rmp2_tree_create(robot, arr, len(self.descs), ctypes.byref(self.handle)))
+
+    @staticmethod
+    def _pair_source(entry):
+        """-> callable returning the leaf's current pair rows [K,8] (layout: include/rmp2_b200.h)."""
+        leaf, space, _, _, taskmap = entry
+        if space == _native.SPACE_FRAME_DISTANCE_PAIRS:
+            return taskmap.current_pairs
+
+        def rows():
+            rel, data = taskmap.current_points(), leaf.current_data()
+            if rel.shape[0] != data.shape[0]:
+                raise ValueError(f"{leaf.name}: relative_pos has {rel.shape[0]} rows, d/vec have {data.shape[0]}")
+            return torch.cat([rel, data, torch.zeros(rel.shape[0], 1)], dim=1)
+        return rows
 
     def _make_descs(self):
         return [leaf.leaf_desc(self.n if space == _native.SPACE_CONFIG else 3, space, frame, goal_slot)
@@ -199,7 +237,7 @@ class CompiledTree:
         if self.goal_leaves:
             if goals is None or goals.dim() != 3 or goals.shape[0] != B or goals.shape[1] < len(self.goal_leaves) or goals.shape[2] != 3:
                 raise ValueError(f"goals must be [B, {len(self.goal_leaves)}, 3]")
-        for name, t, last in (("goals", goals, 3), ("spheres", spheres, 4), ("pairs", pairs, 6)):
+        for name, t, last in (("goals", goals, 3), ("spheres", spheres, 4), ("pairs", pairs, _native.PAIR_FLOATS)):
             if t is not None and (t.dim() != 3 or t.shape[0] != B or t.shape[2] != last or t.dtype != torch.float32
                                   or not t.is_contiguous() or t.is_cuda != cuda):
                 raise ValueError(f"{name} must be a contiguous float32 {'CUDA' if cuda else 'host'} tensor [B, K, {last}]")
@@ -344,7 +382,7 @@ class RmpCore:
                 sph = sph[None]
         pairs, counts = None, []
         if tree.pair_taskmaps:
-            per_leaf = [tm.current_pairs() for tm in tree.pair_taskmaps]
+            per_leaf = [rows() for rows in tree.pair_sources]
             counts = [int(p.shape[0]) for p in per_leaf]
             if B != 1:
                 raise NotImplementedError("explicit closest-point pairs (Datamanager feed) describe one environment; "

@@ -128,14 +128,14 @@ class TaskmapJointFrame4x4ToDistance(_DistanceBase):
         return link, obst
 
     def current_pairs(self):
-        """[K,6] = (pos_on_link, pos_on_obstacle), on whatever side the holders live."""
+        """[K,8] pair rows (pos_on_link, pos_on_obstacle, 0, 0) read from the holders right now."""
         link = unwrap(self.pos_on_link_in_base_frame)
         obst = unwrap(self.pos_on_obstacle_in_base_frame)
-        link = torch.as_tensor(link, dtype=torch.float32).reshape(-1, 3)
-        obst = torch.as_tensor(obst, dtype=torch.float32).reshape(-1, 3)
+        link = torch.as_tensor(link, dtype=torch.float32).reshape(-1, 3).cpu()
+        obst = torch.as_tensor(obst, dtype=torch.float32).reshape(-1, 3).cpu()
         if link.shape != obst.shape:
             raise ValueError("pos_on_link_in_base_frame and pos_on_obstacle_in_base_frame need the same shape")
-        return torch.cat([link, obst.to(link.device)], dim=1)
+        return torch.cat([link, obst, torch.zeros(link.shape[0], 2)], dim=1)
 
 
 class TaskmapJointFrame4x4ToSphereDistance(Taskmap):
@@ -163,16 +163,42 @@ class TaskmapFrom4x4ToEuler(Taskmap):
 
 
 class TaskmapRelative4x4(Taskmap):
-    """reference: taskmap.py:79-99 -- used only by the v1 CollisionAvoidance path
-    (SURVEY.md section 8f, rank 3)."""
+    """T = T_reference @ Translation(relative_pos_k) for K points fixed in the reference frame
+    (reference: taskmap.py:79-99); used by the v1 CollisionAvoidance path
+    (experiments/two_joint_robot/05_obstacle_avoidance.py:51-61).  Inside a compiled tree the chain
+    [FK, Relative4x4, 4x4ToPosition] is evaluated analytically by the step kernel."""
 
     def __init__(self, relative_pos):
-        self.relative_pos = relative_pos
+        self.relative_pos = relative_pos              # [K,3] tensor / array / Variable
+
+    def _rel(self, dev):
+        return to_device(self.relative_pos, dev).reshape(-1, 3)
 
     def forward(self, input):
-        raise NotImplementedError("TaskmapRelative4x4 is outside the accelerated hot path")
+        dev = require_cuda()
+        rel = self._rel(dev)
+        T = to_device(input, dev).reshape(-1, 4, 4).expand(rel.shape[0], 4, 4).clone()
+        T[:, :3, 3] = T[:, :3, 3] + (T[:, :3, :3] @ rel[:, :, None])[:, :, 0]
+        return like_input(T.reshape(-1, 16), input)
 
-    differentiate = forward
+    def differentiate(self, q, qd):
+        """x [K,16], xd, J [K,16,16], c = 0 (the map is linear in the 16 entries of T_reference)."""
+        dev = require_cuda()
+        rel = self._rel(dev)
+        K = rel.shape[0]
+        J = torch.zeros(K, 16, 16, device=dev)
+        idx = torch.arange(16, device=dev)
+        J[:, idx, idx] = 1.0
+        for r in range(3):                          # T[r,3] += sum_c T[r,c] rel[c]
+            for c in range(3):
+                J[:, 4 * r + 3, 4 * r + c] = rel[:, c]
+        x = (J @ to_device(q, dev).reshape(1, 16, 1).expand(K, 16, 1))[:, :, 0]
+        xd = (J @ to_device(qd, dev).reshape(1, 16, 1).expand(K, 16, 1))[:, :, 0]
+        out = (x, xd, J, torch.zeros(K, 16, device=dev))
+        return tuple(like_input(t, q) for t in out)
+
+    def current_points(self):
+        return torch.as_tensor(unwrap(self.relative_pos), dtype=torch.float32).reshape(-1, 3).cpu()
 
 
 def _chain_taskmaps(taskmap_1, taskmap_2):

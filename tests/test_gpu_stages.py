@@ -65,6 +65,23 @@ def _leaf_pairs(ns, ons):
     return list(zip(mk(ns), mk(ons)))
 
 
+def test_v1_collision_avoidance_leaf(ns):
+    """CollisionAvoidance.evaluate(x, xd) with its own d / vec data (rmp.py:264-315)."""
+    rng = np.random.RandomState(5)
+    K = 50
+    d = rng.uniform(0.02, 1.5, size=K).astype(np.float32)
+    vec = rng.normal(size=(K, 3))
+    vec = (vec / np.linalg.norm(vec, axis=1, keepdims=True)).astype(np.float32)
+    x = rng.uniform(-1, 1, size=(K, 3)).astype(np.float32)
+    xd = rng.uniform(-0.5, 0.5, size=(K, 3)).astype(np.float32)
+    args = dict(eta_rep=0.1 * np.e, nu_rep=0.3, eta_damp=1, nu_damp=0.3, r=1.1, c=1e5)
+    f, A = ns.CollisionAvoidance(d, vec, taskmap=ns.IdentityTaskmap(), **args).evaluate(x, xd)
+    fo, Ao = O.CollisionAvoidance(torch.as_tensor(d).double(), torch.as_tensor(vec).double(), taskmap=None, **args).evaluate(
+        torch.as_tensor(x).double(), torch.as_tensor(xd).double())
+    np.testing.assert_allclose(f.numpy(), fo.numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(A.numpy(), Ao.numpy(), rtol=2e-5, atol=2e-6)
+
+
 def test_every_leaf_policy(ns):
     """leaf.evaluate(x, xd) -> (xdd, M) for every leaf class against the oracle in float64
     (single row at a time where the reference's norm is a whole-tensor norm, rmp.py:243)."""

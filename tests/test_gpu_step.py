@@ -111,6 +111,61 @@ def test_datamanager_pairs_feed_matches_oracle(ns):
         assert e32 <= REL_TOL or e64 <= max(REL_TOL, 2 * yard), (b, e32, e64, yard)
 
 
+def test_v1_collision_avoidance_two_joint(ns):
+    """The v1 obstacle path of experiments/two_joint_robot/05_obstacle_avoidance.py:44-61:
+    chain [FK(frame), TaskmapRelative4x4(relative_position), TaskmapFrom4x4ToPosition] + CollisionAvoidance
+    on every frame, fed through Datamanager (distance, normal_vec, relative_position), plus TargetPolicy."""
+    from oracle import rmp_oracle as O
+    fk = product_fkine(ns, 2)
+    rng = np.random.RandomState(21)
+    q_all, qd_all, goal_all = S.sample_two_joint(12, seed=22)
+    got, ref32, ref64 = [], [], []
+    for b in range(12):
+        q, qd, goal = q_all[b], qd_all[b], goal_all[b]
+        distance_data = []
+        for frame in fk.frame_names:
+            for _ in range(rng.randint(0, 4)):                      # ragged, possibly empty
+                T = fk.forward(q[None], frame)[0].numpy()
+                on_link = T[:3, 3] + T[:3, :3] @ rng.uniform(-0.3, 0.3, size=3)
+                direction = rng.normal(size=3)
+                direction /= np.linalg.norm(direction)
+                dist = rng.uniform(0.05, 1.3)                      # some beyond r = 1.1
+                distance_data.append((frame, on_link.astype(np.float32), (on_link - dist * direction).astype(np.float32),
+                                      direction.astype(np.float32), np.float32(dist), 'synthetic'))
+
+        def build(m, fkine, dm):
+            core = m.RmpCore()
+            core.add_rmp(m.TargetPolicy(alpha=0.1, beta=0.1, c=0.1, goal=goal, name='target',
+                                        taskmap=S.ee_position_taskmap(m, fkine, 'link_23')))
+            for frame in fkine.frame_names:
+                tm = m.chain_taskmaps([m.TaskmapByForwardKinematic(fkine, frame),
+                                       m.TaskmapRelative4x4(relative_pos=dm[frame]['relative_position']),
+                                       m.TaskmapFrom4x4ToPosition()])
+                core.add_rmp(m.CollisionAvoidance(d=dm[frame]['distance'], vec=dm[frame]['normal_vec'],
+                                                  eta_rep=0.1 * np.e, nu_rep=0.3, eta_damp=1, nu_damp=0.3, r=1.1, c=1e5,
+                                                  taskmap=tm, name=f'collision_avoidance_for_{frame}'))
+            return core
+
+        dm = ns.Datamanager(fk)
+        core = build(ns, fk, dm)
+        dm.update(q, distance_data)
+        got.append(core.evaluate(q, qd).numpy())
+        # oracle side: same tuples; relative_position computed the reference's way (data_management.py:44-52)
+        for dtype, sink in ((torch.float32, ref32), (torch.float64, ref64)):
+            ons = H.namespace(dtype)
+            fko = H.make_fkine(2, dtype)
+            odm = {}
+            for frame in fko.frame_names:
+                rows = [d for d in distance_data if d[0] == frame]
+                T = fko.forward(torch.as_tensor(q)[None], frame)[0]
+                rel = [T[:3, :3].T @ (torch.as_tensor(d[1]).to(dtype) - T[:3, 3]) for d in rows]
+                odm[frame] = {'relative_position': torch.stack(rel) if rel else torch.zeros(0, 3, dtype=dtype),
+                              'distance': torch.tensor([float(d[4]) for d in rows], dtype=dtype),
+                              'normal_vec': torch.tensor(np.array([d[3] for d in rows]).reshape(-1, 3), dtype=dtype)}
+            sink.append(build(ons, fko, odm).evaluate(torch.as_tensor(q), torch.as_tensor(qd)).numpy())
+    assert_parity(np.stack(got), np.stack(ref32), np.stack(ref64), label="v1 CollisionAvoidance two-joint")
+
+
 def test_edge_cases(ns):
     n = 7
     fk = product_fkine(ns, n)
