@@ -42,7 +42,7 @@ OPT_EARLY_OUT = 0
 EXPORTS = [
     "rmp2_robot_create", "rmp2_robot_destroy", "rmp2_tree_create", "rmp2_tree_destroy",
     "rmp2_tree_update_leaf", "rmp2_step", "rmp2_step_host", "rmp2_rollout", "rmp2_fk",
-    "rmp2_leaf_evaluate", "rmp2_last_error", "rmp2_version", "rmp2_launch_count",
+    "rmp2_leaf_evaluate", "rmp2_obstacle_feed", "rmp2_last_error", "rmp2_version", "rmp2_launch_count",
     "rmp2_tree_kernel_info", "rmp2_tree_profile", "rmp2_tree_profile_read", "rmp2_tree_set_option",
 ]
 
@@ -112,6 +112,8 @@ def lib():
     L.rmp2_fk.restype = ctypes.c_int
     L.rmp2_leaf_evaluate.argtypes = [ctypes.POINTER(LeafDesc), i32, i64, vp, vp, vp, vp, vp, vp]
     L.rmp2_leaf_evaluate.restype = ctypes.c_int
+    L.rmp2_obstacle_feed.argtypes = [vp, vp, i32, i64, vp, vp, i32, vp, i32, vp, vp, vp]
+    L.rmp2_obstacle_feed.restype = ctypes.c_int
     L.rmp2_last_error.argtypes = []
     L.rmp2_last_error.restype = ctypes.c_char_p
     L.rmp2_version.argtypes = []

@@ -788,6 +788,45 @@ int rmp2_fk(const rmp2_robot* rb, int32_t frame, int64_t B, const float* q, cons
   return RMP2_OK;
 }
 
+int rmp2_obstacle_feed(const rmp2_robot* rb, const int32_t* frames, int32_t n_frames, int64_t B, const float* q,
+                       const float* spheres, int32_t n_spheres, const float* capsules, int32_t n_capsules,
+                       float* pairs, float* aux, void* stream) {
+  if (!rb || !frames || !q || !pairs) return fail(RMP2_ERR_INVALID, "robot, frames, q and pairs are required");
+  if (n_frames <= 0 || n_frames > RMP2_MAX_LEAVES) return fail(RMP2_ERR_INVALID, "n_frames out of range");
+  if (n_spheres < 0 || n_capsules < 0 || (n_spheres > 0 && !spheres) || (n_capsules > 0 && !capsules))
+    return fail(RMP2_ERR_INVALID, "obstacle arrays do not match their counts");
+  if (B <= 0) return B == 0 ? RMP2_OK : fail(RMP2_ERR_INVALID, "B must be >= 0");
+  // marker leaves make the tree compiler produce the pruned, depth-first frame table
+  std::vector<rmp2_leaf_desc> marks(n_frames);
+  for (int i = 0; i < n_frames; ++i) {
+    memset(&marks[i], 0, sizeof(rmp2_leaf_desc));
+    marks[i].type = RMP2_LEAF_OBSTACLE_AVOIDANCE;
+    marks[i].space = RMP2_SPACE_FRAME_DISTANCE_SPHERES;
+    marks[i].frame = frames[i];
+    marks[i].goal_slot = -1;
+    for (int k = 0; k < 11; ++k) marks[i].params[k] = 1.f;
+  }
+  rmp2_tree* tmp = nullptr;
+  int rc = rmp2_tree_create(rb, marks.data(), n_frames, &tmp);
+  if (rc != RMP2_OK) return rc;
+  for (int i = 0; i < n_frames; ++i) tmp->tab.leaves[tmp->table_index[i]].pair_set = i;
+  FeedArgs A;
+  A.B = B;
+  A.q = q;
+  A.spheres = spheres;
+  A.capsules = capsules;
+  A.pairs = pairs;
+  A.aux = aux;
+  A.n_spheres = n_spheres;
+  A.n_capsules = n_capsules;
+  A.n_listed = n_frames;
+  cudaError_t e = rmp2_launch_feed(tmp->tab, A, (cudaStream_t)stream);
+  rmp2_tree_destroy(tmp);
+  if (e != cudaSuccess) return cuda_fail(e, "rmp2_obstacle_feed launch");
+  g_launches.fetch_add(1);
+  return RMP2_OK;
+}
+
 int rmp2_leaf_evaluate(const rmp2_leaf_desc* leaf, int32_t m, int64_t K, const float* x, const float* xd,
                        const float* aux, float* xdd, float* M, void* stream) {
   if (!leaf || !x || !xd || !xdd || !M) return fail(RMP2_ERR_INVALID, "null argument");

@@ -557,6 +557,67 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_RESOLVE_MIN_BLOCKS(N)
   finish_step<N>(A, n, e, active, rollout, q, qd, qdd);
 }
 
+// --------------------------------------------------------------------------------- feed kernel
+// On-GPU stand-in for Simulation.calculate_distances (reference: simulation.py:462-484) with primitive
+// obstacles and the frame origin as control point: for every (environment, listed frame, obstacle) one
+// closest-point pair in the reference's distance_data layout -- pair row (pos_on_link, pos_on_obstacle,
+// 0, 0) and aux row (distance, normal from obstacle to link).  Marker leaves carry the listing index of
+// their frame in LeafTab::pair_set.  Spheres: (c, r); capsules: (a, b, r, 0).
+template <int N>
+__global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
+    rmp2_feed_kernel(const __grid_constant__ StepTables T, const __grid_constant__ FeedArgs A) {
+  extern __shared__ float slots[];
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= A.B) return;
+  const int n = T.n;
+  float q[N], qd[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    q[j] = (j < n) ? A.q[env * n + j] : 0.f;
+    qd[j] = 0.f;
+  }
+  float zj[N][3], pj[N][3];
+  Chain ch;
+  chain_reset(ch);
+  const int K = A.n_spheres + A.n_capsules;
+  for (int fi = 0; fi < T.n_frames; ++fi) {
+    visit_frame<N, false>(T, fi, q, qd, ch, zj, pj, slots);
+    const FrameTab& F = T.frames[fi];
+    for (int li = F.leaf_begin; li < F.leaf_end; ++li) {
+      const int listing = T.leaves[li].pair_set;
+      float* prow = A.pairs + ((size_t)env * A.n_listed * K + (size_t)listing * K) * RMP2_PAIR_FLOATS;
+      float* arow = A.aux ? A.aux + ((size_t)env * A.n_listed * K + (size_t)listing * K) * 4 : nullptr;
+      for (int o = 0; o < K; ++o) {
+        float cx, cy, cz, rad;
+        if (o < A.n_spheres) {
+          const float4 sp = __ldg(reinterpret_cast<const float4*>(A.spheres) + (size_t)env * A.n_spheres + o);
+          cx = sp.x, cy = sp.y, cz = sp.z, rad = sp.w;
+        } else {
+          const float4* cp = reinterpret_cast<const float4*>(A.capsules) + ((size_t)env * A.n_capsules + (o - A.n_spheres)) * 2;
+          const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1);          // (ax ay az bx) (by bz r 0)
+          const float ux = c0.w - c0.x, uy = c1.x - c0.y, uz = c1.y - c0.z;
+          const float uu = fmaf(ux, ux, fmaf(uy, uy, uz * uz));
+          float t = fmaf(ch.p[0] - c0.x, ux, fmaf(ch.p[1] - c0.y, uy, (ch.p[2] - c0.z) * uz));
+          t = (uu > 0.f) ? fminf(fmaxf(t / uu, 0.f), 1.f) : 0.f;    // closest point of the axis segment
+          cx = fmaf(t, ux, c0.x), cy = fmaf(t, uy, c0.y), cz = fmaf(t, uz, c0.z), rad = c1.z;
+        }
+        const float rx = ch.p[0] - cx, ry = ch.p[1] - cy, rz = ch.p[2] - cz;
+        const float dc = sqrtf(fmaxf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)), 1e-24f));
+        const float inv = 1.f / dc;
+        const float nx = rx * inv, ny = ry * inv, nz = rz * inv;
+        float* pr = prow + (size_t)o * RMP2_PAIR_FLOATS;
+        pr[0] = ch.p[0], pr[1] = ch.p[1], pr[2] = ch.p[2];
+        pr[3] = fmaf(rad, nx, cx), pr[4] = fmaf(rad, ny, cy), pr[5] = fmaf(rad, nz, cz);
+        pr[6] = 0.f, pr[7] = 0.f;
+        if (arow) {
+          float* ar = arow + (size_t)o * 4;
+          ar[0] = dc - rad, ar[1] = nx, ar[2] = ny, ar[3] = nz;
+        }
+      }
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------- FK kernel
 // Frames of `T` are the path base -> requested frame (serial).  Outputs follow the reference's
 // layout: x = row-major vec of the 4x4 transform (kinematics.py:262), J [16][n].
@@ -861,6 +922,15 @@ cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, si
   if (e != cudaSuccess) return e;
   *regs = attr.numRegs;
   return cudaSuccess;
+}
+
+cudaError_t rmp2_launch_feed(const StepTables& T, const FeedArgs& A, cudaStream_t stream) {
+  const int block = RMP2_BLOCK_THREADS;
+  const long long blocks = (A.B + block - 1) / block;
+  if (blocks <= 0) return cudaSuccess;
+  const size_t smem = (size_t)T.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
+  RMP2_DISPATCH_N(T.n, (rmp2_feed_kernel<NN><<<(unsigned)blocks, block, smem, stream>>>(T, A)));
+  return cudaGetLastError();
 }
 
 cudaError_t rmp2_launch_fk(const StepTables& T, long long B, const float* q, const float* qd, float* x, float* xd,

@@ -22,6 +22,7 @@ cudaError_t rmp2_launch_resolve(const StepTables& T, const StepArgs& A, int bloc
 // which: 0 frames, 1 spheres, 2 step (fused resolve), 3 step (split), 4 resolve
 cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, size_t smem, int* regs,
                                    int* blocks_per_sm);
+cudaError_t rmp2_launch_feed(const StepTables& T, const FeedArgs& A, cudaStream_t stream);
 cudaError_t rmp2_launch_fk(const StepTables& T, long long B, const float* q, const float* qd, float* x, float* xd,
                            float* J, float* c, cudaStream_t stream);
 cudaError_t rmp2_launch_leaf(const LeafTab& L, const LeafVec& V, int m, long long K, const float* x, const float* xd,

@@ -63,6 +63,16 @@ struct SphereTables {
   float p[RMP2_MAX_LEAVES][RMP2_LEAF_PARAMS];
 };
 
+struct FeedArgs {
+  long long B;
+  const float* q;
+  const float* spheres;   // [B][n_spheres][4]
+  const float* capsules;  // [B][n_capsules][8]
+  float* pairs;           // [B][n_listed * (n_spheres + n_capsules)][8]
+  float* aux;             // [B][n_listed * (n_spheres + n_capsules)][4] or NULL
+  int32_t n_spheres, n_capsules, n_listed;
+};
+
 struct ResolveArgs {
   int32_t n;
   float rcond;
