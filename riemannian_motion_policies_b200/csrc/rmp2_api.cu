@@ -859,7 +859,8 @@ int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_sphere
   if (which < 0 || which > 4)
     return fail(RMP2_ERR_INVALID, "which must be 0 (frames), 1 (spheres), 2 (step, fused), 3 (step, split) or 4 (resolve)");
   int block = RMP2_BLOCK_THREADS;
-  size_t smem = (which == 4) ? 0 : (size_t)tree->tab.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
+  size_t smem = (which == 4) ? 0 : (which >= 2 ? rmp2_step_smem(tree->tab, block)
+                                                 : (size_t)tree->tab.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float));
   bool use_tma = false;
   if (which == 1) {
     if (tree->tab.n_sphere_slots == 0) return fail(RMP2_ERR_INVALID, "tree has no sphere-obstacle leaves");

@@ -65,7 +65,7 @@ RMP2_DEV void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int32_t x, int3
 // when kCols, record the world axis and origin of the joint column the frame drives.
 template <int N, bool kCols>
 RMP2_DEV void visit_frame(const StepTables& T, int fi, const float (&q)[N], const float (&qd)[N], Chain& ch,
-                          float (&zj)[N][3], float (&pj)[N][3], float* slots) {
+                          float* cols, float* slots) {
   const FrameTab& F = T.frames[fi];
   if (F.restore_slot == RMP2_SLOT_BASE) {
     chain_reset(ch);
@@ -84,16 +84,13 @@ RMP2_DEV void visit_frame(const StepTables& T, int fi, const float (&q)[N], cons
     }
   float z[3];
   chain_advance(ch, F, qi, qdi, z);
-  if (kCols) {
+  if (kCols && F.qidx >= 0) {                    // joint column -> shared memory (see pullback)
+    float* c = cols + (size_t)F.qidx * 6 * blockDim.x;
 #pragma unroll
-    for (int j = 0; j < N; ++j)
-      if (j == F.qidx) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          zj[j][i] = z[i];
-          pj[j][i] = ch.p[i];
-        }
-      }
+    for (int i = 0; i < 3; ++i) {
+      c[i * blockDim.x] = z[i];
+      c[(3 + i) * blockDim.x] = ch.p[i];
+    }
   }
   if (F.save_slot >= 0) {
     float* s = slots + (size_t)F.save_slot * RMP2_CHAIN_FLOATS * blockDim.x + threadIdx.x;
@@ -118,14 +115,13 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
     q[j] = (j < n) ? A.q[env * n + j] : 0.f;
     qd[j] = (j < n) ? A.qd[env * n + j] : 0.f;
   }
-  float zj[N][3], pj[N][3];   // unused (kCols = false), optimised away
   Chain ch;
   chain_reset(ch);
   // records are field-major: rec[(field * L + slot) * B + env] -> every store below is one full line
   float* rec = A.rec + env;
   const size_t fstride = (size_t)T.n_sphere_slots * A.B;
   for (int fi = 0; fi < T.n_frames; ++fi) {
-    visit_frame<N, false>(T, fi, q, qd, ch, zj, pj, slots);
+    visit_frame<N, false>(T, fi, q, qd, ch, nullptr, slots);
     const FrameTab& F = T.frames[fi];
     for (int li = F.leaf_begin; li < F.leaf_end; ++li) {
       const LeafTab& L = T.leaves[li];
@@ -347,13 +343,13 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, kSplit ? RMP2_SPLIT_MIN_BL
   for (int i = 0; i < N; ++i) f[i] = 0.f;
 
   {
-    float zj[N][3], pj[N][3];
-#pragma unroll
-    for (int j = 0; j < N; ++j) zj[j][0] = zj[j][1] = zj[j][2] = pj[j][0] = pj[j][1] = pj[j][2] = 0.f;
+    // shared memory: [chain-state slots | joint columns (6 N floats per thread)]
+    float* cols = slots + (size_t)T.n_slots * RMP2_CHAIN_FLOATS * blockDim.x + threadIdx.x;
+    const int cstride = blockDim.x;
     Chain ch;
     chain_reset(ch);
     for (int fi = 0; fi < T.n_frames; ++fi) {
-      visit_frame<N, true>(T, fi, q, qd, ch, zj, pj, slots);
+      visit_frame<N, true>(T, fi, q, qd, ch, cols, slots);
       const FrameTab& F = T.frames[fi];
       if (F.leaf_begin >= F.leaf_end) continue;
 
@@ -431,11 +427,11 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, kSplit ? RMP2_SPLIT_MIN_BL
             collision_avoidance_v1(L.p, dist, vec, xd, fl, w);
             const float Sp[6] = {w, 0.f, 0.f, w, 0.f, w};
             const float gp[3] = {w * (fl[0] - cp[0]), w * (fl[1] - cp[1]), w * (fl[2] - cp[2])};
-            pullback<N>(zj, pj, xp, F.anc_mask, T.prismatic_mask, Sp, gp, Msym, f);
+            pullback<N>(cols, cstride, xp, F.anc_mask, T.prismatic_mask, Sp, gp, Msym, f);
           }
         }
       }
-      if (contrib) pullback<N>(zj, pj, ch.p, F.anc_mask, T.prismatic_mask, S, g, Msym, f);
+      if (contrib) pullback<N>(cols, cstride, ch.p, F.anc_mask, T.prismatic_mask, S, g, Msym, f);
     }
   }
 
@@ -576,12 +572,11 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
     q[j] = (j < n) ? A.q[env * n + j] : 0.f;
     qd[j] = 0.f;
   }
-  float zj[N][3], pj[N][3];
   Chain ch;
   chain_reset(ch);
   const int K = A.n_spheres + A.n_capsules;
   for (int fi = 0; fi < T.n_frames; ++fi) {
-    visit_frame<N, false>(T, fi, q, qd, ch, zj, pj, slots);
+    visit_frame<N, false>(T, fi, q, qd, ch, nullptr, slots);
     const FrameTab& F = T.frames[fi];
     for (int li = F.leaf_begin; li < F.leaf_end; ++li) {
       const int listing = T.leaves[li].pair_set;
@@ -810,6 +805,10 @@ __global__ void __launch_bounds__(128)
 }
 
 // -------------------------------------------------------------------------------- host launchers
+size_t rmp2_step_smem(const StepTables& T, int block) {
+  return ((size_t)T.n_slots * RMP2_CHAIN_FLOATS + 6 * (size_t)rmp2_pick_width(T.n)) * block * sizeof(float);
+}
+
 int rmp2_pick_width(int n) {
   if (n <= 2) return 2;
   if (n <= 7) return 7;
@@ -865,7 +864,7 @@ cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, const
 cudaError_t rmp2_launch_step(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream) {
   const long long blocks = (A.B + block - 1) / block;
   if (blocks <= 0) return cudaSuccess;
-  const size_t smem = (size_t)T.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
+  const size_t smem = rmp2_step_smem(T, block);
   if (A.mf) {
     RMP2_DISPATCH_N(T.n, (rmp2_step_kernel<NN, true><<<(unsigned)blocks, block, smem, stream>>>(T, A)));
   } else {

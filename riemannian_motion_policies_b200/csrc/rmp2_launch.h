@@ -12,6 +12,7 @@ struct LeafVec {
 };
 
 int rmp2_pick_width(int n);
+size_t rmp2_step_smem(const StepTables& T, int block);
 
 cudaError_t rmp2_launch_frames(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);
 size_t rmp2_spheres_smem(const SphereTables& ST, int n_spheres, bool use_tma);

@@ -124,8 +124,11 @@ RMP2_DEV void chain_advance(Chain& c, const FrameTab& F, float qi, float qdi, fl
 //   M += J^T S J,   f += J^T g,   J[:, j] = z_j x (p_k - p_j)  (revolute) | z_j (prismatic)
 // S symmetric 3x3 as (xx, xy, xz, yy, yz, zz).  Msym holds the lower triangle, row-major.
 // --------------------------------------------------------------------------------------------------
+// Joint columns live in shared memory, one float per (joint, component, thread):
+//   cols[(j * 6 + i) * stride] = z_j[i] (i < 3) | p_j[i - 3] (i >= 3), `cols` already offset by threadIdx.x
+// (conflict-free, ~30-cycle loads, and 6n registers less than keeping them per thread).
 template <int N>
-RMP2_DEV void pullback(const float (&zj)[N][3], const float (&pj)[N][3], const float (&pk)[3], uint32_t anc,
+RMP2_DEV void pullback(const float* __restrict__ cols, int stride, const float (&pk)[3], uint32_t anc,
                        uint32_t prismatic, const float (&S)[6], const float (&g)[3],
                        float (&Msym)[N * (N + 1) / 2], float (&f)[N]) {
   float col[N][3], u[N][3];
@@ -134,13 +137,15 @@ RMP2_DEV void pullback(const float (&zj)[N][3], const float (&pj)[N][3], const f
     col[j][0] = col[j][1] = col[j][2] = 0.f;
     u[j][0] = u[j][1] = u[j][2] = 0.f;
     if (anc & (1u << j)) {                       // warp-uniform
+      const float z[3] = {cols[(j * 6 + 0) * stride], cols[(j * 6 + 1) * stride], cols[(j * 6 + 2) * stride]};
       if (prismatic & (1u << j)) {
-        col[j][0] = zj[j][0];
-        col[j][1] = zj[j][1];
-        col[j][2] = zj[j][2];
+        col[j][0] = z[0];
+        col[j][1] = z[1];
+        col[j][2] = z[2];
       } else {
-        const float r[3] = {pk[0] - pj[j][0], pk[1] - pj[j][1], pk[2] - pj[j][2]};
-        cross3(zj[j], r, col[j]);
+        const float r[3] = {pk[0] - cols[(j * 6 + 3) * stride], pk[1] - cols[(j * 6 + 4) * stride],
+                            pk[2] - cols[(j * 6 + 5) * stride]};
+        cross3(z, r, col[j]);
       }
       u[j][0] = fmaf(S[0], col[j][0], fmaf(S[1], col[j][1], S[2] * col[j][2]));
       u[j][1] = fmaf(S[1], col[j][0], fmaf(S[3], col[j][1], S[4] * col[j][2]));
