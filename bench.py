@@ -399,6 +399,16 @@ def run_b200_arm(args):
         else:
             dom_bytes = B * BYTES_PER_ENV[config]
             dom_flops = B * FLOPS_PER_ENV[config]
+        # measured DRAM traffic of the same kernel at the same size (one ncu --set full capture, profiles/)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            if tj.get("config") == config and tj.get("envs") == B:
+                for kname, kv in tj["kernels"].items():
+                    if kname.startswith(f"rmp2_{dom}_kernel"):
+                        traffic = kv["dram_bytes_read"] + kv["dram_bytes_write"]
         dom_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
         dom_tflops = dom_flops / (dom_ms * 1e-3) / 1e12
         line = {
@@ -410,7 +420,7 @@ def run_b200_arm(args):
                        "l2_policy": f"inputs larger than L2: {n_buffers} rotating sphere buffers of "
                                     f"{B * O_ * 16 / 1e6:.0f} MB each" if O_ else "q/qd/goal re-read each step"},
             "roofline": {"bound": "hbm", "kernel": f"rmp2_{dom}_kernel", "achieved": dom_gbs, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": dom_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+                         "unit": "GB/s", "frac": dom_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
                          "kernel_ms_per_launch": dom_ms, "kernel_share_of_step": dom_ms / max(total_kernel_ms, 1e-12),
                          "algorithmic_bytes_per_launch": dom_bytes,
                          "note": "this path is FP32/MUFU-issue bound by design, not HBM bound (see roofline_fp32); the "
