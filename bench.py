@@ -153,32 +153,60 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- CPU arm
-def _cpu_worker(args):
-    """One host core: restated reference (oracle), one environment per call like the reference."""
-    config, n, seed, n_envs, n_spheres = args
+_CPU = {}
+
+
+def _cpu_init(config, n, n_spheres):
+    """Pool initializer: import the oracle, build the kinematics once and pay torch's first-call cost."""
     import torch
     torch.set_num_threads(1)
     from oracle import harness as H
     from riemannian_motion_policies_b200 import scenarios as S
-    q, qd, goal = S.sample_panda_state(n_envs + 1, n, seed)
-    sph = S.sample_spheres(n_envs + 1, n_spheres, seed) if n_spheres else None
-    fk = H.make_fkine(n)
-    H.evaluate_loop(config, n, q[:1], qd[:1], goal[:1], None if sph is None else sph[:1], fkine=fk)   # warm-up
+    _CPU.update(H=H, S=S, config=config, n=n, n_spheres=n_spheres, fk=H.make_fkine(n))
+    _cpu_worker((999, 1))
+
+
+def _cpu_worker(args):
+    """One host core: restated reference (oracle), one environment per call like the reference."""
+    seed, n_envs = args
+    H, S, config, n, O_ = _CPU["H"], _CPU["S"], _CPU["config"], _CPU["n"], _CPU["n_spheres"]
+    q, qd, goal = S.sample_panda_state(n_envs, n, seed)
+    sph = S.sample_spheres(n_envs, O_, seed) if O_ else None
     t0 = time.perf_counter()
-    H.evaluate_loop(config, n, q[1:], qd[1:], goal[1:], None if sph is None else sph[1:], fkine=fk)
+    H.evaluate_loop(config, n, q, qd, goal, sph, fkine=_CPU["fk"])
     return n_envs, time.perf_counter() - t0
 
 
+class CpuReference:
+    """The restated reference on `cores` host processes (1 thread each), warmed up once."""
+
+    def __init__(self, config, n, cores, n_spheres):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context("spawn").Pool(cores, initializer=_cpu_init, initargs=(config, n, n_spheres))
+        self.step_id = 0
+
+    def step(self, envs_per_core):
+        """One bounded sample: every core evaluates `envs_per_core` environments; -> (env-steps/s, envs, seconds)."""
+        self.step_id += 1
+        jobs = [(1000 * self.step_id + i, envs_per_core) for i in range(self.cores)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+        total = sum(r[0] for r in res)
+        return total / wall, total, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
 def cpu_reference_throughput(config, n, cores, envs_per_core, n_spheres):
-    """env-steps/s of the restated reference on `cores` host processes (1 thread each)."""
-    import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    jobs = [(config, n, 1000 + i, envs_per_core, n_spheres) for i in range(cores)]
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, jobs)
-    total = sum(r[0] for r in res)
-    slowest = max(r[1] for r in res)
-    return total / slowest, total, slowest
+    ref = CpuReference(config, n, cores, n_spheres)
+    try:
+        return ref.step(envs_per_core)
+    finally:
+        ref.close()
 
 
 def host_cores():
@@ -200,14 +228,22 @@ def run_reference_arm(args):
     cores = min(host_cores(), 64)
     per_core = max(2, args.envs_per_core)
     O_ = {2: 0, 3: 16, 4: 64, 5: 64}[config]
-    values = []
-    for _ in range(max(1, args.steps)):
-        v, total, slowest = cpu_reference_throughput(config, n, cores, per_core, O_)
-        values.append(v)
+    ref = CpuReference(config, n, cores, O_)
+    values, t_start = [], time.perf_counter()
+    try:
+        for _ in range(max(0, args.warmup)):
+            ref.step(1)
+        for _ in range(max(1, args.steps)):
+            values.append(ref.step(per_core)[0])
+            if time.perf_counter() - t_start > args.reference_budget_s:     # bounded: a few minutes at most
+                break
+    finally:
+        ref.close()
     value = float(np.median(values))
     sample = f"{cores} processes x {per_core} envs per step, one env per RmpCore.evaluate call (autodiff per leaf)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "steps_measured": len(values),
         "warmup": args.warmup, "ms_per_step": 1e3 * cores * per_core / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD[config], "envs_per_step": cores * per_core, "spheres_per_env": O_, "dof": n},
@@ -451,6 +487,7 @@ def main():
     ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4, 5])
     ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: 1,048,576)")
     ap.add_argument("--envs-per-core", type=int, default=6, help="CPU arm: environments per host process per step")
+    ap.add_argument("--reference-budget-s", type=float, default=150.0, help="CPU arm: stop after this many seconds")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-early-out", action="store_true")
     ap.add_argument("--skip-checks", action="store_true", help="skip the oracle parity spot check and the CPU baseline")

@@ -150,16 +150,36 @@ class TaskmapJointFrame4x4ToSphereDistance(Taskmap):
 
 
 class TaskmapFrom4x4ToEuler(Taskmap):
-    """reference: taskmap.py:57-67 -- orientation task map, not on the control-step path
-    (SURVEY.md section 8f, rank 4)."""
+    """xyz Euler angles of the rotation block (reference: taskmap.py:57-67, kinematics.py:74-96).
+    Not on the control-step path -- the reference only uses it in tests/test_taskmaps.py -- so the
+    derivatives are written out in closed form as torch ops on CUDA tensors:
+        theta_y = -asin(r20), theta_z = atan2(r10, r00), theta_x = atan2(r21, r22)
+    (dividing both atan2 arguments by cos(theta_y) > 0 as the reference does leaves the angle unchanged)."""
+
+    @staticmethod
+    def _angles(T):
+        r00, r10, r20, r21, r22 = T[:, 0], T[:, 4], T[:, 8], T[:, 9], T[:, 10]
+        theta_y = -torch.asin(r20)
+        cy = torch.cos(theta_y)
+        safe = torch.where(cy.abs() < 1e-6, torch.ones_like(cy), cy)
+        return torch.stack((torch.atan2(r21 / safe, r22 / safe), theta_y, torch.atan2(r10 / safe, r00 / safe)), dim=-1)
 
     def forward(self, input):
-        from .kinematics import euler_from_rotation_matrix
-        t = to_device(input)
-        return like_input(euler_from_rotation_matrix(t.reshape(-1, 4, 4)[:, :3, :3]), input)
+        t = to_device(input).reshape(-1, 16)
+        return like_input(self._angles(t), input)
 
     def differentiate(self, q, qd):
-        raise NotImplementedError("TaskmapFrom4x4ToEuler.differentiate is outside the accelerated hot path")
+        """x [K,3], xd [K,3], J [K,3,16], c [K,3] with q = vec(T) [K,16] and qd its velocity."""
+        from torch.func import jacrev, jvp, vmap
+        dev = require_cuda()
+        qt, qdt = to_device(q, dev).reshape(-1, 16), to_device(qd, dev).reshape(-1, 16)
+        one = lambda t: self._angles(t[None])[0]
+        x = self._angles(qt)
+        J = vmap(jacrev(one))(qt)
+        xd = (J @ qdt[..., None])[..., 0]
+        vel = lambda t, td: jvp(one, (t,), (td,))[1]
+        c = vmap(lambda t, td: jvp(lambda u: vel(u, td), (t,), (td,))[1])(qt, qdt)
+        return tuple(like_input(o, q) for o in (x, xd, J, c))
 
 
 class TaskmapRelative4x4(Taskmap):

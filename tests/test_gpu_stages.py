@@ -49,6 +49,23 @@ def test_fk_reference_call_shapes(ns):
         fk.forward(np.zeros((1, 9), np.float32), "no_such_frame")
 
 
+def test_euler_taskmap_chain(ns):
+    """chain [FK, TaskmapFrom4x4ToEuler] (reference: tests/test_taskmaps.py:18-76 checks this chain's J against
+    PyBullet's angular Jacobian at 1e-3): x, xd, J, c against the float64 autodiff oracle."""
+    fk = product_fkine(ns, 7)
+    ofk = H.make_fkine(7, torch.float64)
+    tm = ns.chain_taskmaps([ns.TaskmapByForwardKinematic(fk, "panda_joint6"), ns.TaskmapFrom4x4ToEuler()])
+    otm = O.chain_taskmaps([O.TaskmapByForwardKinematic(ofk, "panda_joint6"), O.TaskmapFrom4x4ToEuler()])
+    q, qd, _ = S.sample_panda_state(5, 7, seed=9)
+    for b in range(5):
+        x, xd, J, c = (t.numpy() for t in tm.differentiate(q[b:b + 1], qd[b:b + 1]))
+        xo, xdo, Jo, co = (t.numpy() for t in otm.differentiate(torch.as_tensor(q[b:b + 1]).double(), torch.as_tensor(qd[b:b + 1]).double()))
+        np.testing.assert_allclose(x, xo, atol=1e-5)
+        np.testing.assert_allclose(J, Jo, atol=1e-4)
+        np.testing.assert_allclose(xd, xdo, atol=1e-4)
+        np.testing.assert_allclose(c, co, atol=1e-3)
+
+
 def _leaf_pairs(ns, ons):
     lim_lo, lim_hi = S.PANDA_Q_LOW[:7], S.PANDA_Q_HIGH[:7]
     mk = lambda m: (
