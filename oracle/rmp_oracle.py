@@ -20,11 +20,16 @@ PINNING STATUS
     against SciPy exactly as the reference's tests do (reference: tests/test_kinematic_forwards.py:16-106).
   * FK of every Panda frame: the reference pins it against PyBullet (tests/test_kinematic_forwards.py:108-137);
     PyBullet is absent, so it is pinned against an independent float64 SciPy FK instead.
-  * J-dot q-dot, every leaf policy, the pullback, the accumulation dtype and the pinv cutoff:
-    **PARITY UNPINNED** -- the reference holds no test or golden vector for them and cannot be
-    run here.  The restatement follows the source line by line; third-party semantics that
-    are restated from the published TensorFlow 2.10 implementation: ``tf.linalg.pinv``
-    (rcond = 10 * max(rows, cols) * eps, SVD, singular values <= rcond * max replaced by inf).
+  * FK derivatives (x, xd, J, J-dot q-dot), every leaf policy, the task-map chains, the pullback, the
+    accumulation and the resolve: pinned against the REFERENCE'S OWN SOURCE FILES, executed unchanged in the
+    build container with a TensorFlow-API stand-in over torch (oracle/tf_shim; TensorFlow itself is not
+    installed): tests/golden/run_reference_under_shim.py -> tests/golden/ref_*.npz, checked by
+    tests/test_reference_golden.py (and re-generated live there whenever /root/reference is present).
+  * Still restated rather than executed, because they live inside TensorFlow 2.10 (third party, absent):
+    ``tf.linalg.pinv`` (rcond = 10 * max(rows, cols) * eps, SVD, singular values <= rcond * max replaced by
+    inf), the ``ndarray += Tensor`` deferral that makes the accumulators float32 and
+    ``GradientTape`` (torch autograd in the shim).  For exactly these three, parity with a real TensorFlow
+    run remains UNPINNED; the reference holds no test or golden vector for them.
 
 dtype switch: ``dtype=torch.float32`` is the reference-faithful mode (everything, including the
 accumulators and the pinv, runs in float32 -- SURVEY.md section 0); ``dtype=torch.float64`` is the

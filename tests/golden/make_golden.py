@@ -8,8 +8,9 @@
     both the oracle's and the product's URDF readers to the real reference.
 (b) config*.npz / fk_*.npz -- seeded inputs with the outputs of the CPU oracle (oracle/rmp_oracle.py)
     in float32 (reference-faithful) and float64 (truth).  The reference itself (TensorFlow) cannot run
-    here, so these are ORACLE outputs, not reference outputs (see the oracle header: parity unpinned
-    for leaves / pullback / resolve).
+    here, so these are ORACLE outputs, not reference outputs.
+(c) ref_*.npz come from a different script, run_reference_under_shim.py: the reference's own source files
+    executed under oracle/tf_shim.
 """
 import json
 import os

@@ -29,6 +29,46 @@ def test_golden_fixtures(ns, config, n):
     print(f"config{config} n{n}: {stats}")
 
 
+@pytest.mark.parametrize("config,n", [(1, 2), (2, 7), (2, 9), (3, 7), (3, 9), (4, 7), (5, 7)])
+def test_reference_source_vectors(ns, config, n):
+    """tests/golden/ref_*.npz: outputs of the REFERENCE'S OWN source files run under the TensorFlow-API shim
+    (tests/golden/run_reference_under_shim.py).  The kernel must match them like it matches the oracle."""
+    g = np.load(os.path.join(GOLDEN, f"ref_config{config}_n{n}.npz"))
+    sph = g["spheres"] if "spheres" in g else None
+    got = product_evaluate(ns, config, n, g["q"], g["qd"], g["goal"], sph)
+    ref64 = H.evaluate_vmap(config, n, g["q"], g["qd"], g["goal"], sph, dtype=torch.float64)
+    _, M64 = H.combined_vmap(config, n, g["q"], g["qd"], g["goal"], sph, dtype=torch.float64)
+    stats = assert_parity(got, g["qdd_ref"], ref64, M64, n, label=f"reference-source config{config} n{n}", max_excluded=0.3)
+    print(f"reference-source config{config} n{n}: {stats}")
+
+
+def test_reference_source_vectors_v1(ns):
+    """The v1 CollisionAvoidance tree of the reference (two-joint experiment 05) on the same distance_data."""
+    g = np.load(os.path.join(GOLDEN, "ref_v1_two_joint.npz"))
+    fk = product_fkine(ns, 2)
+    frames = list(g["frames"])
+    got = []
+    for b in range(g["q"].shape[0]):
+        q, qd, goal, rows = g["q"][b], g["qd"][b], g["goal"][b], g["distance_rows"][b]
+        distance_data = [(frames[i], rows[i, 0:3], rows[i, 3:6], rows[i, 6:9], rows[i, 9], "golden") for i in range(len(frames))]
+        dm = ns.Datamanager(fk)
+        core = ns.RmpCore()
+        core.add_rmp(ns.TargetPolicy(alpha=0.1, beta=0.1, c=0.1, goal=goal, name="target",
+                                     taskmap=S.ee_position_taskmap(ns, fk, "link_23")))
+        for frame in fk.frame_names:
+            tm = ns.chain_taskmaps([ns.TaskmapByForwardKinematic(fk, frame),
+                                    ns.TaskmapRelative4x4(relative_pos=dm[frame]["relative_position"]),
+                                    ns.TaskmapFrom4x4ToPosition()])
+            core.add_rmp(ns.CollisionAvoidance(d=dm[frame]["distance"], vec=dm[frame]["normal_vec"],
+                                               eta_rep=0.1 * np.e, nu_rep=0.3, eta_damp=1, nu_damp=0.3, r=1.1, c=1e5,
+                                               taskmap=tm, name=f"collision_avoidance_for_{frame}"))
+        dm.update(q, distance_data)
+        got.append(core.evaluate(q, qd).numpy())
+    from test_reference_golden import v1_oracle
+    ref64 = np.stack([v1_oracle(g, b, torch.float64) for b in range(g["q"].shape[0])])
+    assert_parity(np.stack(got), g["qdd_ref"], ref64, label="reference-source v1 CollisionAvoidance")
+
+
 @pytest.mark.parametrize("config,n,B", [(1, 2, 1000), (2, 7, 4096), (3, 7, 2048), (4, 7, 1024), (5, 7, 1024), (5, 9, 256)])
 def test_seeded_batches_against_oracle(ns, config, n, B):
     """Same seeded inputs through the oracle (vmap, f32 and f64) and the kernel."""
