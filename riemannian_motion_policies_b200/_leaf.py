@@ -16,6 +16,9 @@ def as_float_list(value, length=None, what="vector"):
     return [float(v) for v in arr]
 
 
+import inspect
+
+
 class RiemannianMotionPolicy:
     """Abstract leaf: a task map plus ``evaluate(x, xd) -> (xdd, M)``."""
 
@@ -70,3 +73,45 @@ class RiemannianMotionPolicy:
                                                        None if aux is None else aux.data_ptr(), xdd.data_ptr(),
                                                        M.data_ptr(), current_stream_ptr(dev)))
         return like_input(xdd, x), like_input(M, x)
+
+
+class DeclaredLeaf(RiemannianMotionPolicy):
+    """Leaf whose constructor is declared as data: ``FIELDS`` lists the constructor arguments in the
+    reference's order, as ``name`` or ``(name, default)``; every argument becomes an attribute of the same
+    name, exactly as the reference's constructors do by hand.  ``taskmap`` / ``name`` may be among them;
+    a leaf without a ``taskmap`` argument lives on the identity task map."""
+
+    FIELDS = ()
+    PARAMS = ()          # attribute names handed to the kernel, in the order of include/rmp2_b200.h
+
+    @classmethod
+    def _signature(cls):
+        ps = []
+        for f in cls.FIELDS:
+            name, default = (f, inspect.Parameter.empty) if isinstance(f, str) else f
+            ps.append(inspect.Parameter(name, inspect.Parameter.POSITIONAL_OR_KEYWORD, default=default))
+        return inspect.Signature(ps)
+
+    def __init_subclass__(cls, **kwargs):
+        super().__init_subclass__(**kwargs)
+        if cls.FIELDS:
+            cls.__signature__ = cls._signature()
+
+    def __init__(self, *args, **kwargs):
+        bound = self._signature().bind(*args, **kwargs)
+        bound.apply_defaults()
+        values = dict(bound.arguments)
+        taskmap = values.pop("taskmap", None)
+        if taskmap is None:
+            from .taskmap import IdentityTaskmap
+            taskmap = IdentityTaskmap()
+        super().__init__(values.pop("name"), taskmap)
+        for key, value in values.items():
+            setattr(self, key, value)
+        self._post_init()
+
+    def _post_init(self):
+        pass
+
+    def _params(self):
+        return [getattr(self, k) for k in self.PARAMS]
