@@ -55,6 +55,18 @@ def test_environments_are_independent(world):
         assert torch.equal(part, w["qdd"][lo:hi])
 
 
+def test_batches_beyond_one_internal_chunk(world):
+    """rmp2_step processes at most 2^20 environments per internal chunk (bounded scratch); a batch of
+    2^20 + 12345 environments must give the same rows as the pieces it is made of."""
+    w = world
+    extra = 12345
+    cat = lambda t: torch.cat([t, t[:extra]], dim=0).contiguous()
+    out = torch.empty(B_FULL + extra, N, device=w["dev"])
+    w["tree"].step(cat(w["q"]), cat(w["qd"]), out, goals=cat(w["goals"]), spheres=cat(w["spheres"]))
+    assert torch.equal(out[:B_FULL], w["qdd"])
+    assert torch.equal(out[B_FULL:], w["qdd"][:extra])
+
+
 def test_full_size_subset_against_oracle(world):
     w = world
     rng = np.random.RandomState(1)
