@@ -70,6 +70,31 @@ struct rmp2_tree {
 
 #define RMP2_STEP_CHUNK (1LL << 20)       // environments per internal chunk (bounds the scratch)
 
+// Sphere-row parameters of an ObstacleAvoidance leaf for the packed pair loop (SP_* in rmp2_leaves.cuh).
+// The kernel works with xs = clamp((x - margin)/r, 0, 1): r is folded into every coefficient that
+// multiplies x, metric_scalar into the first denominator.  A leaf whose metric vanishes identically
+// (metric_scalar == 0, or a radius <= 0: rmp2.py:187,194) gets a zero gate.
+static void fill_sphere_row(const rmp2_leaf_desc& d, float* row) {
+  const float* r = d.params;
+  for (int i = 0; i < RMP2_LEAF_PARAMS; ++i) row[i] = 0.f;
+  const double margin = r[0], rad = r[7], ms = r[8];
+  const bool live = (ms != 0.0) && (rad > 0.0);
+  const double fold = live ? ms : 1.0, R = live ? rad : 1.0;
+  row[SP_XA] = (float)(1.0 / R);
+  row[SP_XB] = (float)(-margin / R);
+  row[SP_GT_A] = live ? 1.f : 0.f;
+  row[SP_GT_B] = live ? -1.f : 0.f;
+  row[SP_D1A] = (float)(R / ((double)r[9] * fold));
+  row[SP_D1B] = (float)((double)r[10] / fold);
+  row[SP_D2A] = (float)(R / (double)r[2]);
+  row[SP_D2B] = r[3];
+  row[SP_K_VEL] = (float)(1.4426950408889634 / (double)r[4]);
+  row[SP_K_REP] = (float)(-1.4426950408889634 * R / (double)r[6]);
+  row[SP_RGAIN] = r[5];
+  row[SP_NEG_DGAIN] = -r[1];
+  row[SP_REACH] = (float)((rad + margin) * 1.00001);
+}
+
 // ------------------------------------------------------------------------------ parameter derivation
 // Raw constructor arguments (layout in include/rmp2_b200.h) -> kernel parameters (rmp2_leaves.cuh).
 // Python evaluates these expressions in double before they meet a float32 tensor, so they are
@@ -337,7 +362,7 @@ int rmp2_tree_create(const rmp2_robot* rb, const rmp2_leaf_desc* leaves, int32_t
     if (rc != RMP2_OK) return rc;
     if (L.space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) {
       L.sphere_slot = T.n_sphere_slots++;
-      for (int j = 0; j < RMP2_LEAF_PARAMS; ++j) tr->sph.p[L.sphere_slot][j] = L.p[j];
+      fill_sphere_row(leaves[i], tr->sph.p[L.sphere_slot]);
     }
     if (vec_cursor + vlen > RMP2_VECPOOL) return fail(RMP2_ERR_UNSUPPORTED, "vector-parameter pool exhausted");
     L.vec_off = vec_cursor;
@@ -433,7 +458,7 @@ int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* 
   if (rc != RMP2_OK) return rc;
   for (int j = 0; j < vlen; ++j) tree->tab.vecpool[L.vec_off + j] = vec[j];
   if (L.sphere_slot >= 0)
-    for (int j = 0; j < RMP2_LEAF_PARAMS; ++j) tree->sph.p[L.sphere_slot][j] = L.p[j];
+    fill_sphere_row(*leaf, tree->sph.p[L.sphere_slot]);
   tree->leaves[index] = *leaf;
   return RMP2_OK;
 }

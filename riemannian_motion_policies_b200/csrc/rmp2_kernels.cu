@@ -60,6 +60,13 @@ RMP2_DEV void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int32_t x, int3
       : "memory");
 }
 
+// read-only 16-byte shared-memory load the compiler may schedule freely (see rmp2_spheres_kernel)
+RMP2_DEV float4 lds128(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 // ------------------------------------------------------------------------------ chain walking
 // Visit frame `fi` of the depth-first execution list: restore / advance / save the chain state and,
 // when kCols, record the world axis and origin of the joint column the frame drives.
@@ -147,8 +154,14 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 // consecutive environments, so record loads/stores are contiguous across lanes and every quarter
 // warp reads 8 distinct swizzled rows of the staged spheres.  Staged layout: box b (8 spheres) = E rows of 128 B, box stride padded to
 // 1024 B so that the 128-byte TMA swizzle (16-byte chunk index XOR row & 7) is row-relative.
+#ifndef RMP2_SPHERES_MIN_BLOCKS
+#define RMP2_SPHERES_MIN_BLOCKS 5     // resident blocks per SM the register allocation aims at (<= 102 registers)
+#endif
+#ifndef RMP2_SPHERES_STEPS_PER_TRIP
+#define RMP2_SPHERES_STEPS_PER_TRIP 4 // packed (two-sphere) steps per loop trip of the TMA path: 2 or 4
+#endif
 template <bool kTma, bool kSkip>
-__global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
+__global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_SPHERES_MIN_BLOCKS)
     rmp2_spheres_kernel(const __grid_constant__ SphereTables ST, const __grid_constant__ StepArgs A,
                         const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -175,7 +188,10 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
     __syncthreads();                              // barrier initialised before anyone polls it
     if (!active) return;
     mbar_wait(bar, 0);
-    tiles += (uint32_t)e_local * 128u;
+    tiles += (uint32_t)e_local * 128u;            // this thread's 128-byte row of box 0
+    // the sphere loads below are plain (non-volatile) asm so that the scheduler may hoist them over
+    // arithmetic; making their address depend on this statement keeps them after the wait
+    asm volatile("" : "+r"(tiles) : : "memory");
   } else {
     if (!active) return;
   }
@@ -191,28 +207,37 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 #pragma unroll
   for (int i = 0; i < RMP2_LEAF_PARAMS; ++i) p[i] = ST.p[slot][i];
 
-  float S[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float g[3] = {0.f, 0.f, 0.f};
-  auto one_sphere = [&](const float4 sp) {
+  // Two spheres per step in packed f32x2 arithmetic: lane x of every accumulator takes the even
+  // spheres of the environment, lane y the odd ones (fixed assignment -> the early-out variant adds
+  // the same terms to the same accumulators in the same order and stays bit-identical).
+  float2 S[6], g[3];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) S[i] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) g[i] = make_float2(0.f, 0.f);
+  auto two_spheres = [&](const float4 s0, const float4 s1) {
     // pos_on_link = frame origin; pos_on_obstacle = closest surface point of the sphere
-    const float rx = px - sp.x, ry = py - sp.y, rz = pz - sp.z;
-    const float dc2 = fmaxf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)), 1e-24f);
-    const float inv_dc = fast_rsqrt(dc2);
-    const float sd = fmaf(dc2, inv_dc, -sp.w);               // signed surface distance
-    const float sgn = (sd < 0.f) ? -inv_dc : inv_dc;
-    const float d = fmaxf(fabsf(sd), 1e-12f);
-    obstacle_pair(p, rx * sgn, ry * sgn, rz * sgn, d, fast_rcp(d), v, a, vv, S, g);
+    const float2 rx = make_float2(px - s0.x, px - s1.x);
+    const float2 ry = make_float2(py - s0.y, py - s1.y);
+    const float2 rz = make_float2(pz - s0.z, pz - s1.z);
+    // |r|^2 + 1e-24: a centre on the frame origin stays finite without a separate clamp
+    const float2 dc2 = __ffma2_rn(rx, rx, __ffma2_rn(ry, ry, __ffma2_rn(rz, rz, bc2(1e-24f))));
+    const float2 inv_dc = make_float2(fast_rsqrt(dc2.x), fast_rsqrt(dc2.y));
+    const float2 sd = make_float2(fmaf(dc2.x, inv_dc.x, -s0.w), fmaf(dc2.y, inv_dc.y, -s1.w));   // signed surface distance
+    const float2 sgn = make_float2(copysignf(inv_dc.x, sd.x), copysignf(inv_dc.y, sd.y));       // inside: normal flips
+    const float2 d = make_float2(fmaxf(fabsf(sd.x), 1e-12f), fmaxf(fabsf(sd.y), 1e-12f));
+    const float2 inv_d = make_float2(fast_rcp(d.x), fast_rcp(d.y));
+    obstacle_pair2(p, __fmul2_rn(rx, sgn), __fmul2_rn(ry, sgn), __fmul2_rn(rz, sgn), d, inv_d, v, a, vv, S, g);
   };
+  // a sphere that contributes exactly zero (beyond every metric radius; d ~ 1e15 keeps all terms finite)
+  const float4 far_away = make_float4(px + 1e15f, py, pz, 0.f);
   const uint32_t x7 = ((uint32_t)e_local & 7u) << 4;
   const uint32_t box_stride = ((uint32_t)E * 128u + 1023u) & ~1023u;
   const float4* gs = reinterpret_cast<const float4*>(A.spheres) + (size_t)env * O;
   auto load_sphere = [&](int o) -> float4 {
     float4 sp;
     if (kTma) {
-      const uint32_t addr = tiles + (uint32_t)(o >> 3) * box_stride + ((((uint32_t)o & 7u) << 4) ^ x7);
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(sp.x), "=f"(sp.y), "=f"(sp.z), "=f"(sp.w)
-                   : "r"(addr));
+      sp = lds128(tiles + (uint32_t)(o >> 3) * box_stride + ((((uint32_t)o & 7u) << 4) ^ x7));
     } else {
       sp = __ldg(gs + o);
     }
@@ -220,57 +245,77 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
   };
   if (!kSkip) {
     if (kTma) {
-      // 8 swizzled chunk addresses of this thread's row, advanced by one box stride per box;
-      // 4 spheres per trip so that the unrolled body stays inside the L0 instruction cache
+      // 8 swizzled chunk addresses of this thread's row (per-thread, loop invariant) plus the
+      // warp-uniform box offset: LDS.128 [R + UR], no per-thread address arithmetic in the loop
+      constexpr int kStepsPerTrip = RMP2_SPHERES_STEPS_PER_TRIP;
       uint32_t addr[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) addr[c] = tiles + ((((uint32_t)c) << 4) ^ x7);
-      for (int b = 0; b < (O >> 3); ++b) {
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
+      uint32_t box_off = 0;
+      for (int b = 0; b < (O >> 3); ++b, box_off += box_stride) {
+        if (kStepsPerTrip == 4) {
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            float4 sp;
-            const uint32_t ad = (h == 0) ? addr[c4] : addr[4 + c4];
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(sp.x), "=f"(sp.y), "=f"(sp.z), "=f"(sp.w)
-                         : "r"(ad));
-            one_sphere(sp);
+          for (int c2 = 0; c2 < 8; c2 += 2) two_spheres(lds128(addr[c2] + box_off), lds128(addr[c2 + 1] + box_off));
+        } else {
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int c2 = 0; c2 < 4; c2 += 2) {
+              const uint32_t ad0 = (h == 0) ? addr[c2] : addr[4 + c2];
+              const uint32_t ad1 = (h == 0) ? addr[c2 + 1] : addr[5 + c2];
+              two_spheres(lds128(ad0 + box_off), lds128(ad1 + box_off));
+            }
           }
         }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) addr[c] += box_stride;
       }
     } else {
-#pragma unroll 4
-      for (int o = 0; o < O; ++o) one_sphere(load_sphere(o));
+      int o = 0;
+#pragma unroll 2
+      for (; o + 1 < O; o += 2) two_spheres(load_sphere(o), load_sphere(o + 1));
+      if (o < O) two_spheres(load_sphere(o), far_away);
     }
   } else {
     // Exact early-out (reference: rmp2.py:194 -- a pair beyond the metric radius has M = 0 and adds
-    // exactly nothing): first a cheap squared-distance test of every sphere into a bit mask, then the
-    // full pair only for the set bits.  The test is conservative (1e-5 wider than the leaf's own test).
-    const float reach = (p[OA_R] + p[OA_MARGIN]) * 1.00001f;
+    // exactly nothing): first a cheap squared-distance test of every sphere into two bit masks (even
+    // and odd spheres), then the full pair only for the set bits, an even with an odd sphere per packed
+    // step (the shorter list is padded with far_away).  The test is conservative (1e-5 wider than the
+    // leaf's own test).
+    const float reach = p[SP_REACH];
     for (int o0 = 0; o0 < O; o0 += 64) {
-      unsigned long long mask = 0ull;
+      uint32_t mask_even = 0u, mask_odd = 0u;
       const int cnt = min(64, O - o0);
-      for (int o = 0; o < cnt; ++o) {
-        const float4 sp = load_sphere(o0 + o);
-        const float rx = px - sp.x, ry = py - sp.y, rz = pz - sp.z;
-        const float dc2 = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
-        const float lim = sp.w + reach;
-        mask |= (unsigned long long)(dc2 <= lim * lim) << o;
+      for (int o = 0; o < cnt; o += 2) {
+        const float4 s0 = load_sphere(o0 + o);
+        const float4 s1 = (o + 1 < cnt) ? load_sphere(o0 + o + 1) : far_away;
+        const float2 rx = make_float2(px - s0.x, px - s1.x);
+        const float2 ry = make_float2(py - s0.y, py - s1.y);
+        const float2 rz = make_float2(pz - s0.z, pz - s1.z);
+        const float2 dc2 = __ffma2_rn(rx, rx, __ffma2_rn(ry, ry, __fmul2_rn(rz, rz)));
+        const float2 lim = make_float2(s0.w + reach, s1.w + reach);
+        const float2 lim2 = __fmul2_rn(lim, lim);
+        mask_even |= (uint32_t)(dc2.x <= lim2.x) << (o >> 1);
+        mask_odd |= (uint32_t)(dc2.y <= lim2.y) << (o >> 1);
       }
-      while (mask) {
-        const int o = __ffsll((long long)mask) - 1;
-        mask &= mask - 1ull;
-        one_sphere(load_sphere(o0 + o));
+      while (mask_even | mask_odd) {
+        float4 s0 = far_away, s1 = far_away;
+        if (mask_even) {
+          const int k = __ffs((int)mask_even) - 1;
+          mask_even &= mask_even - 1u;
+          s0 = load_sphere(o0 + 2 * k);
+        }
+        if (mask_odd) {
+          const int k = __ffs((int)mask_odd) - 1;
+          mask_odd &= mask_odd - 1u;
+          s1 = load_sphere(o0 + 2 * k + 1);
+        }
+        two_spheres(s0, s1);
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 6; ++i) rec[i * fstride] = S[i];       // fields 0..5: S, 6..8: g (in place)
+  for (int i = 0; i < 6; ++i) rec[i * fstride] = S[i].x + S[i].y;       // fields 0..5: S, 6..8: g (in place)
 #pragma unroll
-  for (int i = 0; i < 3; ++i) rec[(6 + i) * fstride] = g[i];
+  for (int i = 0; i < 3; ++i) rec[(6 + i) * fstride] = g[i].x + g[i].y;
 }
 
 // --------------------------------------------------------------------------------- step kernel

@@ -204,6 +204,81 @@ RMP2_DEV void obstacle_pair(const float* __restrict__ p, float nx, float ny, flo
   g[2] = fmaf(h, nz, g[2]);
 }
 
+// ---- packed form of the pair, two spheres per thread step (rmp2_spheres_kernel) ---------------------
+// Blackwell issues fma/mul/add.f32x2 (SASS FFMA2) on register pairs: half the issue slots of the scalar
+// form for the same FP32-lane work, which lets the MUFU pipe run underneath it.  Measured on a B200
+// (tools/pipe_peaks.cu): FFMA2 sustains 124-128 FMA/clk/SM with MUFU overlapped; scalar FFMA 97-107;
+// and every ALU-pipe instruction (FMNMX, FSEL, FSETP, LOP3) takes the same lane time as a scalar FP32
+// instruction away from FFMA2.  So the cost of a pair is its count of lane operations, FP32 and ALU
+// alike, and the leaf is arranged to minimise that count (49 lane operations and 5 MUFU per pair;
+// the first scalar version had 61 and 6):
+//   xs = sat((d - margin)/r) in ONE FFMA.SAT replaces max(.,0), the x > r test and its select:
+//        gate = (xs - 1)^2 is exactly 0 beyond the radius (rmp2.py:170-174, 194), r is folded into the
+//        coefficients that multiply x;
+//   one reciprocal q = 1 / (den1' den2 (1 + e_v)) gives  (1-sigmoid) m0 = q den2  and
+//        (1-sigmoid)/den2 = q den1'   (den1' = den1 / metric_scalar, e_v = exp(xdot / l_v));
+//   xdd - c = G e_rep - D t - c  as two FMAs.
+// Sphere-row parameters, derived on the host in double (fill_sphere_row, rmp2_api.cu):
+#define SP_XA 0           // 1 / r
+#define SP_XB 1           // -margin / r
+#define SP_GT_A 2         // 1            (0 when metric_scalar == 0: the leaf's metric vanishes)
+#define SP_GT_B 3         // -1           (0 when metric_scalar == 0)
+#define SP_D1A 4          // r / (metric_exploder_std_dev * metric_scalar)
+#define SP_D1B 5          // metric_exploder_eps / metric_scalar
+#define SP_D2A 6          // r / damping_std_dev
+#define SP_D2B 7          // damping_robustness_eps
+#define SP_K_VEL 8        //  log2(e) / damping_velocity_gate_length_scale
+#define SP_K_REP 9        // -log2(e) r / repulsion_std_dev
+#define SP_RGAIN 10
+#define SP_NEG_DGAIN 11
+#define SP_REACH 12       // (r + margin) * (1 + 1e-5): conservative bound of the early-out test
+
+RMP2_DEV float2 bc2(float s) { return make_float2(s, s); }
+RMP2_DEV float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+RMP2_DEV float fma_sat(float a, float b, float c) {                               // FFMA.SAT: clamp to [0, 1]
+  float y;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+
+// n = unit vectors obstacle -> link of the two pairs, d = distances, inv_d = 1/d.
+// S[i], g[i]: lane x accumulates the even spheres of the environment, lane y the odd ones.
+RMP2_DEV void obstacle_pair2(const float* __restrict__ p, float2 nx, float2 ny, float2 nz, float2 d, float2 inv_d,
+                             const float (&v)[3], const float (&a)[3], float vv, float2 (&S)[6],
+                             float2 (&g)[3]) {
+  const float2 xdot = __ffma2_rn(nx, bc2(v[0]), __ffma2_rn(ny, bc2(v[1]), __fmul2_rn(nz, bc2(v[2]))));
+  const float2 curv = __fmul2_rn(__ffma2_rn(neg2(xdot), xdot, bc2(vv)), inv_d);
+  const float2 negc = __ffma2_rn(neg2(nx), bc2(a[0]), __ffma2_rn(neg2(ny), bc2(a[1]), __ffma2_rn(neg2(nz), bc2(a[2]), neg2(curv))));
+  // xs = clamp((d - margin) / r, 0, 1)                                           rmp2.py:185-186, 170-174
+  const float2 xs = make_float2(fma_sat(d.x, p[SP_XA], p[SP_XB]), fma_sat(d.y, p[SP_XA], p[SP_XB]));
+  const float2 den1 = __ffma2_rn(xs, bc2(p[SP_D1A]), bc2(p[SP_D1B]));           // (x/s_e + eps_e) / scalar  rmp2.py:187
+  const float2 den2 = __ffma2_rn(xs, bc2(p[SP_D2A]), bc2(p[SP_D2B]));           // x/s_d + eps_d             rmp2.py:191
+  const float2 tv = __fmul2_rn(xdot, bc2(p[SP_K_VEL]));
+  const float2 ev = make_float2(fast_exp2(tv.x), fast_exp2(tv.y));               // 1/(1 - sigmoid) = 1 + ev  rmp2.py:190
+  const float2 den12 = __fmul2_rn(den1, den2);
+  const float2 Q = __ffma2_rn(den12, ev, den12);
+  const float2 q = make_float2(fast_rcp(Q.x), fast_rcp(Q.y));                    // 0 when ev overflowed: no metric, no force
+  const float2 w1 = __fmul2_rn(q, den2);                                          // (1-sig) scalar / (x/s_e + eps_e)
+  const float2 w2 = __fmul2_rn(q, den1);                                          // (1-sig) / (x/s_d + eps_d)
+  const float2 gt = __ffma2_rn(xs, bc2(p[SP_GT_A]), bc2(p[SP_GT_B]));           // x/r - 1, 0 beyond the radius
+  const float2 m = __fmul2_rn(w1, __fmul2_rn(gt, gt));                            // rmp2.py:172,194
+  const float2 tr = __fmul2_rn(xs, bc2(p[SP_K_REP]));
+  const float2 er = make_float2(fast_exp2(tr.x), fast_exp2(tr.y));               // rmp2.py:189
+  const float2 t = __fmul2_rn(w2, xdot);
+  const float2 ac = __ffma2_rn(bc2(p[SP_RGAIN]), er, __ffma2_rn(bc2(p[SP_NEG_DGAIN]), t, negc));   // xdd - c
+  const float2 h = __fmul2_rn(m, ac);
+  const float2 mx = __fmul2_rn(m, nx), my = __fmul2_rn(m, ny), mz = __fmul2_rn(m, nz);
+  S[0] = __ffma2_rn(mx, nx, S[0]);
+  S[1] = __ffma2_rn(mx, ny, S[1]);
+  S[2] = __ffma2_rn(mx, nz, S[2]);
+  S[3] = __ffma2_rn(my, ny, S[3]);
+  S[4] = __ffma2_rn(my, nz, S[4]);
+  S[5] = __ffma2_rn(mz, nz, S[5]);
+  g[0] = __ffma2_rn(h, nx, g[0]);
+  g[1] = __ffma2_rn(h, ny, g[1]);
+  g[2] = __ffma2_rn(h, nz, g[2]);
+}
+
 // scalar form used by rmp2_leaf_evaluate: x, xd -> xdd, M
 RMP2_DEV void obstacle_scalar(const float* __restrict__ p, float xin, float xdot, float& xdd, float& M) {
   const float x = fmaxf(xin - p[OA_MARGIN], 0.f);
