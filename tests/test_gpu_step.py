@@ -292,3 +292,95 @@ def test_joint_subset_pads_the_kernel_width(ns):
             oc.add_rmp(ons.JointDamping(accel_d_gain=1, metric_scalar=0.005, inertia=0.3))
             ref.append(oc.evaluate(torch.as_tensor(q[b]), torch.as_tensor(qd[b])).numpy())
         assert rel_err(got, np.stack(ref)).max() <= tol
+
+
+def _tree_with_obstacle_gains(ns_, fk, goal, n, tm_for, **gains):
+    """target attractor + joint damping + one ObstacleAvoidance leaf per collision frame with the given gains."""
+    base = dict(margin=0., damping_gain=50, damping_std_dev=0.04, damping_robustness_eps=0.01,
+                damping_velocity_gate_length_scale=0.01, repulsion_gain=800, repulsion_std_dev=0.01,
+                metric_modulation_radius=0.5, metric_scalar=1, metric_exploder_std_dev=0.02, metric_exploder_eps=0.001)
+    base.update(gains)
+    core = ns_.RmpCore()
+    core.add_rmp(S.target_attractor(ns_, fk, goal))
+    core.add_rmp(ns_.JointDamping(accel_d_gain=1, metric_scalar=0.005, inertia=0.3))
+    for frame in S.collision_frames(fk):
+        tm = ns_.chain_taskmaps([ns_.TaskmapByForwardKinematic(fk, frame), tm_for(frame)])
+        core.add_rmp(ns_.ObstacleAvoidance(taskmap=tm, name=f"oa_{frame}", **base))
+    return core
+
+
+@pytest.mark.parametrize("gains", [
+    dict(margin=0.05),
+    dict(margin=0.02, metric_modulation_radius=0.3, metric_scalar=2.5),
+    dict(metric_scalar=-0.5, repulsion_gain=-100.0),          # signs the reference accepts too
+    dict(damping_velocity_gate_length_scale=0.002),           # exp(xdot / l_v) overflows for receding pairs
+])
+def test_obstacle_leaf_parameter_variants(ns, gains):
+    """The packed pair loop folds margin, radius and metric_scalar into its coefficients on the host
+    (fill_sphere_row): non-default gains must still match the oracle, which evaluates rmp2.py:184-196 as written."""
+    n, B, O_ = 7, 512, 16
+    q, qd, goal = S.sample_panda_state(B, n, seed=77)
+    ofk = H.make_fkine(n, torch.float64)
+    frames = S.collision_frames(ofk)
+    origins = torch.func.vmap(lambda qq: H.frame_origins(ofk, qq, frames))(torch.as_tensor(q).double()).numpy()
+    sph = S.sample_spheres(B, O_, 78, origins)
+    fk = product_fkine(ns, n)
+    core = _tree_with_obstacle_gains(ns, fk, goal[0], n, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance(), **gains)
+    dev = torch.device("cuda")
+    got = core.evaluate(torch.as_tensor(q, device=dev), torch.as_tensor(qd, device=dev),
+                        goals=torch.as_tensor(goal, device=dev), spheres=torch.as_tensor(sph, device=dev)).cpu().numpy()
+
+    def oracle(dtype, combine=False):
+        ons = H.namespace(dtype)
+        fko = H.make_fkine(n, dtype)
+
+        def one(q1, qd1, goal1, s):
+            q1, qd1, goal1, s = q1.to(dtype), qd1.to(dtype), goal1.to(dtype), s.to(dtype)
+            org = H.frame_origins(fko, q1, frames)
+            r = org[:, None, :] - s[None, :, :3]
+            on_obst = s[None, :, :3] + s[None, :, 3:4] * r / torch.linalg.norm(r, dim=-1, keepdim=True)
+            on_link = org[:, None, :].expand_as(on_obst)
+            idx = {fr: i for i, fr in enumerate(frames)}
+            oc = _tree_with_obstacle_gains(ons, fko, goal1, n,
+                                           lambda fr: ons.TaskmapJointFrame4x4ToDistance(on_link[idx[fr]], on_obst[idx[fr]]),
+                                           **gains)
+            return oc.combine(q1, qd1)[1] if combine else oc.evaluate(q1, qd1)
+
+        return torch.func.vmap(one)(torch.as_tensor(q), torch.as_tensor(qd), torch.as_tensor(goal),
+                                    torch.as_tensor(sph)).numpy()
+
+    stats = assert_parity(got, oracle(torch.float32), oracle(torch.float64), oracle(torch.float64, combine=True), n,
+                          label=f"obstacle gains {gains}")
+    print(gains, stats)
+
+
+def test_inert_and_degenerate_spheres(ns):
+    """metric_scalar = 0 and spheres beyond every metric radius contribute exactly nothing (bitwise);
+    a frame origin inside a sphere or exactly on its centre stays finite."""
+    n, B, O_ = 7, 256, 12
+    q, qd, goal = S.sample_panda_state(B, n, seed=91)
+    fk = product_fkine(ns, n)
+    dev = torch.device("cuda")
+    tq, tqd, tg = (torch.as_tensor(a, device=dev) for a in (q, qd, goal))
+    tm_for = lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance()
+    ofk = H.make_fkine(n, torch.float64)
+    frames = S.collision_frames(ofk)
+    origins = torch.func.vmap(lambda qq: H.frame_origins(ofk, qq, frames))(torch.as_tensor(q).double()).numpy()
+    near = torch.as_tensor(S.sample_spheres(B, O_, 92, origins), device=dev)
+    far = near.clone()
+    far[..., :3] += 50.0
+    plain = ns.RmpCore()
+    plain.add_rmp(S.target_attractor(ns, fk, goal[0]))
+    plain.add_rmp(ns.JointDamping(accel_d_gain=1, metric_scalar=0.005, inertia=0.3))
+    want = plain.evaluate(tq, tqd, goals=tg).cpu().numpy()
+    inert = _tree_with_obstacle_gains(ns, fk, goal[0], n, tm_for, metric_scalar=0.0)
+    np.testing.assert_array_equal(inert.evaluate(tq, tqd, goals=tg, spheres=near).cpu().numpy(), want)
+    live = _tree_with_obstacle_gains(ns, fk, goal[0], n, tm_for)
+    np.testing.assert_array_equal(live.evaluate(tq, tqd, goals=tg, spheres=far).cpu().numpy(), want)
+    # sphere 0 swallows the last collision frame's origin, sphere 1 is centred exactly on the first one's
+    bad = near.clone()
+    bad[:, 0, :3] = torch.as_tensor(origins[:, -1], device=dev, dtype=torch.float32) + 0.01
+    bad[:, 0, 3] = 0.05
+    bad[:, 1, :3] = torch.as_tensor(origins[:, 0], device=dev, dtype=torch.float32)
+    out = live.evaluate(tq, tqd, goals=tg, spheres=bad)
+    assert torch.isfinite(out).all()
