@@ -468,48 +468,16 @@ int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* 
 // ------------------------------------------------------------------------------------ step launch
 namespace {
 
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                        CUtensorMapFloatOOBfill);
-
-PFN_tmapEncodeTiled get_encode_fn() {
-  static PFN_tmapEncodeTiled fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      p = nullptr;
-    return (PFN_tmapEncodeTiled)p;
-  }();
-  return fn;
-}
-
 int pick_block(long long B) {
   return (B >= 148LL * 4 * 128) ? 128 : (B >= 148LL * 4 * 64 ? 64 : 32);
 }
 
+// The staged (TMA bulk-copy) sphere path needs 16-byte aligned rows and two stages of E rows in shared memory.
 bool tma_eligible(const rmp2_tree* tree, const StepArgs& A) {
   const int O = A.n_spheres;
   if (getenv("RMP2_DISABLE_TMA")) return false;
   const size_t smem = rmp2_spheres_smem(tree->sph, O, true);
-  return O > 0 && (O % 8) == 0 && A.spheres != nullptr && ((uintptr_t)A.spheres % 16) == 0 &&
-         A.B < (1LL << 31) && smem <= 200 * 1024;
-}
-
-int encode_sphere_map(const rmp2_tree* tree, const StepArgs& A, CUtensorMap* tmap) {
-  PFN_tmapEncodeTiled enc = get_encode_fn();
-  if (!enc) return fail(RMP2_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-  const int O = A.n_spheres;
-  const cuuint64_t gdim[2] = {(cuuint64_t)O * 4, (cuuint64_t)A.B};
-  const cuuint64_t gstride[1] = {(cuuint64_t)O * 16};
-  const cuuint32_t box[2] = {32, (cuuint32_t)tree->sph.envs_per_block};   // 8 spheres x E environments
-  const cuuint32_t estride[2] = {1, 1};
-  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(A.spheres), gdim, gstride, box,
-                   estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(RMP2_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-  return RMP2_OK;
+  return O > 0 && A.spheres != nullptr && ((uintptr_t)A.spheres % 16) == 0 && smem <= 96 * 1024;
 }
 
 struct ScopedClock {               // brackets one launch with events when profiling is on
@@ -580,15 +548,9 @@ int launch_chunk(rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
     }
     if (e != cudaSuccess) return cuda_fail(e, "rmp2_frames_kernel launch");
     const bool use_tma = tma_eligible(tree, A);
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
-    if (use_tma) {
-      int rc = encode_sphere_map(tree, A, &tmap);
-      if (rc != RMP2_OK) return rc;
-    }
     {
       ScopedClock clk(tree, 1, stream);
-      e = rmp2_launch_spheres(tree->sph, A, &tmap, use_tma, stream);
+      e = rmp2_launch_spheres(tree->sph, A, use_tma, stream);
     }
     if (e != cudaSuccess) return cuda_fail(e, "rmp2_spheres_kernel launch");
     g_launches.fetch_add(2);
@@ -889,7 +851,7 @@ int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_sphere
   bool use_tma = false;
   if (which == 1) {
     if (tree->tab.n_sphere_slots == 0) return fail(RMP2_ERR_INVALID, "tree has no sphere-obstacle leaves");
-    use_tma = n_spheres > 0 && n_spheres % 8 == 0;
+    use_tma = n_spheres > 0 && rmp2_spheres_smem(tree->sph, n_spheres, true) <= 96 * 1024;
     block = ((tree->sph.envs_per_block * tree->sph.n_slots + 31) / 32) * 32;
     smem = rmp2_spheres_smem(tree->sph, n_spheres, use_tma);
   }

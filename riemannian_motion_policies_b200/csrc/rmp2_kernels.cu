@@ -5,12 +5,12 @@
 //
 //   rmp2_frames_kernel<N>    thread per environment: kinematic chain -> origin position, velocity and
 //                            Jdot*qd of every frame that carries a sphere-obstacle leaf  (48 B records)
-//   rmp2_spheres_kernel      thread per (environment, obstacle leaf): the O(frames x spheres) pair loop.
-//                            The spheres of the E environments of a block are staged into shared memory
-//                            by TMA 2-D tiled bulk copies (cp.async.bulk.tensor, 128-byte swizzle,
-//                            mbarrier completion): HBM is read once in full 128-byte lines and the
-//                            LDS.128 row reads are bank-conflict free.  Small code, ~60 registers,
-//                            high occupancy -- this kernel carries >= 60 % of the instructions.
+//   rmp2_spheres_kernel      thread per (environment, obstacle leaf): the O(frames x spheres) pair loop,
+//                            two spheres per step in packed f32x2 arithmetic (FFMA2).  The sphere rows
+//                            of the E environments of a block are staged into shared memory by 1-D
+//                            TMA bulk copies (cp.async.bulk, mbarrier completion) at an odd pitch: HBM
+//                            is read once in whole rows and the LDS.128 reads are bank-conflict free
+//                            with immediate offsets.  This kernel carries >= 50 % of the step.
 //                            Output: per (env, leaf) the 3x3 metric sum S and the force sum g, written
 //                            over the input record.
 //   rmp2_step_kernel<N>      thread per environment: chain again (cheap), target leaves, pullback of every
@@ -51,13 +51,6 @@ RMP2_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   } while (!done);
-}
-
-RMP2_DEV void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, int32_t x, int32_t y, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
-      : "memory");
 }
 
 // read-only 16-byte shared-memory load the compiler may schedule freely (see rmp2_spheres_kernel)
@@ -150,21 +143,36 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 }
 
 // ------------------------------------------------------------------------------ spheres kernel
-// Thread t of a block <-> (obstacle-leaf slot t / E, local environment t % E); the block owns E
-// consecutive environments, so record loads/stores are contiguous across lanes and every quarter
-// warp reads 8 distinct swizzled rows of the staged spheres.  Staged layout: box b (8 spheres) = E rows of 128 B, box stride padded to
-// 1024 B so that the 128-byte TMA swizzle (16-byte chunk index XOR row & 7) is row-relative.
+// Thread t of a block <-> (obstacle-leaf slot t / E, local environment t % E); the block owns a tile of
+// E consecutive environments, so record loads/stores are contiguous across lanes.
+//
+// Staging (kTma): the spheres of one environment are one contiguous row of 16*O bytes in HBM; lane e < E
+// copies row e of the tile with one 1-D bulk copy (cp.async.bulk -- the TMA unit, completion on an
+// mbarrier by transaction bytes) into shared memory at a pitch of 16*O + 16 bytes.  The odd pitch is
+// what a swizzle would buy: the LDS.128 of 8 consecutive lanes (environments) lands in 8 distinct
+// 16-byte bank groups, and a thread's sphere o sits at row + 16*o -- an immediate offset, so the pair
+// loop has no per-thread address arithmetic (ALU instructions cost FP32 lane time on this machine).
+// One tile per block on purpose: a persistent, double-buffered variant of this kernel measured 10 %
+// SLOWER (1.09 vs 0.99 ms, config 4) -- its resident blocks run in lockstep, all warps of an SM want the
+// MUFU pipe, then the FMA pipe, at the same time; short blocks that start whenever another one retires
+// keep the warps of an SM spread over the phases of the loop.
 #ifndef RMP2_SPHERES_MIN_BLOCKS
 #define RMP2_SPHERES_MIN_BLOCKS 5     // resident blocks per SM the register allocation aims at (<= 102 registers)
 #endif
 #ifndef RMP2_SPHERES_STEPS_PER_TRIP
-#define RMP2_SPHERES_STEPS_PER_TRIP 4 // packed (two-sphere) steps per loop trip of the TMA path: 2 or 4
+#define RMP2_SPHERES_STEPS_PER_TRIP 4 // packed (two-sphere) steps per loop trip
 #endif
+
+RMP2_DEV void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 template <bool kTma, bool kSkip>
 __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_SPHERES_MIN_BLOCKS)
-    rmp2_spheres_kernel(const __grid_constant__ SphereTables ST, const __grid_constant__ StepArgs A,
-                        const __grid_constant__ CUtensorMap tmap) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
+    rmp2_spheres_kernel(const __grid_constant__ SphereTables ST, const __grid_constant__ StepArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int L = ST.n_slots, E = ST.envs_per_block;
   const int t = threadIdx.x;
   const int slot = t / E, e_local = t - slot * E;   // consecutive lanes = consecutive environments
@@ -173,40 +181,44 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_SPHERES_MIN_BLOCKS)
   const int O = A.n_spheres;
   const bool active = (slot < L) && (env < A.B);
 
-  uint32_t tiles = 0;
+  uint32_t row = 0;                                 // shared-memory address of this thread's sphere row
   if (kTma) {
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t box_stride = ((uint32_t)E * 128u + 1023u) & ~1023u;
-    const int nbox = O >> 3;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(base + (size_t)nbox * box_stride);
-    tiles = smem_u32(base);
+    const uint32_t row_bytes = (uint32_t)O * 16u, pitch = row_bytes + 16u;
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + (size_t)E * pitch);
+    const long long rows = (A.B - env0 < E) ? (A.B - env0) : E;
     if (t == 0) {
       mbar_init(bar, 1);
-      mbar_expect_tx(bar, (uint32_t)nbox * (uint32_t)E * 128u);
-      for (int b = 0; b < nbox; ++b) tma_load_2d(tiles + b * box_stride, &tmap, b * 32, (int32_t)env0, bar);
+      mbar_expect_tx(bar, (uint32_t)rows * row_bytes);
     }
-    __syncthreads();                              // barrier initialised before anyone polls it
+    __syncthreads();                              // barrier initialised before anyone copies or polls
+    for (int e = t; e < rows; e += blockDim.x)    // lane e copies row e (one warp's worth for E <= 32)
+      bulk_load_1d(smem_u32(base) + (uint32_t)e * pitch,
+                   reinterpret_cast<const unsigned char*>(A.spheres) + (size_t)(env0 + e) * row_bytes, row_bytes, bar);
     if (!active) return;
-    mbar_wait(bar, 0);
-    tiles += (uint32_t)e_local * 128u;            // this thread's 128-byte row of box 0
-    // the sphere loads below are plain (non-volatile) asm so that the scheduler may hoist them over
-    // arithmetic; making their address depend on this statement keeps them after the wait
-    asm volatile("" : "+r"(tiles) : : "memory");
+    row = smem_u32(base) + (uint32_t)e_local * pitch;
   } else {
     if (!active) return;
   }
 
-  // this thread's frame record and leaf parameters
+  // this thread's frame record and leaf parameters (loads in flight while the rows land)
   float* rec = A.rec + (size_t)slot * A.B + env;
   const size_t fstride = (size_t)L * A.B;
   const float px = rec[0 * fstride], py = rec[1 * fstride], pz = rec[2 * fstride];
   const float v[3] = {rec[3 * fstride], rec[4 * fstride], rec[5 * fstride]};
   const float a[3] = {rec[6 * fstride], rec[7 * fstride], rec[8 * fstride]};
   const float vv = rec[9 * fstride];
-  float p[RMP2_LEAF_PARAMS];
+  float p[SP_COUNT];
 #pragma unroll
-  for (int i = 0; i < RMP2_LEAF_PARAMS; ++i) p[i] = ST.p[slot][i];
-
+  for (int i = 0; i < SP_COUNT; ++i) p[i] = ST.p[slot][i];
+  if (kTma) {
+    uint64_t* bar = reinterpret_cast<uint64_t*>(((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127)) +
+                                                (size_t)E * ((size_t)O * 16 + 16));
+    mbar_wait(bar, 0);
+    // the sphere loads below are plain (non-volatile) asm so that the scheduler may hoist them over
+    // arithmetic; making their address depend on this statement keeps them after the wait
+    asm volatile("" : "+r"(row) : : "memory");
+  }
   // Two spheres per step in packed f32x2 arithmetic: lane x of every accumulator takes the even
   // spheres of the environment, lane y the odd ones (fixed assignment -> the early-out variant adds
   // the same terms to the same accumulators in the same order and stays bit-identical).
@@ -225,55 +237,23 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_SPHERES_MIN_BLOCKS)
     const float2 inv_dc = make_float2(fast_rsqrt(dc2.x), fast_rsqrt(dc2.y));
     const float2 sd = make_float2(fmaf(dc2.x, inv_dc.x, -s0.w), fmaf(dc2.y, inv_dc.y, -s1.w));   // signed surface distance
     const float2 sgn = make_float2(copysignf(inv_dc.x, sd.x), copysignf(inv_dc.y, sd.y));       // inside: normal flips
-    const float2 d = make_float2(fmaxf(fabsf(sd.x), 1e-12f), fmaxf(fabsf(sd.y), 1e-12f));
+    const float2 d = make_float2(fabsf(sd.x) + 1e-12f, fabsf(sd.y) + 1e-12f);                   // > 0 (FADD, not FMNMX)
     const float2 inv_d = make_float2(fast_rcp(d.x), fast_rcp(d.y));
     obstacle_pair2(p, __fmul2_rn(rx, sgn), __fmul2_rn(ry, sgn), __fmul2_rn(rz, sgn), d, inv_d, v, a, vv, S, g);
   };
   // a sphere that contributes exactly zero (beyond every metric radius; d ~ 1e15 keeps all terms finite)
   const float4 far_away = make_float4(px + 1e15f, py, pz, 0.f);
-  const uint32_t x7 = ((uint32_t)e_local & 7u) << 4;
-  const uint32_t box_stride = ((uint32_t)E * 128u + 1023u) & ~1023u;
   const float4* gs = reinterpret_cast<const float4*>(A.spheres) + (size_t)env * O;
-  auto load_sphere = [&](int o) -> float4 {
-    float4 sp;
-    if (kTma) {
-      sp = lds128(tiles + (uint32_t)(o >> 3) * box_stride + ((((uint32_t)o & 7u) << 4) ^ x7));
-    } else {
-      sp = __ldg(gs + o);
-    }
-    return sp;
-  };
+  auto load_sphere = [&](int o) -> float4 { return kTma ? lds128(row + (uint32_t)o * 16u) : __ldg(gs + o); };
   if (!kSkip) {
-    if (kTma) {
-      // 8 swizzled chunk addresses of this thread's row (per-thread, loop invariant) plus the
-      // warp-uniform box offset: LDS.128 [R + UR], no per-thread address arithmetic in the loop
-      constexpr int kStepsPerTrip = RMP2_SPHERES_STEPS_PER_TRIP;
-      uint32_t addr[8];
+    constexpr int kStep = 2 * RMP2_SPHERES_STEPS_PER_TRIP;      // spheres per loop trip
+    int o = 0;
+    for (; o + kStep <= O; o += kStep) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) addr[c] = tiles + ((((uint32_t)c) << 4) ^ x7);
-      uint32_t box_off = 0;
-      for (int b = 0; b < (O >> 3); ++b, box_off += box_stride) {
-        if (kStepsPerTrip == 4) {
-#pragma unroll
-          for (int c2 = 0; c2 < 8; c2 += 2) two_spheres(lds128(addr[c2] + box_off), lds128(addr[c2 + 1] + box_off));
-        } else {
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-#pragma unroll
-            for (int c2 = 0; c2 < 4; c2 += 2) {
-              const uint32_t ad0 = (h == 0) ? addr[c2] : addr[4 + c2];
-              const uint32_t ad1 = (h == 0) ? addr[c2 + 1] : addr[5 + c2];
-              two_spheres(lds128(ad0 + box_off), lds128(ad1 + box_off));
-            }
-          }
-        }
-      }
-    } else {
-      int o = 0;
-#pragma unroll 2
-      for (; o + 1 < O; o += 2) two_spheres(load_sphere(o), load_sphere(o + 1));
-      if (o < O) two_spheres(load_sphere(o), far_away);
+      for (int k = 0; k < kStep; k += 2) two_spheres(load_sphere(o + k), load_sphere(o + k + 1));
     }
+    for (; o + 1 < O; o += 2) two_spheres(load_sphere(o), load_sphere(o + 1));
+    if (o < O) two_spheres(load_sphere(o), far_away);
   } else {
     // Exact early-out (reference: rmp2.py:194 -- a pair beyond the metric radius has M = 0 and adds
     // exactly nothing): first a cheap squared-distance test of every sphere into two bit masks (even
@@ -879,29 +859,26 @@ cudaError_t rmp2_launch_frames(const StepTables& T, const StepArgs& A, int block
 
 size_t rmp2_spheres_smem(const SphereTables& ST, int n_spheres, bool use_tma) {
   if (!use_tma) return 0;
-  const size_t box_stride = ((size_t)ST.envs_per_block * 128 + 1023) & ~size_t(1023);
-  return 1024 + (size_t)(n_spheres / 8) * box_stride + 16;
+  const size_t pitch = (size_t)n_spheres * 16 + 16;
+  return 128 + (size_t)ST.envs_per_block * pitch + sizeof(uint64_t);
 }
 
-cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, const CUtensorMap* tmap, bool use_tma,
-                                cudaStream_t stream) {
+cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, bool use_tma, cudaStream_t stream) {
   const long long blocks = (A.B + ST.envs_per_block - 1) / ST.envs_per_block;
   if (blocks <= 0) return cudaSuccess;
+  if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
   const int threads = ((ST.envs_per_block * ST.n_slots + 31) / 32) * 32;
   const size_t smem = rmp2_spheres_smem(ST, A.n_spheres, use_tma);
-  CUtensorMap dummy;
-  memset(&dummy, 0, sizeof(dummy));
-  const CUtensorMap& tm = use_tma ? *tmap : dummy;
   const unsigned nb = (unsigned)blocks;
   if (use_tma) {
     const void* fn = A.early_out ? (const void*)rmp2_spheres_kernel<true, true> : (const void*)rmp2_spheres_kernel<true, false>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (A.early_out) rmp2_spheres_kernel<true, true><<<nb, threads, smem, stream>>>(ST, A, tm);
-    else rmp2_spheres_kernel<true, false><<<nb, threads, smem, stream>>>(ST, A, tm);
+    if (A.early_out) rmp2_spheres_kernel<true, true><<<nb, threads, smem, stream>>>(ST, A);
+    else rmp2_spheres_kernel<true, false><<<nb, threads, smem, stream>>>(ST, A);
   } else {
-    if (A.early_out) rmp2_spheres_kernel<false, true><<<nb, threads, 0, stream>>>(ST, A, tm);
-    else rmp2_spheres_kernel<false, false><<<nb, threads, 0, stream>>>(ST, A, tm);
+    if (A.early_out) rmp2_spheres_kernel<false, true><<<nb, threads, 0, stream>>>(ST, A);
+    else rmp2_spheres_kernel<false, false><<<nb, threads, 0, stream>>>(ST, A);
   }
   return cudaGetLastError();
 }

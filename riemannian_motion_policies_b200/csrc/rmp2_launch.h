@@ -16,8 +16,7 @@ size_t rmp2_step_smem(const StepTables& T, int block);
 
 cudaError_t rmp2_launch_frames(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);
 size_t rmp2_spheres_smem(const SphereTables& ST, int n_spheres, bool use_tma);
-cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, const CUtensorMap* tmap, bool use_tma,
-                                cudaStream_t stream);
+cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, bool use_tma, cudaStream_t stream);
 cudaError_t rmp2_launch_step(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);
 cudaError_t rmp2_launch_resolve(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);
 // which: 0 frames, 1 spheres, 2 step (fused resolve), 3 step (split), 4 resolve

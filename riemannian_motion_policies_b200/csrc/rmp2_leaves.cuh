@@ -232,6 +232,7 @@ RMP2_DEV void obstacle_pair(const float* __restrict__ p, float nx, float ny, flo
 #define SP_RGAIN 10
 #define SP_NEG_DGAIN 11
 #define SP_REACH 12       // (r + margin) * (1 + 1e-5): conservative bound of the early-out test
+#define SP_COUNT 13
 
 RMP2_DEV float2 bc2(float s) { return make_float2(s, s); }
 RMP2_DEV float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
