@@ -131,35 +131,32 @@ template <int N>
 RMP2_DEV void pullback(const float* __restrict__ cols, int stride, const float (&pk)[3], uint32_t anc,
                        uint32_t prismatic, const float (&S)[6], const float (&g)[3],
                        float (&Msym)[N * (N + 1) / 2], float (&f)[N]) {
-  float col[N][3], u[N][3];
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    col[j][0] = col[j][1] = col[j][2] = 0.f;
-    u[j][0] = u[j][1] = u[j][2] = 0.f;
-    if (anc & (1u << j)) {                       // warp-uniform
-      const float z[3] = {cols[(j * 6 + 0) * stride], cols[(j * 6 + 1) * stride], cols[(j * 6 + 2) * stride]};
-      if (prismatic & (1u << j)) {
-        col[j][0] = z[0];
-        col[j][1] = z[1];
-        col[j][2] = z[2];
-      } else {
-        const float r[3] = {pk[0] - cols[(j * 6 + 3) * stride], pk[1] - cols[(j * 6 + 4) * stride],
-                            pk[2] - cols[(j * 6 + 5) * stride]};
-        cross3(z, r, col[j]);
-      }
-      u[j][0] = fmaf(S[0], col[j][0], fmaf(S[1], col[j][1], S[2] * col[j][2]));
-      u[j][1] = fmaf(S[1], col[j][0], fmaf(S[3], col[j][1], S[4] * col[j][2]));
-      u[j][2] = fmaf(S[2], col[j][0], fmaf(S[4], col[j][1], S[5] * col[j][2]));
-      f[j] = fmaf(col[j][0], g[0], fmaf(col[j][1], g[1], fmaf(col[j][2], g[2], f[j])));
-    }
-  }
+  // One pass over the joint columns: column i is built, multiplied by S (u_i = S J_i, kept for the rows
+  // below) and contracted with every u_j, j <= i, at once -- only u stays live, not the columns.
+  float u[N][3];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    if (anc & (1u << i)) {
+    u[i][0] = u[i][1] = u[i][2] = 0.f;
+    if (anc & (1u << i)) {                       // warp-uniform
+      float col[3];
+      const float z[3] = {cols[(i * 6 + 0) * stride], cols[(i * 6 + 1) * stride], cols[(i * 6 + 2) * stride]};
+      if (prismatic & (1u << i)) {
+        col[0] = z[0];
+        col[1] = z[1];
+        col[2] = z[2];
+      } else {
+        const float r[3] = {pk[0] - cols[(i * 6 + 3) * stride], pk[1] - cols[(i * 6 + 4) * stride],
+                            pk[2] - cols[(i * 6 + 5) * stride]};
+        cross3(z, r, col);
+      }
+      u[i][0] = fmaf(S[0], col[0], fmaf(S[1], col[1], S[2] * col[2]));
+      u[i][1] = fmaf(S[1], col[0], fmaf(S[3], col[1], S[4] * col[2]));
+      u[i][2] = fmaf(S[2], col[0], fmaf(S[4], col[1], S[5] * col[2]));
+      f[i] = fmaf(col[0], g[0], fmaf(col[1], g[1], fmaf(col[2], g[2], f[i])));
 #pragma unroll
-      for (int j = 0; j <= i; ++j) {
+      for (int j = 0; j <= i; ++j) {             // u_j = 0 for joints off the path
         const int idx = i * (i + 1) / 2 + j;
-        Msym[idx] = fmaf(col[i][0], u[j][0], fmaf(col[i][1], u[j][1], fmaf(col[i][2], u[j][2], Msym[idx])));
+        Msym[idx] = fmaf(col[0], u[j][0], fmaf(col[1], u[j][1], fmaf(col[2], u[j][2], Msym[idx])));
       }
     }
   }
