@@ -543,9 +543,9 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, kSplit ? RMP2_SPLIT_MIN_BL
     return;
   }
   if (T.precondition)                            // same arithmetic as the stand-alone resolve kernel
-    resolve_pinv<N, true>(M, f, T.rcond, qdd);
+    resolve_pinv<N, true>(M, f, n, T.rcond, qdd);
   else
-    resolve_pinv<N, false>(M, f, T.rcond, qdd);
+    resolve_pinv<N, false>(M, f, n, T.rcond, qdd);
   finish_step<N>(A, n, e, active, rollout, q, qd, qdd);
 }
 
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_RESOLVE_MIN_BLOCKS(N)
     for (int j = 0; j < N; ++j) M[i][j] = __ldg(in + (size_t)(i * N + j) * A.B);
 #pragma unroll
   for (int i = 0; i < N; ++i) f[i] = __ldg(in + (size_t)(N * N + i) * A.B);
-  resolve_pinv<N, kQr>(M, f, R.rcond, qdd);
+  resolve_pinv<N, kQr>(M, f, n, R.rcond, qdd);
   float q[N], qd[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
