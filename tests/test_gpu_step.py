@@ -384,3 +384,46 @@ def test_inert_and_degenerate_spheres(ns):
     bad[:, 1, :3] = torch.as_tensor(origins[:, 0], device=dev, dtype=torch.float32)
     out = live.evaluate(tq, tqd, goals=tg, spheres=bad)
     assert torch.isfinite(out).all()
+
+
+def test_direct_solve_and_jacobi_lanes_mix(ns):
+    """Trees with an isotropic metric leaf solve by plain QR where the matrix is provably clear of the pinv
+    cutoff and fall back to the Jacobi sweeps otherwise, lane by lane.  A weak isotropic weight puts
+    sigma_min/sigma_max ~ 1e-4 (no truncation, but around the rigorous test's threshold), so both kinds of
+    lanes share warps: every environment must match the oracle, and must not depend on its neighbours."""
+    from oracle import rmp_oracle as O
+    n, B = 7, 512
+    q, qd, goal = S.sample_panda_state(B, n, seed=55)
+    fk = product_fkine(ns, n)
+
+    def build(ns_, fk_, g):
+        core = ns_.RmpCore()
+        core.add_rmp(ns_.TargetPolicy(alpha=0.1, beta=1, c=0.1, goal=g, name="target", taskmap=S.ee_position_taskmap(ns_, fk_)))
+        core.add_rmp(ns_.ConfigurationSpaceBiasing(gamma_p=0.01, gamma_d=0.1, q0=S.NULLSPACE_Q0_9[:n], name="bias", w=1e-4))
+        return core
+
+    dev = torch.device("cuda")
+    core = build(ns, fk, goal[0])
+    tq, tqd, tg = (torch.as_tensor(a, device=dev) for a in (q, qd, goal))
+    got = core.evaluate(tq, tqd, goals=tg).cpu().numpy()
+
+    def oracle(dtype, combine=False):
+        ons = H.namespace(dtype)
+        fko = H.make_fkine(n, dtype)
+
+        def one(q1, qd1, g1):
+            oc = build(ons, fko, g1.to(dtype))
+            return oc.combine(q1.to(dtype), qd1.to(dtype))[1] if combine else oc.evaluate(q1.to(dtype), qd1.to(dtype))
+
+        return torch.func.vmap(one)(torch.as_tensor(q), torch.as_tensor(qd), torch.as_tensor(goal)).numpy()
+
+    M64 = oracle(torch.float64, combine=True)
+    s = np.linalg.svd(M64, compute_uv=False)
+    ratio = s[:, -1] / s[:, 0]
+    assert (ratio > 4 * 10 * n * np.finfo(np.float32).eps).all()          # nothing is truncated in this batch
+    assert (ratio < 2.4e-4).any() and (ratio > 2.4e-4).any()              # ... but it straddles the direct-solve test
+    stats = assert_parity(got, oracle(torch.float32), oracle(torch.float64), M64, n, label="direct/jacobi mix")
+    print(stats, "sigma ratio range", ratio.min(), ratio.max())
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(dev)
+    again = core.evaluate(tq[perm], tqd[perm], goals=tg[perm]).cpu().numpy()
+    np.testing.assert_array_equal(again, got[perm.cpu().numpy()])
