@@ -35,6 +35,13 @@ WORKLOAD = {
 }
 DEFAULT_ENVS = {2: 1 << 20, 3: 1 << 20, 4: 1 << 20, 5: 1 << 20}
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # analytic, at clocks.max.sm
+# The pair loop's real bound (profiles/r1_pipe_peaks.json): FP32 and ALU-pipe instructions
+# share lane time on a B200 SM (128 lanes/clk), MUFU (16/clk/SM) runs underneath.  Thread-level operations
+# per (frame, sphere) pair, counted from the SASS of rmp2_spheres_kernel's unrolled loop:
+LANE_OPS_PER_PAIR = 49.0        # 46 FP32 (41 packed halves + 5 scalar) + 3 ALU
+MUFU_PER_PAIR = 5.0
+LANE_PEAK_TOPS = 148 * 128 * 1.965e9 / 1e12
+MUFU_PEAK_TOPS = 148 * 16 * 1.965e9 / 1e12
 
 
 def measured_peaks():
@@ -201,10 +208,23 @@ class CpuReference:
         self.pool.join()
 
 
-def cpu_reference_throughput(config, n, cores, envs_per_core, n_spheres):
+def cpu_reference_throughput(config, n, cores, envs_per_core, n_spheres, budget_s=20.0):
+    """Bounded CPU sample: two warm-up rounds (Pool() returns before the workers have imported torch, so the
+    first maps still pay for it), then up to five measured rounds within `budget_s`; -> (median env-steps/s,
+    environments measured, seconds measured)."""
     ref = CpuReference(config, n, cores, n_spheres)
     try:
-        return ref.step(envs_per_core)
+        for _ in range(2):
+            ref.pool.map(_cpu_worker, [(7 + i, 1) for i in range(2 * cores)], chunksize=1)
+        values, total, wall, t0 = [], 0, 0.0, time.perf_counter()
+        for _ in range(5):
+            v, envs, w = ref.step(envs_per_core)
+            values.append(v)
+            total += envs
+            wall += w
+            if time.perf_counter() - t0 > budget_s:
+                break
+        return float(np.median(values)), total, wall
     finally:
         ref.close()
 
@@ -412,10 +432,12 @@ def run_b200_arm(args):
 
     if rank == 0 and not args.skip_checks and world == 1:
         cores = min(host_cores(), 64)
-        v, total, slowest = cpu_reference_throughput(config, n, cores, args.envs_per_core, O_)
+        per_core = max(args.envs_per_core, 24)
+        v, total, wall = cpu_reference_throughput(config, n, cores, per_core, O_)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{total} envs of the same workload, {cores} processes x {args.envs_per_core} envs, "
-                                  f"oracle port run one env per call ({slowest:.1f} s)"}
+                        "sample": f"{total} envs of the same workload in rounds of {cores} processes x {per_core} envs "
+                                  f"(median round, {wall:.1f} s measured after warm-up), oracle port run one env per "
+                                  f"call like the reference"}
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -446,6 +468,25 @@ def run_b200_arm(args):
                     if kname.startswith(f"rmp2_{dom}_kernel"):
                         traffic = kv["dram_bytes_read"] + kv["dram_bytes_write"]
         dom_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
+        lanes = None
+        if O_:
+            pairs = float(B) * O_ * n_slots
+            lane_tops = pairs * LANE_OPS_PER_PAIR / (dom_ms * 1e-3) / 1e12
+            mufu_tops = pairs * MUFU_PER_PAIR / (dom_ms * 1e-3) / 1e12
+            pipe = None
+            ppath = os.path.join(ROOT, "profiles", "r1_pipe_peaks.json")
+            if os.path.exists(ppath):
+                with open(ppath) as fh:
+                    pj = json.load(fh)
+                pipe = {"ffma2_fma_per_clk_per_sm": pj.get("ffma2_fma_per_clk_per_sm"),
+                        "ffma_per_clk_per_sm": pj.get("ffma_per_clk_per_sm"),
+                        "mufu_per_clk_per_sm": (pj.get("mufu_per_clk_per_sm") or {}).get("ex2")}
+            lanes = {"bound": "fp32+alu lane time", "lane_ops_per_pair": LANE_OPS_PER_PAIR, "mufu_per_pair": MUFU_PER_PAIR,
+                     "achieved_tera_lane_ops": lane_tops, "peak": LANE_PEAK_TOPS, "frac": lane_tops / LANE_PEAK_TOPS,
+                     "mufu_frac": mufu_tops / MUFU_PEAK_TOPS, "measured_pipe_rates": pipe,
+                     "note": "executed (not algorithmic) thread-level FP32+ALU operations of the pair loop over "
+                             "148 x 128 lanes x f_SM; ALU-pipe instructions cost FP32 lane time on B200 "
+                             "(tools/pipe_peaks.cu), so this, not the flop count, is what the kernel saturates"}
         dom_tflops = dom_flops / (dom_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -467,7 +508,8 @@ def run_b200_arm(args):
                               "whole_step": {"achieved": tflops, "frac": tflops / FP32_PEAK_TFLOPS,
                                              "flops_per_env_step": FLOPS_PER_ENV[config],
                                              "hbm_gbs": gbs, "bytes_per_env_step": BYTES_PER_ENV[config]},
-                              "peak_source": "analytic 148 SM x 128 lanes x 2 x 1.965 GHz"},
+                              "peak_source": "analytic 148 SM x 128 lanes x 2 x 1.965 GHz",
+                              "lanes": lanes},
             "kernel_ms": {k: {"ms_per_step": v[0] / args.steps, "launches": int(v[1])} for k, v in kernel_ms.items()},
             "per_gpu_value": per_gpu, "gpu_launches": int(launches), "kernel": info, "clocks": clocks.summary(),
             "early_out": early, "e2e": e2e, "cpu_baseline": cpu_baseline, "parity": parity,

@@ -1,8 +1,13 @@
 """Turn an .ncu-rep (ncu --set full) and a launch list (ncu --metrics gpu__time_duration.sum --csv) into the
 markdown summary committed under profiles/.  Runs in the build container (no GPU needed).
 
-    python tools/summarize_ncu.py gpurun_out/prof_r1_v4.ncu-rep gpurun_out/launches_r1.csv profiles/r1_ncu_summary.md "<command>"
+    python tools/summarize_ncu.py gpurun_out/prof_r1_v4.ncu-rep gpurun_out/launches_r1.csv profiles/r1_ncu_summary.md "<command>" \
+        [profiles/r1_traffic.json <config> <envs>]
+
+The optional traffic file (per-kernel dram__bytes_read/write of the captured launch) is what bench.py reads for
+`roofline.traffic`.
 """
+import json
 import csv
 import io
 import subprocess
@@ -12,7 +17,8 @@ METRICS = [
     "gpu__time_duration.sum", "launch__registers_per_thread", "launch__block_size", "launch__grid_size",
     "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
     "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-    "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -30,9 +36,19 @@ def main():
     lines = ["# ncu summary", "", f"command: `{cmd}`", "",
              "Captured with `ncu --set full --clock-control none --import-source on` on a B200 (one launch of each",
              "kernel, after warm-up; per-launch times under ncu are cold-cache and serialised -- compare shares).", ""]
+    traffic = {}
     for r in data:
         d = dict(zip(hdr, r))
         u = dict(zip(hdr, units))
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        try:
+            traffic[d["Kernel Name"].replace("void ", "").split("(")[0]] = {
+                "dram_bytes_read": float(d["dram__bytes_read.sum"]) * scale[u["dram__bytes_read.sum"]],
+                "dram_bytes_write": float(d["dram__bytes_write.sum"]) * scale[u["dram__bytes_write.sum"]],
+                "duration_ms_under_ncu": float(d["gpu__time_duration.sum"]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}[u["gpu__time_duration.sum"]],
+            }
+        except (KeyError, ValueError):
+            pass
         lines.append(f"## {d['Kernel Name']}")
         lines.append("")
         lines.append("| metric | value | unit |")
@@ -72,6 +88,13 @@ def main():
     with open(out, "w") as fh:
         fh.write("\n".join(lines) + "\n")
     print("wrote", out)
+    if len(sys.argv) >= 8:
+        tpath, config, envs = sys.argv[5], int(sys.argv[6]), int(sys.argv[7])
+        with open(tpath, "w") as fh:
+            json.dump({"command": cmd, "config": config, "envs": envs, "kernels": traffic,
+                       "note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of each kernel from the "
+                               "ncu --set full capture summarised in " + out}, fh, indent=1)
+        print("wrote", tpath)
 
 
 if __name__ == "__main__":
