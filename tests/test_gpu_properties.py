@@ -121,3 +121,48 @@ def test_rollout_equals_stepwise_euler(world):
     # steps stays far below these bounds
     torch.testing.assert_close(q, q2, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(qd, qd2, rtol=1e-3, atol=1e-4)
+
+
+def test_rollout_is_cuda_graph_capturable(world):
+    """Every launch of rmp2_step / rmp2_rollout is asynchronous on the caller's stream and, after a first
+    (warm-up) call has sized the tree's scratch, allocates nothing: a whole closed-loop rollout can be
+    captured in a CUDA graph and replayed -- the way to run small, launch-bound batches.  The replay must
+    reproduce the eager result bit for bit."""
+    w = world
+    ns, fk, dev = w["ns"], w["fk"], w["dev"]
+    core = S.build_config5(ns, fk, [0.5, 0.0, 0.5], N, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance())
+    tree = core.compile(N, goal_leaves=["attractor"])
+    Br, dt, n_steps, every = 2048, 0.01, 30, 10
+    goals, sph = w["goals"][:Br].contiguous(), w["spheres"][:Br].contiguous()
+    q0, qd0 = w["q"][:Br].clone(), w["qd"][:Br].clone()
+    q, qd, qdd = q0.clone(), qd0.clone(), torch.empty(Br, N, device=dev)
+    tree.rollout(q, qd, qdd, dt, n_steps, every, goals=goals, spheres=sph)       # eager (also the warm-up)
+    want_q, want_qd, want_qdd = q.clone(), qd.clone(), qdd.clone()
+    gq, gqd, gqdd = q0.clone(), qd0.clone(), torch.empty(Br, N, device=dev)
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            tree.rollout(gq, gqd, gqdd, dt, n_steps, every, goals=goals, spheres=sph)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(2):                                                              # replay twice from the same start
+        gq.copy_(q0)
+        gqd.copy_(qd0)
+        graph.replay()
+        torch.cuda.synchronize()
+        for got, want in ((gq, want_q), (gqd, want_qd), (gqdd, want_qdd)):
+            assert torch.equal(got.view(torch.int32), want.view(torch.int32))      # bit patterns
+    # timing, informational: eager launches vs one graph launch
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    for _ in range(5):
+        tree.rollout(q, qd, qdd, dt, n_steps, every, goals=goals, spheres=sph)
+    ev[1].record()
+    ev[2].record()
+    for _ in range(5):
+        graph.replay()
+    ev[3].record()
+    torch.cuda.synchronize()
+    print(f"rollout of {n_steps} sim steps ({n_steps // every} control steps), {Br} envs: eager "
+          f"{ev[0].elapsed_time(ev[1]) / 5:.3f} ms, CUDA graph replay {ev[2].elapsed_time(ev[3]) / 5:.3f} ms")
