@@ -287,7 +287,11 @@ def run_b200_arm(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_cores = 0
     if world > 1:
+        # one process per GPU: keep this rank's pinned staging memory and its copy threads on the GPU's own socket
+        from riemannian_motion_policies_b200.sharding import bind_host_to_gpu
+        numa_cores = bind_host_to_gpu(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner to stdout on first use; keep stdout for the one JSON line
         sys.stdout.flush()
@@ -425,7 +429,8 @@ def run_b200_arm(args):
         d2h = B * n * 4
         e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": e2e_steps, "note": "RmpCore -> CompiledTree.step_host -> rmp2_step_host, pinned host tensors, "
-                                           "64k-env chunks pipelined over 3 streams"}
+                                           "64k-env chunks pipelined over 3 streams",
+               "host_cores_bound_per_rank": numa_cores}
         same = torch.allclose(qdd_h[:4096], qdd[:4096].cpu(), rtol=0, atol=0) if not O_ else None
         if same is not None:
             e2e["matches_device_path"] = bool(same)

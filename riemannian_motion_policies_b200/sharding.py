@@ -6,8 +6,32 @@ communication is an optional all-gather of `qdd` when one host needs all results
 of the step and is timed separately.  Works with the `nccl` backend on GPUs and with `gloo` on CPU
 tensors (used by the CPU tests of the partition / collection logic).
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def bind_host_to_gpu(device_index):
+    """Pin this process (and the host memory it touches from now on: first-touch NUMA placement, which is
+    what decides where pinned staging buffers live) to the CPU cores closest to GPU `device_index`.
+    With one process per GPU on a two-socket box this keeps every rank's host<->device copies on its own
+    socket's memory controllers and PCIe root instead of funnelling all eight through one socket.
+    Returns the number of cores bound to, or 0 when NVML / sched_setaffinity is unavailable (no-op)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cores = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return 0
+        os.sched_setaffinity(0, allowed)
+        return len(allowed)
+    except Exception:
+        return 0
 
 
 def shard_bounds(B, world_size, rank):
