@@ -316,6 +316,11 @@ def run_b200_arm(args):
     core = S.build_config2(ns, fk, goal0, n) if config == 2 else S.BUILDERS[config](ns, fk, goal0, n, sphere_tm)
     goal_leaf = "target" if config == 2 else "attractor"
     tree = core.compile(n, goal_leaves=[goal_leaf])
+    # the product's path for large batches: frames / step kernels rebuilt for this tree by NVRTC (one-off,
+    # outside the timed region like any warm-up); --no-specialize times the generic table-driven kernels
+    specialized = {"on": False, "nvrtc_seconds": None}
+    if not args.no_specialize:
+        specialized = {"on": True, "nvrtc_seconds": tree.specialize()}
     # Headline and roofline: every (frame, sphere) pair goes through the full arithmetic.  The exact
     # early-out of the obstacle kernel (library default) is measured separately below.
     tree.set_early_out(False)
@@ -516,7 +521,8 @@ def run_b200_arm(args):
                               "peak_source": "analytic 148 SM x 128 lanes x 2 x 1.965 GHz",
                               "lanes": lanes},
             "kernel_ms": {k: {"ms_per_step": v[0] / args.steps, "launches": int(v[1])} for k, v in kernel_ms.items()},
-            "per_gpu_value": per_gpu, "gpu_launches": int(launches), "kernel": info, "clocks": clocks.summary(),
+            "per_gpu_value": per_gpu, "gpu_launches": int(launches), "kernel": info, "specialized": specialized,
+            "clocks": clocks.summary(),
             "early_out": early, "e2e": e2e, "cpu_baseline": cpu_baseline, "parity": parity,
         }
         print(json.dumps(line), flush=True)
@@ -535,6 +541,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="environments per GPU (default: 1,048,576)")
     ap.add_argument("--envs-per-core", type=int, default=6, help="CPU arm: environments per host process per step")
     ap.add_argument("--reference-budget-s", type=float, default=150.0, help="CPU arm: stop after this many seconds")
+    ap.add_argument("--no-specialize", action="store_true", help="keep the generic (table-interpreting) frames/step kernels")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-early-out", action="store_true")
     ap.add_argument("--skip-checks", action="store_true", help="skip the oracle parity spot check and the CPU baseline")

@@ -121,6 +121,10 @@ typedef struct rmp2_step_io {
   int32_t pair_counts[RMP2_MAX_PAIR_SETS]; /* K of each such leaf; K_total = their sum        */
 } rmp2_step_io;
 
+/* The entry points below are host functions; device code that only needs the constants and structs above
+ * (the library's own NVRTC build of its kernels) skips them. */
+#ifndef __CUDACC_RTC__
+
 /* ---- lifetime -------------------------------------------------------------------------- */
 
 /* Build the constant tables of a robot.  Stands in for UrdfForwardKinematic._build
@@ -213,11 +217,26 @@ int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_sphere
 #define RMP2_OPT_EARLY_OUT 0
 int rmp2_tree_set_option(rmp2_tree* tree, int32_t option, int32_t value);
 
+/* Tree-specialised kernels.  The frames and step kernels interpret the tree's tables at run time; for a
+ * large batch that shares one tree that interpretation is pure overhead.  rmp2_tree_specialize rebuilds
+ * the two kernels for THIS tree with NVRTC (tables as a compile-time constant, frame and leaf loops
+ * unrolled; a few seconds, once) and uses them for every later rmp2_step / rmp2_rollout of the tree.
+ * Results agree with the generic kernels to rounding (same source, different constant folding).
+ * rmp2_tree_update_leaf drops the specialisation (the tables changed); call again to rebuild.
+ * flags: RMP2_SPECIALIZE_COMPILE_ONLY = run NVRTC but do not load (needs no GPU; build checks).
+ * Fails with RMP2_ERR_UNSUPPORTED when NVRTC (libnvrtc.so.12) cannot be loaded. */
+#define RMP2_SPECIALIZE_COMPILE_ONLY 1
+int rmp2_tree_specialize(rmp2_tree* tree, int32_t flags);
+/* 1 when specialised kernels are loaded for the tree; *compile_seconds (may be NULL) = NVRTC time. */
+int rmp2_tree_is_specialized(const rmp2_tree* tree, double* compile_seconds);
+
 /* Per-kernel device timing with CUDA events on the launching stream (bench.py's roofline leg).
  * rmp2_tree_profile_read waits for the recorded launches, returns the accumulated milliseconds and
  * launch counts of {frames, spheres, step, resolve} since the last read, and resets them. */
 int rmp2_tree_profile(rmp2_tree* tree, int32_t enable);
 int rmp2_tree_profile_read(rmp2_tree* tree, double* ms /*[4]*/, int64_t* launches /*[4]*/);
+
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,7 @@ SPACE_FRAME_POINTS = 4
 PAIR_FLOATS = 8
 
 OPT_EARLY_OUT = 0
+SPECIALIZE_COMPILE_ONLY = 1
 
 # every symbol include/rmp2_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -44,6 +45,7 @@ EXPORTS = [
     "rmp2_tree_update_leaf", "rmp2_step", "rmp2_step_host", "rmp2_rollout", "rmp2_fk",
     "rmp2_leaf_evaluate", "rmp2_obstacle_feed", "rmp2_last_error", "rmp2_version", "rmp2_launch_count",
     "rmp2_tree_kernel_info", "rmp2_tree_profile", "rmp2_tree_profile_read", "rmp2_tree_set_option",
+    "rmp2_tree_specialize", "rmp2_tree_is_specialized",
 ]
 
 
@@ -125,6 +127,10 @@ def lib():
     L.rmp2_tree_kernel_info.restype = ctypes.c_int
     L.rmp2_tree_set_option.argtypes = [vp, i32, i32]
     L.rmp2_tree_set_option.restype = ctypes.c_int
+    L.rmp2_tree_specialize.argtypes = [vp, i32]
+    L.rmp2_tree_specialize.restype = ctypes.c_int
+    L.rmp2_tree_is_specialized.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    L.rmp2_tree_is_specialized.restype = ctypes.c_int
     L.rmp2_tree_profile.argtypes = [vp, i32]
     L.rmp2_tree_profile.restype = ctypes.c_int
     L.rmp2_tree_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "rmp2_launch.h"
+#include "rmp2_jit.h"
 #include "rmp2_leaves.cuh"
 
 namespace {
@@ -66,6 +67,7 @@ struct rmp2_tree {
   bool early_out = true;                  // RMP2_OPT_EARLY_OUT
   KernelClock clock[4];                   // frames, spheres, step, resolve
   HostStage stage[3];
+  SpecModule* spec = nullptr;             // tree-specialised frames / step kernels (rmp2_tree_specialize)
 };
 
 #define RMP2_STEP_CHUNK (1LL << 20)       // environments per internal chunk (bounds the scratch)
@@ -440,9 +442,29 @@ void rmp2_tree_destroy(rmp2_tree* tree) {
   }
   if (tree->rec) cudaFree(tree->rec);
   if (tree->mf) cudaFree(tree->mf);
+  rmp2_jit_destroy(tree->spec);
   for (auto& c : tree->clock)
     for (auto ev : c.pending) cudaEventDestroy(ev);
   delete tree;
+}
+
+int rmp2_tree_specialize(rmp2_tree* tree, int32_t flags) {
+  if (!tree) return fail(RMP2_ERR_INVALID, "null argument");
+  const bool compile_only = (flags & RMP2_SPECIALIZE_COMPILE_ONLY) != 0;
+  SpecModule* m = nullptr;
+  std::string err;
+  if (rmp2_jit_build(tree->tab, rmp2_pick_width(tree->tab.n), compile_only, &m, err) != 0)
+    return fail(err.rfind("NVRTC not found", 0) == 0 ? RMP2_ERR_UNSUPPORTED : RMP2_ERR_CUDA, "rmp2_tree_specialize: " + err);
+  if (!compile_only) {
+    rmp2_jit_destroy(tree->spec);
+    tree->spec = m;
+  }
+  return RMP2_OK;
+}
+
+int rmp2_tree_is_specialized(const rmp2_tree* tree, double* compile_seconds) {
+  if (compile_seconds) *compile_seconds = (tree && tree->spec) ? rmp2_jit_seconds(tree->spec) : 0.0;
+  return (tree && tree->spec) ? 1 : 0;
 }
 
 int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* leaf) {
@@ -460,6 +482,10 @@ int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* 
   if (L.sphere_slot >= 0)
     fill_sphere_row(*leaf, tree->sph.p[L.sphere_slot]);
   tree->leaves[index] = *leaf;
+  if (tree->spec) {                       // the tables are baked into the specialised kernels: drop them
+    rmp2_jit_destroy(tree->spec);
+    tree->spec = nullptr;
+  }
   return RMP2_OK;
 }
 
@@ -541,12 +567,18 @@ int launch_chunk(rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
   const StepTables& T = tree->tab;
   const int block = pick_block(A.B);
   cudaError_t e;
+  std::string jit_err;
   if (T.n_sphere_slots > 0 && A.n_spheres > 0) {
     {
       ScopedClock clk(tree, 0, stream);
-      e = rmp2_launch_frames(T, A, block, stream);
+      if (tree->spec) {
+        const size_t smem = (size_t)T.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
+        e = rmp2_jit_launch(tree->spec, 0, A, (unsigned)((A.B + block - 1) / block), block, smem, stream, jit_err);
+      } else {
+        e = rmp2_launch_frames(T, A, block, stream);
+      }
     }
-    if (e != cudaSuccess) return cuda_fail(e, "rmp2_frames_kernel launch");
+    if (e != cudaSuccess) return cuda_fail(e, (std::string("rmp2_frames_kernel launch") + (jit_err.empty() ? "" : ": " + jit_err)).c_str());
     const bool use_tma = tma_eligible(tree, A);
     {
       ScopedClock clk(tree, 1, stream);
@@ -557,9 +589,13 @@ int launch_chunk(rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
   }
   {
     ScopedClock clk(tree, 2, stream);
-    e = rmp2_launch_step(T, A, block, stream);
+    if (tree->spec)
+      e = rmp2_jit_launch(tree->spec, A.mf ? 2 : 1, A, (unsigned)((A.B + block - 1) / block), block,
+                          rmp2_step_smem(T, block), stream, jit_err);
+    else
+      e = rmp2_launch_step(T, A, block, stream);
   }
-  if (e != cudaSuccess) return cuda_fail(e, "rmp2_step_kernel launch");
+  if (e != cudaSuccess) return cuda_fail(e, (std::string("rmp2_step_kernel launch") + (jit_err.empty() ? "" : ": " + jit_err)).c_str());
   g_launches.fetch_add(1);
   if (A.mf) {
     {

@@ -23,7 +23,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "rmp2_step.cuh"
+#include "rmp2_tree_kernels.cuh"
 #include "rmp2_launch.h"
 
 // ----------------------------------------------------------------------------- TMA / mbarrier PTX
@@ -60,86 +60,12 @@ RMP2_DEV float4 lds128(uint32_t addr) {
   return v;
 }
 
-// ------------------------------------------------------------------------------ chain walking
-// Visit frame `fi` of the depth-first execution list: restore / advance / save the chain state and,
-// when kCols, record the world axis and origin of the joint column the frame drives.
-template <int N, bool kCols>
-RMP2_DEV void visit_frame(const StepTables& T, int fi, const float (&q)[N], const float (&qd)[N], Chain& ch,
-                          float* cols, float* slots) {
-  const FrameTab& F = T.frames[fi];
-  if (F.restore_slot == RMP2_SLOT_BASE) {
-    chain_reset(ch);
-  } else if (F.restore_slot >= 0) {
-    const float* s = slots + (size_t)F.restore_slot * RMP2_CHAIN_FLOATS * blockDim.x + threadIdx.x;
-    float* cf = reinterpret_cast<float*>(&ch);
-#pragma unroll
-    for (int i = 0; i < RMP2_CHAIN_FLOATS; ++i) cf[i] = s[i * blockDim.x];
-  }
-  float qi = 0.f, qdi = 0.f;
-#pragma unroll
-  for (int j = 0; j < N; ++j)
-    if (j == F.qidx) {
-      qi = q[j];
-      qdi = qd[j];
-    }
-  float z[3];
-  chain_advance(ch, F, qi, qdi, z);
-  if (kCols && F.qidx >= 0) {                    // joint column -> shared memory (see pullback)
-    float* c = cols + (size_t)F.qidx * 6 * blockDim.x;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      c[i * blockDim.x] = z[i];
-      c[(3 + i) * blockDim.x] = ch.p[i];
-    }
-  }
-  if (F.save_slot >= 0) {
-    float* s = slots + (size_t)F.save_slot * RMP2_CHAIN_FLOATS * blockDim.x + threadIdx.x;
-    const float* cf = reinterpret_cast<const float*>(&ch);
-#pragma unroll
-    for (int i = 0; i < RMP2_CHAIN_FLOATS; ++i) s[i * blockDim.x] = cf[i];
-  }
-}
-
 // ------------------------------------------------------------------------------- frames kernel
-// rec[field][slot][env] = (p, v, a, |v|^2) for every sphere-obstacle leaf slot (fields 0..9).
+// (body: rmp2_tree_kernels.cuh)
 template <int N>
 __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
     rmp2_frames_kernel(const __grid_constant__ StepTables T, const __grid_constant__ StepArgs A) {
-  extern __shared__ float slots[];
-  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= A.B) return;
-  const int n = T.n;
-  float q[N], qd[N];
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    q[j] = (j < n) ? A.q[env * n + j] : 0.f;
-    qd[j] = (j < n) ? A.qd[env * n + j] : 0.f;
-  }
-  Chain ch;
-  chain_reset(ch);
-  // records are field-major: rec[(field * L + slot) * B + env] -> every store below is one full line
-  float* rec = A.rec + env;
-  const size_t fstride = (size_t)T.n_sphere_slots * A.B;
-  for (int fi = 0; fi < T.n_frames; ++fi) {
-    visit_frame<N, false>(T, fi, q, qd, ch, nullptr, slots);
-    const FrameTab& F = T.frames[fi];
-    for (int li = F.leaf_begin; li < F.leaf_end; ++li) {
-      const LeafTab& L = T.leaves[li];
-      if (L.space != RMP2_SPACE_FRAME_DISTANCE_SPHERES) continue;
-      const float vv = fmaf(ch.v[0], ch.v[0], fmaf(ch.v[1], ch.v[1], ch.v[2] * ch.v[2]));
-      float* r = rec + (size_t)L.sphere_slot * A.B;
-      r[0 * fstride] = ch.p[0];
-      r[1 * fstride] = ch.p[1];
-      r[2 * fstride] = ch.p[2];
-      r[3 * fstride] = ch.v[0];
-      r[4 * fstride] = ch.v[1];
-      r[5 * fstride] = ch.v[2];
-      r[6 * fstride] = ch.a[0];
-      r[7 * fstride] = ch.a[1];
-      r[8 * fstride] = ch.a[2];
-      r[9 * fstride] = vv;
-    }
-  }
+  frames_body<N>(T, A);
 }
 
 // ------------------------------------------------------------------------------ spheres kernel
@@ -299,254 +225,11 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_SPHERES_MIN_BLOCKS)
 }
 
 // --------------------------------------------------------------------------------- step kernel
-// Tail shared by the fused step kernel and the resolve kernel: optional explicit-Euler sub-steps with
-// the command held (reference loop: control at 10 Hz, simulation at 100 Hz --
-// experiments/franka_panda/05_obstacle_avoidance.py:92-97), then the stores.
-template <int N>
-RMP2_DEV void finish_step(const StepArgs& A, int n, long long e, bool active, bool rollout, float (&q)[N],
-                          float (&qd)[N], const float (&qdd)[N]) {
-  if (rollout) {
-    for (int s = 0; s < A.n_sim_steps; ++s) {
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        qd[j] = fmaf(qdd[j], A.dt, qd[j]);
-        q[j] = fmaf(qd[j], A.dt, q[j]);
-      }
-    }
-    if (active) {
-#pragma unroll
-      for (int j = 0; j < N; ++j)
-        if (j < n) {
-          A.q_rw[e * n + j] = q[j];
-          A.qd_rw[e * n + j] = qd[j];
-        }
-    }
-  }
-  if (active) {
-#pragma unroll
-    for (int j = 0; j < N; ++j)
-      if (j < n) A.qdd[e * n + j] = qdd[j];
-  }
-}
-
-#ifndef RMP2_RESOLVE_MIN_BLOCKS
-#define RMP2_RESOLVE_MIN_BLOCKS(N) ((N) <= 7 ? 6 : ((N) <= 9 ? 3 : 2))
-#endif
-#ifndef RMP2_SPLIT_MIN_BLOCKS
-#define RMP2_SPLIT_MIN_BLOCKS(N) ((N) <= 7 ? 4 : ((N) <= 9 ? 3 : 2))
-#endif
-// resident blocks per SM the register allocation aims at (N <= 7: 128 registers -> 16 warps/SM)
-#ifndef RMP2_STEP_MIN_BLOCKS
-#define RMP2_STEP_MIN_BLOCKS(N) ((N) <= 7 ? 4 : ((N) <= 9 ? 3 : 2))
-#endif
-// kSplit: stop after the combined (M, f) and hand them to rmp2_resolve_kernel through A.mf
-// (field-major [N*N + N][B]); used for large batches, where two small kernels beat one big one.
+// (body: rmp2_tree_kernels.cuh)
 template <int N, bool kSplit>
 __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, kSplit ? RMP2_SPLIT_MIN_BLOCKS(N) : RMP2_STEP_MIN_BLOCKS(N))
     rmp2_step_kernel(const __grid_constant__ StepTables T, const __grid_constant__ StepArgs A) {
-  extern __shared__ float slots[];
-  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  // no early return: the resolve uses full-warp votes; out-of-range lanes redo the last environment
-  const bool active = env < A.B;
-  const long long e = active ? env : A.B - 1;
-  const int n = T.n;
-  const bool rollout = A.n_sim_steps > 0;
-
-  float q[N], qd[N], qdd[N];
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const bool in = j < n;
-    q[j] = in ? (rollout ? A.q_rw : A.q)[e * n + j] : 0.f;
-    qd[j] = in ? (rollout ? A.qd_rw : A.qd)[e * n + j] : 0.f;
-  }
-
-  float Msym[N * (N + 1) / 2];
-  float f[N];
-#pragma unroll
-  for (int i = 0; i < N * (N + 1) / 2; ++i) Msym[i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < N; ++i) f[i] = 0.f;
-
-  {
-    // shared memory: [chain-state slots | joint columns (6 N floats per thread)]
-    float* cols = slots + (size_t)T.n_slots * RMP2_CHAIN_FLOATS * blockDim.x + threadIdx.x;
-    const int cstride = blockDim.x;
-    Chain ch;
-    chain_reset(ch);
-    for (int fi = 0; fi < T.n_frames; ++fi) {
-      visit_frame<N, true>(T, fi, q, qd, ch, cols, slots);
-      const FrameTab& F = T.frames[fi];
-      if (F.leaf_begin >= F.leaf_end) continue;
-
-      float S[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      float g[3] = {0.f, 0.f, 0.f};
-      bool contrib = false;
-      for (int li = F.leaf_begin; li < F.leaf_end; ++li) {
-        const LeafTab& L = T.leaves[li];
-        if (L.space == RMP2_SPACE_FRAME_POSITION) {
-          float goal[3], xdd[3], zeta[3], iso, dir;
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-            goal[i] = (L.goal_slot >= 0) ? __ldg(A.goals + (e * A.n_goal_slots + L.goal_slot) * 3 + i)
-                                         : T.vecpool[L.vec_off + i];
-          if (L.type == RMP2_LEAF_TARGET_POLICY)
-            target_policy<3>(L.p, ch.p, ch.v, goal, 3, xdd, zeta, iso, dir);
-          else
-            target_attractor(L.p, ch.p, ch.v, goal, xdd, zeta, iso, dir);
-          const float er[3] = {xdd[0] - ch.a[0], xdd[1] - ch.a[1], xdd[2] - ch.a[2]};
-          const float ze = dir * fmaf(zeta[0], er[0], fmaf(zeta[1], er[1], zeta[2] * er[2]));
-          const float dz[3] = {dir * zeta[0], dir * zeta[1], dir * zeta[2]};
-          S[0] += fmaf(dz[0], zeta[0], iso);
-          S[1] = fmaf(dz[0], zeta[1], S[1]);
-          S[2] = fmaf(dz[0], zeta[2], S[2]);
-          S[3] += fmaf(dz[1], zeta[1], iso);
-          S[4] = fmaf(dz[1], zeta[2], S[4]);
-          S[5] += fmaf(dz[2], zeta[2], iso);
-#pragma unroll
-          for (int i = 0; i < 3; ++i) g[i] += fmaf(iso, er[i], ze * zeta[i]);
-          contrib = true;
-        } else if (L.space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) {
-          if (A.n_spheres <= 0) continue;
-          // sums over this leaf's spheres, produced by rmp2_spheres_kernel
-          const float* r = A.rec + (size_t)L.sphere_slot * A.B + e;
-          const size_t fstride = (size_t)T.n_sphere_slots * A.B;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) S[i] += __ldg(r + i * fstride);
-#pragma unroll
-          for (int i = 0; i < 3; ++i) g[i] += __ldg(r + (6 + i) * fstride);
-          contrib = true;
-        } else if (L.space == RMP2_SPACE_FRAME_DISTANCE_PAIRS) {  // explicit (pos_on_link, pos_on_obstacle)
-          const int k0 = A.pair_off[L.pair_set], k1 = A.pair_off[L.pair_set + 1];
-          const float* pp = A.pairs + ((size_t)e * A.pair_total + k0) * RMP2_PAIR_FLOATS;
-          const float vv = fmaf(ch.v[0], ch.v[0], fmaf(ch.v[1], ch.v[1], ch.v[2] * ch.v[2]));
-          for (int k = 0; k < k1 - k0; ++k) {
-            const float* row = pp + RMP2_PAIR_FLOATS * k;
-            const float rx = __ldg(row + 0) - __ldg(row + 3);
-            const float ry = __ldg(row + 1) - __ldg(row + 4);
-            const float rz = __ldg(row + 2) - __ldg(row + 5);
-            const float d2 = fmaxf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)), 1e-24f);
-            const float inv_d = fast_rsqrt(d2);
-            obstacle_pair(L.p, rx * inv_d, ry * inv_d, rz * inv_d, d2 * inv_d, inv_d, ch.v, ch.a, vv, S, g);
-          }
-          contrib = true;
-        } else {  // RMP2_SPACE_FRAME_POINTS: points fixed in the frame (v1 CollisionAvoidance)
-          // x = p + R rel;  xd = v + w x rho;  c = a + alpha x rho + w x (w x rho)   (rho = R rel);
-          // the point's Jacobian is the frame-origin Jacobian evaluated at x, so every pair is
-          // pulled back on its own (reference: taskmap.py:83-99 via autodiff).
-          const int k0 = A.pair_off[L.pair_set], k1 = A.pair_off[L.pair_set + 1];
-          const float* pp = A.pairs + ((size_t)e * A.pair_total + k0) * RMP2_PAIR_FLOATS;
-          for (int k = 0; k < k1 - k0; ++k) {
-            const float* row = pp + RMP2_PAIR_FLOATS * k;
-            const float rel[3] = {__ldg(row + 0), __ldg(row + 1), __ldg(row + 2)};
-            const float dist = __ldg(row + 3);
-            const float vec[3] = {__ldg(row + 4), __ldg(row + 5), __ldg(row + 6)};
-            float rho[3], wr[3], wwr[3], ar[3];
-            matvec3(ch.R, rel, rho);
-            cross3(ch.w, rho, wr);
-            cross3(ch.w, wr, wwr);
-            cross3(ch.al, rho, ar);
-            const float xp[3] = {ch.p[0] + rho[0], ch.p[1] + rho[1], ch.p[2] + rho[2]};
-            const float xd[3] = {ch.v[0] + wr[0], ch.v[1] + wr[1], ch.v[2] + wr[2]};
-            const float cp[3] = {ch.a[0] + ar[0] + wwr[0], ch.a[1] + ar[1] + wwr[1], ch.a[2] + ar[2] + wwr[2]};
-            float fl[3], w;
-            collision_avoidance_v1(L.p, dist, vec, xd, fl, w);
-            const float Sp[6] = {w, 0.f, 0.f, w, 0.f, w};
-            const float gp[3] = {w * (fl[0] - cp[0]), w * (fl[1] - cp[1]), w * (fl[2] - cp[2])};
-            pullback<N>(cols, cstride, xp, F.anc_mask, T.prismatic_mask, Sp, gp, Msym, f);
-          }
-        }
-      }
-      if (contrib) pullback<N>(cols, cstride, ch.p, F.anc_mask, T.prismatic_mask, S, g, Msym, f);
-    }
-  }
-
-  // ---- configuration-space leaves and the resolve, on the full matrix --------------------------
-  float M[N][N];
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-#pragma unroll
-    for (int j = 0; j < N; ++j) M[i][j] = (j <= i) ? Msym[i * (i + 1) / 2 + j] : Msym[j * (j + 1) / 2 + i];
-
-  for (int li = T.n_frame_leaves; li < T.n_leaves; ++li) {
-    const LeafTab& L = T.leaves[li];
-    const float* vec = T.vecpool + L.vec_off;
-    float xdd[N];
-    if (L.type == RMP2_LEAF_CONFIG_BIASING || L.type == RMP2_LEAF_JOINT_DAMPING ||
-        L.type == RMP2_LEAF_CSPACE_BIASING) {
-      float m;
-      if (L.type == RMP2_LEAF_CONFIG_BIASING)
-        leaf_config_biasing<N>(L.p, vec, n, q, qd, xdd, m);
-      else if (L.type == RMP2_LEAF_JOINT_DAMPING)
-        leaf_joint_damping<N>(L.p, n, qd, xdd, m);
-      else
-        leaf_cspace_biasing<N>(L.p, vec, n, q, qd, xdd, m);
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-        if (i < n) {
-          M[i][i] += m;
-          f[i] = fmaf(m, xdd[i], f[i]);
-        }
-    } else if (L.type == RMP2_LEAF_VELOCITY_CAP) {
-      float diag[N], w;
-      leaf_velocity_cap<N>(L.p, n, qd, xdd, diag, w);
-      float sum = 0.f;
-#pragma unroll
-      for (int i = 0; i < N; ++i) sum += xdd[i];
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-        if (i < n) {
-          f[i] += fmaf(w, sum - xdd[i], diag[i] * xdd[i]);
-#pragma unroll
-          for (int j = 0; j < N; ++j)
-            if (j < n) M[i][j] += (i == j) ? diag[i] : w;
-        }
-    } else if (L.type == RMP2_LEAF_JOINT_LIMIT) {
-      float zeta[N], w[N];
-      leaf_joint_limit<N>(L.p, vec, n, q, qd, xdd, zeta, w);
-      const float beta = L.p[JL_BETA];
-      float tt = 0.f;
-#pragma unroll
-      for (int j = 0; j < N; ++j) tt = fmaf(zeta[j] * w[j], xdd[j], tt);
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        f[i] += fmaf(beta * zeta[i], tt, (1.f - beta) * w[i] * xdd[i]);
-#pragma unroll
-        for (int j = 0; j < N; ++j) M[i][j] += fmaf(beta * zeta[i], zeta[j], (i == j) ? (1.f - beta) : 0.f) * w[j];
-      }
-    } else {  // RMP2_LEAF_TARGET_POLICY on the identity task map
-      float goal[N], zeta[N], iso, dir;
-#pragma unroll
-      for (int i = 0; i < N; ++i) goal[i] = (i < n) ? vec[i] : 0.f;
-      target_policy<N>(L.p, q, qd, goal, n, xdd, zeta, iso, dir);
-      float zx = 0.f;
-#pragma unroll
-      for (int j = 0; j < N; ++j) zx = fmaf(zeta[j], xdd[j], zx);
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-        if (i < n) {
-          f[i] += fmaf(iso, xdd[i], dir * zeta[i] * zx);
-#pragma unroll
-          for (int j = 0; j < N; ++j) M[i][j] += fmaf(dir * zeta[i], zeta[j], (i == j) ? iso : 0.f);
-        }
-    }
-  }
-  if (kSplit) {
-    if (active) {
-      float* o = A.mf + e;
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-#pragma unroll
-        for (int j = 0; j < N; ++j) o[(size_t)(i * N + j) * A.B] = M[i][j];
-#pragma unroll
-      for (int i = 0; i < N; ++i) o[(size_t)(N * N + i) * A.B] = f[i];
-    }
-    return;
-  }
-  if (T.precondition)                            // same arithmetic as the stand-alone resolve kernel
-    resolve_pinv<N, true>(M, f, n, T.rcond, qdd);
-  else
-    resolve_pinv<N, false>(M, f, n, T.rcond, qdd);
-  finish_step<N>(A, n, e, active, rollout, q, qd, qdd);
+  step_body<N, kSplit>(T, A);
 }
 
 // -------------------------------------------------------------------------------- resolve kernel

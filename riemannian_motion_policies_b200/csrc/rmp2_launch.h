@@ -5,7 +5,9 @@
 
 #include "rmp2_tables.h"
 
+#ifndef RMP2_BLOCK_THREADS
 #define RMP2_BLOCK_THREADS 128
+#endif
 
 struct LeafVec {
   float v[3 * RMP2_MAX_JOINTS];

@@ -287,6 +287,20 @@ class CompiledTree:
                              block_threads=block.value, warps_per_sm=bps.value * block.value // 32)
         return out
 
+    def specialize(self, compile_only=False):
+        """Rebuild the frames / step kernels for THIS tree with NVRTC (tables as compile-time constants, loops
+        unrolled; a few seconds, once) and use them from now on -- worthwhile for large batches.  Changing a
+        leaf parameter afterwards (``leaf.goal = ...``) drops the specialisation; call again to rebuild.
+        ``compile_only`` runs the compiler without loading the result (needs no GPU).  Returns NVRTC seconds."""
+        _native.check(_native.lib().rmp2_tree_specialize(self.handle, _native.SPECIALIZE_COMPILE_ONLY if compile_only else 0))
+        return self.specialized_seconds()
+
+    def specialized_seconds(self):
+        """NVRTC compile time of the loaded specialisation, or None when the generic kernels are in use."""
+        sec = ctypes.c_double()
+        on = _native.lib().rmp2_tree_is_specialized(self.handle, ctypes.byref(sec))
+        return sec.value if on else None
+
     def set_early_out(self, enable=True):
         """Skip (frame, sphere) pairs beyond the metric radius in the obstacle kernel (exact; default on)."""
         _native.check(_native.lib().rmp2_tree_set_option(self.handle, _native.OPT_EARLY_OUT, 1 if enable else 0))

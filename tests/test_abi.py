@@ -114,3 +114,16 @@ def test_compute_fails_loudly_without_cuda(native_lib):
         core.evaluate(np.zeros(2, np.float32), np.zeros(2, np.float32))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         fk.forward(np.zeros((1, 2), np.float32), "link_23")
+
+
+def test_specialization_compiles_without_a_gpu():
+    """rmp2_tree_specialize(COMPILE_ONLY): NVRTC builds the tree-specialised frames / step kernels from the
+    sources embedded in the library (no GPU needed; loading and launching them is covered by the gpu tests)."""
+    from riemannian_motion_policies_b200 import scenarios as S
+    ns = S.product_namespace()
+    for urdf, order, n, build in ((S.PANDA_WO_TOOL_URDF, S.PANDA_ORDER_7, 7, S.build_config5),
+                                  (S.PANDA_URDF, S.PANDA_ORDER_9, 9, S.build_config3)):
+        fk = ns.UrdfForwardKinematic(urdf, order)
+        core = build(ns, fk, [0.5, 0.0, 0.5], n, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance())
+        tree = core.compile(n, goal_leaves=["attractor"])
+        assert tree.specialize(compile_only=True) is None        # compiled, nothing loaded

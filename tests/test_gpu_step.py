@@ -427,3 +427,66 @@ def test_direct_solve_and_jacobi_lanes_mix(ns):
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(dev)
     again = core.evaluate(tq[perm], tqd[perm], goals=tg[perm]).cpu().numpy()
     np.testing.assert_array_equal(again, got[perm.cpu().numpy()])
+
+
+@pytest.mark.parametrize("config,n", [(1, 2), (2, 7), (3, 7), (3, 9), (4, 7), (5, 7)])
+def test_specialized_kernels_match(ns, config, n):
+    """rmp2_tree_specialize: the frames / step kernels rebuilt by NVRTC for one tree (tables as compile-time
+    constants, loops unrolled) compute what the generic, table-interpreting kernels compute -- same source,
+    so nearly always the same bits -- and meet the oracle parity criterion on their own."""
+    B = 2048 if config != 1 else 512
+    q, qd, goal, sph = make_inputs(config, n, B)
+    fk = product_fkine(ns, n)
+    core = product_core(ns, config, n, fk)
+    dev = torch.device("cuda")
+    tq, tqd, tg = (torch.as_tensor(a, device=dev) for a in (q, qd, goal))
+    ts = None if sph is None else torch.as_tensor(sph, device=dev)
+    goal_leaves = ["target"] if config in (1, 2) else ["attractor"]
+    tree = core.compile(n, goal_leaves=goal_leaves)
+    goals = tg.reshape(B, 1, 3).contiguous()
+    generic = torch.empty(B, n, device=dev)
+    tree.step(tq, tqd, generic, goals=goals, spheres=ts)
+    assert tree.specialized_seconds() is None
+    seconds = tree.specialize()
+    assert seconds is not None and seconds > 0
+    special = torch.empty(B, n, device=dev)
+    tree.step(tq, tqd, special, goals=goals, spheres=ts)
+    same = (generic == special).all(dim=1).float().mean().item()
+    err = rel_err(special.cpu().numpy(), generic.cpu().numpy())
+    print(f"config{config} n{n}: NVRTC {seconds:.1f} s, bit-identical environments {same:.3f}, median rel diff {np.median(err):.2e}")
+    ref32 = H.evaluate_vmap(config, n, q, qd, goal, sph, dtype=torch.float32)
+    ref64 = H.evaluate_vmap(config, n, q, qd, goal, sph, dtype=torch.float64)
+    _, M64 = H.combined_vmap(config, n, q, qd, goal, sph, dtype=torch.float64)
+    assert_parity(special.cpu().numpy(), ref32, ref64, M64, n, label=f"specialized config{config} n{n}",
+                  max_excluded=0.10 if config == 4 else 0.05)
+    # the fused-resolve kernel (small batches) is specialised too
+    small = torch.empty(64, n, device=dev)
+    tree.step(tq[:64].contiguous(), tqd[:64].contiguous(), small, goals=goals[:64].contiguous(),
+              spheres=None if ts is None else ts[:64].contiguous())
+    np.testing.assert_allclose(small.cpu().numpy(), special[:64].cpu().numpy(), rtol=2e-3, atol=1e-5)
+
+
+def test_leaf_update_drops_the_specialization(ns):
+    """The tables are baked into the specialised kernels, so changing a leaf parameter (reference idiom:
+    ``target_rmp.goal = ...``, 06_cluttered_environment.py:142) must fall back to the generic kernels -- and give
+    the new goal's answer -- until specialize() is called again."""
+    n, B = 7, 256
+    q, qd, goal, _ = make_inputs(2, n, B)
+    fk = product_fkine(ns, n)
+    core = product_core(ns, 2, n, fk)
+    dev = torch.device("cuda")
+    tq, tqd = torch.as_tensor(q, device=dev), torch.as_tensor(qd, device=dev)
+    tree = core.compile(n)
+    tree.specialize()
+    a = core.evaluate(tq, tqd).cpu().numpy()
+    assert core.compile(n).specialized_seconds() is not None
+    core.rmps["target"].goal = [0.3, 0.2, 0.6]
+    b = core.evaluate(tq, tqd).cpu().numpy()
+    assert core.compile(n).specialized_seconds() is None
+    assert np.abs(a - b).max() > 1e-4
+    fresh = product_core(ns, 2, n, fk)
+    fresh.rmps["target"].goal = [0.3, 0.2, 0.6]
+    np.testing.assert_array_equal(fresh.evaluate(tq, tqd).cpu().numpy(), b)
+    core.compile(n).specialize()
+    c = core.evaluate(tq, tqd).cpu().numpy()
+    np.testing.assert_allclose(c, b, rtol=1e-5, atol=1e-6)
