@@ -320,7 +320,9 @@ def run_b200_arm(args):
     # outside the timed region like any warm-up); --no-specialize times the generic table-driven kernels
     specialized = {"on": False, "nvrtc_seconds": None}
     if not args.no_specialize:
-        specialized = {"on": True, "nvrtc_seconds": tree.specialize()}
+        t_spec = time.perf_counter()
+        nvrtc_s = tree.specialize()
+        specialized = {"on": True, "nvrtc_seconds": nvrtc_s, "wall_seconds": time.perf_counter() - t_spec}
     # Headline and roofline: every (frame, sphere) pair goes through the full arithmetic.  The exact
     # early-out of the obstacle kernel (library default) is measured separately below.
     tree.set_early_out(False)

@@ -177,8 +177,28 @@ RMP2_DEV void step_body(const StepTables& T, const StepArgs& A) {
     const int cstride = blockDim.x;
     Chain ch;
     chain_reset(ch);
+#ifdef RMP2_JIT
+    // Specialised build: the (S, g) sums of the next frame's sphere leaves (written by rmp2_spheres_kernel)
+    // are pulled into L1 while this frame is processed -- consumed cold they are this kernel's top stall.
+    // (In the generic kernel the table walk this needs costs more than it saves.)
+    auto prefetch_sums = [&](int fn) {
+      if (A.n_spheres <= 0 || fn >= T.n_frames) return;
+      RMP2_UNROLL_SPEC
+      for (int li = T.frames[fn].leaf_begin; li < T.frames[fn].leaf_end; ++li)
+        if (T.leaves[li].space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) {
+          const float* r = A.rec + (size_t)T.leaves[li].sphere_slot * A.B + e;
+          const size_t fs = (size_t)T.n_sphere_slots * A.B;
+#pragma unroll
+          for (int i = 0; i < 9; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(r + i * fs));
+        }
+    };
+    prefetch_sums(0);
+#endif
     RMP2_UNROLL_SPEC
     for (int fi = 0; fi < T.n_frames; ++fi) {
+#ifdef RMP2_JIT
+      prefetch_sums(fi + 1);
+#endif
       visit_frame<N, true>(T, fi, q, qd, ch, cols, slots);
       const FrameTab& F = T.frames[fi];
       if (F.leaf_begin >= F.leaf_end) continue;
