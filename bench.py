@@ -321,8 +321,11 @@ def run_b200_arm(args):
     specialized = {"on": False, "nvrtc_seconds": None}
     if not args.no_specialize:
         t_spec = time.perf_counter()
-        nvrtc_s = tree.specialize()
-        specialized = {"on": True, "nvrtc_seconds": nvrtc_s, "wall_seconds": time.perf_counter() - t_spec}
+        try:
+            nvrtc_s = tree.specialize()
+            specialized = {"on": True, "nvrtc_seconds": nvrtc_s, "wall_seconds": time.perf_counter() - t_spec}
+        except (RuntimeError, NotImplementedError) as exc:   # no NVRTC on this box: the generic CUDA kernels run instead
+            specialized = {"on": False, "nvrtc_seconds": None, "error": str(exc)[:200]}
     # Headline and roofline: every (frame, sphere) pair goes through the full arithmetic.  The exact
     # early-out of the obstacle kernel (library default) is measured separately below.
     tree.set_early_out(False)
