@@ -454,7 +454,7 @@ int rmp2_tree_specialize(rmp2_tree* tree, int32_t flags) {
   SpecModule* m = nullptr;
   std::string err;
   if (rmp2_jit_build(tree->tab, rmp2_pick_width(tree->tab.n), compile_only, &m, err) != 0)
-    return fail(err.rfind("NVRTC not found", 0) == 0 ? RMP2_ERR_UNSUPPORTED : RMP2_ERR_CUDA, "rmp2_tree_specialize: " + err);
+    return fail(err.rfind("NVRTC not", 0) == 0 ? RMP2_ERR_UNSUPPORTED : RMP2_ERR_CUDA, "rmp2_tree_specialize: " + err);
   if (!compile_only) {
     rmp2_jit_destroy(tree->spec);
     tree->spec = m;
