@@ -894,6 +894,11 @@ int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_sphere
   int r = 0, bps = 0;
   cudaError_t e = rmp2_kernel_attributes(tree->tab.n, which, use_tma, block, smem, &r, &bps);
   if (e != cudaSuccess) return cuda_fail(e, "rmp2_tree_kernel_info");
+  if (tree->spec) {                         // specialised frames / step kernels: their own register count
+    const int w = (which == 0) ? 0 : (which == 2 ? 1 : (which == 3 ? 2 : -1));
+    const int r2 = (w >= 0) ? rmp2_jit_registers(tree->spec, w) : 0;
+    if (r2 > 0) r = r2;
+  }
   if (regs) *regs = r;
   if (smem_bytes) *smem_bytes = (int)smem;
   if (blocks_per_sm) *blocks_per_sm = bps;
