@@ -166,3 +166,17 @@ def test_rollout_is_cuda_graph_capturable(world):
     torch.cuda.synchronize()
     print(f"rollout of {n_steps} sim steps ({n_steps // every} control steps), {Br} envs: eager "
           f"{ev[0].elapsed_time(ev[1]) / 5:.3f} ms, CUDA graph replay {ev[2].elapsed_time(ev[3]) / 5:.3f} ms")
+
+
+def test_specialized_kernels_full_size(world):
+    """The NVRTC-specialised frames / step kernels at the full benchmark size: bit-identical to the generic
+    kernels on all 1,048,576 environments, with and without the exact early-out."""
+    w = world
+    core = S.build_config4(w["ns"], w["fk"], [0.5, 0.0, 0.5], N, lambda fr: w["ns"].TaskmapJointFrame4x4ToSphereDistance())
+    tree = core.compile(N, goal_leaves=["attractor"])
+    tree.specialize()
+    out = torch.empty(B_FULL, N, device=w["dev"])
+    for early in (True, False):
+        tree.set_early_out(early)
+        tree.step(w["q"], w["qd"], out, goals=w["goals"], spheres=w["spheres"])
+        assert torch.equal(out.view(torch.int32), w["qdd"].view(torch.int32))
