@@ -1,10 +1,12 @@
 // sm_100a kernels of the RMP2 control step.
 //
-// One control step = up to three launches on the caller's stream (intermediates stay in L2/HBM, which
-// this FP32-bound path uses at a few per cent of its bandwidth):
+// One control step = up to four launches on the caller's stream (intermediates stay in L2/HBM, which
+// this FP32-bound path uses at a few per cent of its bandwidth).  The two table-driven kernels (frames,
+// step) have their bodies in rmp2_tree_kernels.cuh: here they are instantiated generically (tables as a
+// kernel parameter); rmp2_jit.cu rebuilds them per tree with NVRTC (tables as compile-time constants).
 //
 //   rmp2_frames_kernel<N>    thread per environment: kinematic chain -> origin position, velocity and
-//                            Jdot*qd of every frame that carries a sphere-obstacle leaf  (48 B records)
+//                            Jdot*qd of every frame that carries a sphere-obstacle leaf  (40 B records)
 //   rmp2_spheres_kernel      thread per (environment, obstacle leaf): the O(frames x spheres) pair loop,
 //                            two spheres per step in packed f32x2 arithmetic (FFMA2).  The sphere rows
 //                            of the E environments of a block are staged into shared memory by 1-D
@@ -14,7 +16,10 @@
 //                            Output: per (env, leaf) the 3x3 metric sum S and the force sum g, written
 //                            over the input record.
 //   rmp2_step_kernel<N>      thread per environment: chain again (cheap), target leaves, pullback of every
-//                            frame's (S, g), configuration-space leaves, truncated-SVD resolve -> qdd;
+//                            frame's (S, g), configuration-space leaves -> combined (M, f); small batches
+//                            keep the resolve fused in this kernel.
+//   rmp2_resolve_kernel<N>   thread per environment: qdd = pinv(M) f (direct QR solve where provably clear
+//                            of the pinv cutoff, truncated SVD by one-sided Jacobi otherwise);
 //                            optional explicit-Euler sub-steps for closed-loop rollouts.
 //
 //   rmp2_fk_kernel<N>        FK value / velocity / Jacobian / Jdot*qd of one frame (Python API).
