@@ -509,6 +509,8 @@ def run_b200_arm(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD[config], "envs_per_gpu": B, "global_envs": world * B, "spheres_per_env": O_,
                        "dof": n, "parallelism": f"env-sharded x{world}, no step-path collective",
+                       "kernels": "frames/step rebuilt for this tree by NVRTC (rmp2_tree_specialize)" if specialized["on"]
+                                  else "generic table-driven frames/step kernels",
                        "l2_policy": f"inputs larger than L2: {n_buffers} rotating sphere buffers of "
                                     f"{B * O_ * 16 / 1e6:.0f} MB each" if O_ else "q/qd/goal re-read each step"},
             "roofline": {"bound": "hbm", "kernel": f"rmp2_{dom}_kernel", "achieved": dom_gbs, "peak": peaks["hbm_gbs"],
