@@ -426,7 +426,7 @@ int rmp2_tree_create(const rmp2_robot* rb, const rmp2_leaf_desc* leaves, int32_t
   tr->sph.n_slots = T.n_sphere_slots;
   if (T.n_sphere_slots > 0) {
     // E environments per block: E * L threads <= 128, E <= 32 (box rows), shared memory bounded
-    int E = RMP2_BLOCK_THREADS / T.n_sphere_slots;
+    int E = RMP2_SPHERES_BLOCK / T.n_sphere_slots;
     E = std::max(1, std::min(E, 32));
     tr->sph.envs_per_block = E;
   }

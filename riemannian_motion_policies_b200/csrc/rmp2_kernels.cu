@@ -101,7 +101,7 @@ RMP2_DEV void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64
 }
 
 template <bool kTma, bool kSkip>
-__global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_SPHERES_MIN_BLOCKS)
+__global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 128 / RMP2_SPHERES_BLOCK)
     rmp2_spheres_kernel(const __grid_constant__ SphereTables ST, const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int L = ST.n_slots, E = ST.envs_per_block;

@@ -9,6 +9,10 @@
 #define RMP2_BLOCK_THREADS 128
 #endif
 
+#ifndef RMP2_SPHERES_BLOCK
+#define RMP2_SPHERES_BLOCK 128      // threads per block of rmp2_spheres_kernel = E environments x L obstacle leaves
+#endif
+
 struct LeafVec {
   float v[3 * RMP2_MAX_JOINTS];
 };
