@@ -495,6 +495,10 @@ int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* 
 namespace {
 
 int pick_block(long long B) {
+  if (const char* v = getenv("RMP2_FORCE_BLOCK")) {        // tuning hook: 32, 64 or 128 threads per block
+    const int b = atoi(v);
+    if (b == 32 || b == 64 || b == 128) return b;
+  }
   return (B >= 148LL * 4 * 128) ? 128 : (B >= 148LL * 4 * 64 ? 64 : 32);
 }
 
