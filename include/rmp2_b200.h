@@ -88,7 +88,12 @@ enum {
   RMP2_SPACE_FRAME_DISTANCE_PAIRS = 3,
   /* taskmap.py:79-99   chain [FK(frame), TaskmapRelative4x4(relative_pos), TaskmapFrom4x4ToPosition]:
    * K points fixed in the frame; pair row = (relative_pos xyz, distance, normal_vec xyz, 0)     */
-  RMP2_SPACE_FRAME_POINTS = 4
+  RMP2_SPACE_FRAME_POINTS = 4,
+  /* taskmap.py:57-67   chain [FK(frame), TaskmapFrom4x4ToEuler]: xyz Euler angles of the frame's rotation
+   * (kinematics.py:74-96), differentiated analytically with the Euler-rate map omega = H(theta) thetadot
+   * (helper/trigonometry_helper.py:18-38): J = H^-1 J_omega, c = d/dt(H^-1) omega + H^-1 alpha.
+   * Leaves: TargetPolicy / TargetAttractor with a 3-vector goal of Euler angles.                        */
+  RMP2_SPACE_FRAME_EULER = 5
 };
 
 typedef struct rmp2_robot rmp2_robot; /* constant kinematic tables of one URDF              */
@@ -115,7 +120,7 @@ typedef struct rmp2_step_io {
   const float* goals;     /* [B][n_goal_slots][3] or NULL                                    */
   int32_t n_goal_slots;
   int32_t n_spheres;      /* O, spheres per environment                                      */
-  const float* spheres;   /* [B][O][4] = (cx, cy, cz, radius) or NULL                        */
+  const float* spheres;   /* [B][O][4] = (cx, cy, cz, radius) or NULL; 16-byte aligned        */
   const float* pairs;     /* [B][K_total][8] pair rows (layout per space, see above) or NULL   */
   int32_t n_pair_sets;    /* number of FRAME_DISTANCE_PAIRS / FRAME_POINTS leaves, tree order  */
   int32_t pair_counts[RMP2_MAX_PAIR_SETS]; /* K of each such leaf; K_total = their sum        */
@@ -152,11 +157,16 @@ int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* 
 
 /* qdd = pinv(sum_l J_l^T M_l J_l) * sum_l J_l^T M_l (xdd_l - Jdot_l qd) for B environments.
  * Stands in for RmpCore.evaluate (rmp.py:133-155).  All io pointers are device memory.
- * Launches up to four kernels on `stream` (frames -> spheres -> step -> resolve).  The tree handle owns
- * scratch buffers for the per-(environment, obstacle leaf) records (40 B each) and the combined metric
- * (at most 2^20 environments at a time), allocated on first use and grown when needed; therefore the steps
- * of ONE tree must be issued from one thread on one stream at a time. */
+ * Launches up to five kernels on `stream` (frames -> spheres -> step [-> resolve] -> resolve fallback).  The
+ * tree handle owns scratch buffers (per-(environment, obstacle leaf) records of 40 B, the combined metric, the
+ * work list of the fallback resolve; at most 2^20 environments at a time).  They are sized by rmp2_tree_reserve,
+ * or grown on demand with stream-ordered allocation on `stream` (no device-wide stall; refused while `stream`
+ * is being captured); therefore the steps of ONE tree must be issued from one thread on one stream at a time. */
 int rmp2_step(const rmp2_tree* tree, const rmp2_step_io* io, void* stream);
+
+/* Size the tree's scratch for steps of up to B environments with up to n_spheres spheres each, so that no
+ * later rmp2_step / rmp2_rollout allocates (required before capturing steps into a CUDA graph). */
+int rmp2_tree_reserve(rmp2_tree* tree, int64_t B, int32_t n_spheres, void* stream);
 
 /* Same step with HOST buffers: every io pointer is host memory (pinned for full overlap);
  * inputs are copied to device staging owned by the tree, the step runs, qdd is copied back,
@@ -199,6 +209,15 @@ int rmp2_obstacle_feed(const rmp2_robot* robot, const int32_t* frames, int32_t n
                        const float* q, const float* spheres, int32_t n_spheres, const float* capsules,
                        int32_t n_capsules, float* pairs, float* aux, void* stream);
 
+/* x = pinv(M) f for B independent n x n systems, M [B][n][n], f [B][n], x [B][n] (device, row-major), with
+ * tf.linalg.pinv's default cutoff 10 n eps32 sigma_max.  Stands in for the last two lines of RmpCore.evaluate
+ * (rmp.py:153-154) on its own.  pivot != 0: the variant for possibly rank-deficient M (pivoted QR +
+ * rank-revealing direct solve); 0: the variant for well-conditioned M.  mode 0: as in the step (direct solve
+ * where the spectrum is provably clear of the cutoff, one-sided Jacobi SVD otherwise); mode 1: Jacobi SVD for
+ * every system (cross-check of the two solvers). */
+int rmp2_pinv_solve(int32_t n, int64_t B, const float* M, const float* f, float* x, int32_t pivot,
+                    int32_t mode, void* stream);
+
 /* ---- introspection ----------------------------------------------------------------------- */
 const char* rmp2_last_error(void);
 const char* rmp2_version(void);
@@ -206,8 +225,9 @@ const char* rmp2_version(void);
 int64_t rmp2_launch_count(void);
 /* registers/thread, dynamic shared memory, max resident blocks/SM and block size of one of the
  * kernels a step launches: which = 0 frames (chain -> frame records), 1 spheres (the obstacle
- * pair loop; n_spheres selects the staging layout), 2 step with the resolve fused (small batches),
- * 3 step without it and 4 the stand-alone resolve kernel (large batches). */
+ * pair loop; n_spheres selects the staging layout), 2 step with the direct resolve fused (small batches),
+ * 3 step without it and 4 the stand-alone direct-resolve kernel (large batches), 5 the fallback resolve
+ * (Jacobi SVD for the environments the direct solve handed over). */
 int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_spheres, int32_t* regs,
                           int32_t* smem_bytes, int32_t* blocks_per_sm, int32_t* block_threads);
 /* Options of a tree.  RMP2_OPT_EARLY_OUT (default 1): the obstacle kernel evaluates only the
@@ -215,6 +235,14 @@ int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_sphere
  * zero in the reference as well (rmp2.py:194), so results are unchanged.  Set to 0 to force every
  * pair through the full arithmetic (used for the roofline measurement). */
 #define RMP2_OPT_EARLY_OUT 0
+/* RMP2_OPT_TMA (default 1): stage sphere rows through shared memory with TMA bulk copies (0: LDG.128).
+ * RMP2_OPT_SPLIT_RESOLVE (default -1 = by batch size; 0 / 1): run the direct resolve inside the step kernel
+ * or as its own kernel.  RMP2_OPT_BLOCK_THREADS (default 0 = by batch size; 32 / 64 / 128).
+ * RMP2_OPT_CHUNK_ENVS (default 0 = 2^20): environments per internal chunk of a step (bounds the scratch). */
+#define RMP2_OPT_TMA 1
+#define RMP2_OPT_SPLIT_RESOLVE 2
+#define RMP2_OPT_BLOCK_THREADS 3
+#define RMP2_OPT_CHUNK_ENVS 4
 int rmp2_tree_set_option(rmp2_tree* tree, int32_t option, int32_t value);
 
 /* Tree-specialised kernels.  The frames and step kernels interpret the tree's tables at run time; for a
@@ -222,7 +250,8 @@ int rmp2_tree_set_option(rmp2_tree* tree, int32_t option, int32_t value);
  * the two kernels for THIS tree with NVRTC (tables as a compile-time constant, frame and leaf loops
  * unrolled; a few seconds, once) and uses them for every later rmp2_step / rmp2_rollout of the tree.
  * Results agree with the generic kernels to rounding (same source, different constant folding).
- * rmp2_tree_update_leaf drops the specialisation (the tables changed); call again to rebuild.
+ * rmp2_tree_update_leaf rebuilds the specialisation for the new values (the tables are compile-time constants
+ * of the kernels); if that fails the generic kernels take over.
  * flags: RMP2_SPECIALIZE_COMPILE_ONLY = run NVRTC but do not load (needs no GPU; build checks).
  * Fails with RMP2_ERR_UNSUPPORTED when NVRTC (libnvrtc.so.12) cannot be loaded. */
 #define RMP2_SPECIALIZE_COMPILE_ONLY 1
@@ -232,9 +261,10 @@ int rmp2_tree_is_specialized(const rmp2_tree* tree, double* compile_seconds);
 
 /* Per-kernel device timing with CUDA events on the launching stream (bench.py's roofline leg).
  * rmp2_tree_profile_read waits for the recorded launches, returns the accumulated milliseconds and
- * launch counts of {frames, spheres, step, resolve} since the last read, and resets them. */
+ * launch counts of {frames, spheres, step, resolve, resolve fallback} since the last read, and resets them. */
+#define RMP2_PROFILE_KERNELS 5
 int rmp2_tree_profile(rmp2_tree* tree, int32_t enable);
-int rmp2_tree_profile_read(rmp2_tree* tree, double* ms /*[4]*/, int64_t* launches /*[4]*/);
+int rmp2_tree_profile_read(rmp2_tree* tree, double* ms /*[5]*/, int64_t* launches /*[5]*/);
 
 #endif /* __CUDACC_RTC__ */
 

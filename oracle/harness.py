@@ -25,7 +25,9 @@ def namespace(dtype=torch.float32):
     return ns
 
 
-def make_fkine(n, dtype=torch.float32):
+def make_fkine(n, dtype=torch.float32, robot=None):
+    if robot == "gantry":
+        return O.UrdfForwardKinematic(S.GANTRY_URDF, S.GANTRY_ORDER, dtype=dtype)
     if n == 2:
         return O.UrdfForwardKinematic(S.TWO_JOINT_URDF, S.TWO_JOINT_ORDER, dtype=dtype)
     if n == 7:
@@ -91,10 +93,10 @@ def evaluate_vmap(config, n, q, qd, goal, spheres=None, dtype=torch.float32, chu
     return torch.cat(outs).numpy()
 
 
-def combined_vmap(config, n, q, qd, goal, spheres=None, dtype=torch.float64, chunk=1024):
+def combined_vmap(config, n, q, qd, goal, spheres=None, dtype=torch.float64, chunk=1024, fkine=None):
     """(f [B,n], M [B,n,n]) before the resolve -- lets tests measure cond(M) and the singular-value
     gap around the pinv cutoff (SURVEY.md section 8c guards)."""
-    fkine = make_fkine(n, dtype)
+    fkine = fkine or make_fkine(n, dtype)
     one = _single_env_fn(config, n, fkine, dtype, combine=True)
     B = q.shape[0]
     if spheres is None:

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librmp2_b200.so")
+# RMP2_B200_LIB: load another build of the same library (tools/ A/B studies of compile-time knobs)
+LIB_PATH = os.environ.get("RMP2_B200_LIB") or os.path.join(_HERE, "csrc", "librmp2_b200.so")
 
 RMP2_MAX_FRAMES = 24
 RMP2_MAX_JOINTS = 12
@@ -34,9 +35,15 @@ SPACE_FRAME_POSITION = 1
 SPACE_FRAME_DISTANCE_SPHERES = 2
 SPACE_FRAME_DISTANCE_PAIRS = 3
 SPACE_FRAME_POINTS = 4
+SPACE_FRAME_EULER = 5
 PAIR_FLOATS = 8
 
 OPT_EARLY_OUT = 0
+OPT_TMA = 1
+OPT_SPLIT_RESOLVE = 2
+OPT_BLOCK_THREADS = 3
+OPT_CHUNK_ENVS = 4
+PROFILE_KERNELS = 5
 SPECIALIZE_COMPILE_ONLY = 1
 
 # every symbol include/rmp2_b200.h declares (checked by tests/test_abi.py)
@@ -45,7 +52,7 @@ EXPORTS = [
     "rmp2_tree_update_leaf", "rmp2_step", "rmp2_step_host", "rmp2_rollout", "rmp2_fk",
     "rmp2_leaf_evaluate", "rmp2_obstacle_feed", "rmp2_last_error", "rmp2_version", "rmp2_launch_count",
     "rmp2_tree_kernel_info", "rmp2_tree_profile", "rmp2_tree_profile_read", "rmp2_tree_set_option",
-    "rmp2_tree_specialize", "rmp2_tree_is_specialized",
+    "rmp2_tree_specialize", "rmp2_tree_is_specialized", "rmp2_tree_reserve", "rmp2_pinv_solve",
 ]
 
 
@@ -131,6 +138,10 @@ def lib():
     L.rmp2_tree_specialize.restype = ctypes.c_int
     L.rmp2_tree_is_specialized.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.rmp2_tree_is_specialized.restype = ctypes.c_int
+    L.rmp2_tree_reserve.argtypes = [vp, i64, i32, vp]
+    L.rmp2_tree_reserve.restype = ctypes.c_int
+    L.rmp2_pinv_solve.argtypes = [i32, i64, vp, vp, vp, i32, i32, vp]
+    L.rmp2_pinv_solve.restype = ctypes.c_int
     L.rmp2_tree_profile.argtypes = [vp, i32]
     L.rmp2_tree_profile.restype = ctypes.c_int
     L.rmp2_tree_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]

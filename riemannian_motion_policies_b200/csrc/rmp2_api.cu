@@ -46,6 +46,8 @@ struct HostStage {                // device staging for rmp2_step_host, one per 
   cudaStream_t stream = nullptr;
 };
 
+#define RMP2_N_CLOCKS 5
+
 struct KernelClock {              // optional per-kernel timing (rmp2_tree_profile)
   std::vector<cudaEvent_t> pending;   // (start, stop) pairs not yet read
   double ms = 0.0;
@@ -61,11 +63,20 @@ struct rmp2_tree {
   SphereTables sph;                       // parameters of the sphere-obstacle leaves, by record slot
   float* rec = nullptr;                   // sphere-record scratch of rmp2_step (field-major, see rmp2_tables.h)
   size_t rec_floats = 0;
-  float* mf = nullptr;                    // combined (M, f) scratch when the resolve runs as its own kernel
+  float* mf = nullptr;                    // (M, f) scratch between step and resolve kernel / problems handed to the fallback
   size_t mf_floats = 0;
+  int32_t* fb = nullptr;                  // fallback work list (count, ticket, environment indices)
+  size_t fb_ints = 0;
+  long long reserved_envs = 0;            // rmp2_tree_reserve
+  int reserved_spheres = 0;
   bool profiling = false;
   bool early_out = true;                  // RMP2_OPT_EARLY_OUT
-  KernelClock clock[4];                   // frames, spheres, step, resolve
+  bool use_tma = true;                    // RMP2_OPT_TMA
+  int split_resolve = -1;                 // RMP2_OPT_SPLIT_RESOLVE: -1 by batch size, 0 fused, 1 split
+  int force_block = 0;                    // RMP2_OPT_BLOCK_THREADS: 0 by batch size, else 32 / 64 / 128
+  long long chunk_envs = 0;               // RMP2_OPT_CHUNK_ENVS: environments per internal chunk (0 = 2^20)
+  bool respecialize = false;              // rebuild the specialised kernels when a leaf changes
+  KernelClock clock[RMP2_N_CLOCKS];       // frames, spheres, step, resolve, resolve fallback
   HostStage stage[3];
   SpecModule* spec = nullptr;             // tree-specialised frames / step kernels (rmp2_tree_specialize)
 };
@@ -217,11 +228,12 @@ static int check_leaf(const rmp2_leaf_desc& d, int F, int idx) {
     case RMP2_SPACE_CONFIG:
       if (!config_leaf && d.type != RMP2_LEAF_TARGET_POLICY)
         return fail(RMP2_ERR_UNSUPPORTED, at + "this leaf type is not implemented on the identity task map");
-      if (d.goal_slot >= 0) return fail(RMP2_ERR_UNSUPPORTED, at + "per-environment goals need a frame-position task map");
+      if (d.goal_slot >= 0) return fail(RMP2_ERR_UNSUPPORTED, at + "per-environment goals need a frame position / orientation task map");
       break;
     case RMP2_SPACE_FRAME_POSITION:
+    case RMP2_SPACE_FRAME_EULER:
       if (d.type != RMP2_LEAF_TARGET_POLICY && d.type != RMP2_LEAF_TARGET_ATTRACTOR)
-        return fail(RMP2_ERR_UNSUPPORTED, at + "only TargetPolicy / TargetAttractor live on a frame position");
+        return fail(RMP2_ERR_UNSUPPORTED, at + "only TargetPolicy / TargetAttractor live on a frame position / orientation");
       break;
     case RMP2_SPACE_FRAME_DISTANCE_SPHERES:
     case RMP2_SPACE_FRAME_DISTANCE_PAIRS:
@@ -423,6 +435,14 @@ int rmp2_tree_create(const rmp2_robot* rb, const rmp2_leaf_desc* leaves, int32_t
     const int t = leaves[i].type;
     if (t == RMP2_LEAF_CONFIG_BIASING || t == RMP2_LEAF_JOINT_DAMPING || t == RMP2_LEAF_CSPACE_BIASING) T.precondition = 0;
   }
+  // tuning hooks, read once per tree (never on the step path); rmp2_tree_set_option overrides them
+  if (getenv("RMP2_DISABLE_TMA")) tr->use_tma = false;
+  if (const char* v = getenv("RMP2_SPLIT_RESOLVE")) tr->split_resolve = (v[0] == '1') ? 1 : 0;
+  if (const char* v = getenv("RMP2_FORCE_BLOCK")) {
+    const int b = atoi(v);
+    if (b == 32 || b == 64 || b == 128) tr->force_block = b;
+  }
+  if (const char* v = getenv("RMP2_CHUNK_ENVS")) tr->chunk_envs = std::max(0LL, atoll(v));
   tr->sph.n_slots = T.n_sphere_slots;
   if (T.n_sphere_slots > 0) {
     // E environments per block: E * L threads <= 128, E <= 32 (box rows), shared memory bounded
@@ -440,8 +460,10 @@ void rmp2_tree_destroy(rmp2_tree* tree) {
     if (s.buf) cudaFree(s.buf);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
+  if (tree->spec || tree->rec || tree->mf || tree->fb) cudaDeviceSynchronize();   // queued steps may still use them
   if (tree->rec) cudaFree(tree->rec);
   if (tree->mf) cudaFree(tree->mf);
+  if (tree->fb) cudaFree(tree->fb);
   rmp2_jit_destroy(tree->spec);
   for (auto& c : tree->clock)
     for (auto ev : c.pending) cudaEventDestroy(ev);
@@ -456,8 +478,10 @@ int rmp2_tree_specialize(rmp2_tree* tree, int32_t flags) {
   if (rmp2_jit_build(tree->tab, rmp2_pick_width(tree->tab.n), compile_only, &m, err) != 0)
     return fail(err.rfind("NVRTC not", 0) == 0 ? RMP2_ERR_UNSUPPORTED : RMP2_ERR_CUDA, "rmp2_tree_specialize: " + err);
   if (!compile_only) {
+    if (tree->spec) cudaDeviceSynchronize();      // kernels of the old module may still be queued
     rmp2_jit_destroy(tree->spec);
     tree->spec = m;
+    tree->respecialize = true;
   }
   return RMP2_OK;
 }
@@ -482,9 +506,16 @@ int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* 
   if (L.sphere_slot >= 0)
     fill_sphere_row(*leaf, tree->sph.p[L.sphere_slot]);
   tree->leaves[index] = *leaf;
-  if (tree->spec) {                       // the tables are baked into the specialised kernels: drop them
+  if (tree->spec) {
+    // The tables are compile-time constants of the specialised kernels: rebuild them for the new values (NVRTC,
+    // tens of milliseconds once the compiler library is loaded), so that the reference idiom
+    // `target_rmp.goal = ...` keeps the fast path.  If the rebuild fails the generic kernels take over.
+    SpecModule* m = nullptr;
+    std::string err;
+    const int jrc = rmp2_jit_build(tree->tab, rmp2_pick_width(tree->tab.n), false, &m, err);
+    cudaDeviceSynchronize();              // steps queued with the old module finish before it is unloaded
     rmp2_jit_destroy(tree->spec);
-    tree->spec = nullptr;
+    tree->spec = (jrc == 0) ? m : nullptr;
   }
   return RMP2_OK;
 }
@@ -494,20 +525,16 @@ int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* 
 // ------------------------------------------------------------------------------------ step launch
 namespace {
 
-int pick_block(long long B) {
-  if (const char* v = getenv("RMP2_FORCE_BLOCK")) {        // tuning hook: 32, 64 or 128 threads per block
-    const int b = atoi(v);
-    if (b == 32 || b == 64 || b == 128) return b;
-  }
+int pick_block(const rmp2_tree* tree, long long B) {
+  if (tree->force_block) return tree->force_block;
   return (B >= 148LL * 4 * 128) ? 128 : (B >= 148LL * 4 * 64 ? 64 : 32);
 }
 
-// The staged (TMA bulk-copy) sphere path needs 16-byte aligned rows and two stages of E rows in shared memory.
+// The staged (TMA bulk-copy) sphere path needs one tile of E rows (+ barrier) in shared memory.
 bool tma_eligible(const rmp2_tree* tree, const StepArgs& A) {
   const int O = A.n_spheres;
-  if (getenv("RMP2_DISABLE_TMA")) return false;
-  const size_t smem = rmp2_spheres_smem(tree->sph, O, true);
-  return O > 0 && A.spheres != nullptr && ((uintptr_t)A.spheres % 16) == 0 && smem <= 96 * 1024;
+  if (!tree->use_tma || O <= 0 || A.spheres == nullptr) return false;
+  return rmp2_spheres_smem(tree->sph, O, true) <= 96 * 1024;
 }
 
 struct ScopedClock {               // brackets one launch with events when profiling is on
@@ -517,6 +544,7 @@ struct ScopedClock {               // brackets one launch with events when profi
   ScopedClock(rmp2_tree* tree, int which, cudaStream_t s) : stream(s) {
     if (!tree->profiling) return;
     c = &tree->clock[which];
+    if (c->pending.size() >= 2 * 4096) drain(*c);       // bounded: fold finished pairs into the totals
     cudaEvent_t start;
     cudaEventCreate(&start);
     cudaEventCreate(&stop);
@@ -526,6 +554,20 @@ struct ScopedClock {               // brackets one launch with events when profi
   }
   ~ScopedClock() {
     if (c) cudaEventRecord(stop, stream);
+  }
+  static cudaError_t drain(KernelClock& c) {
+    for (size_t i = 0; i + 1 < c.pending.size(); i += 2) {
+      cudaError_t e = cudaEventSynchronize(c.pending[i + 1]);
+      if (e != cudaSuccess) return e;
+      float t = 0.f;
+      cudaEventElapsedTime(&t, c.pending[i], c.pending[i + 1]);
+      c.ms += t;
+      c.launches += 1;
+      cudaEventDestroy(c.pending[i]);
+      cudaEventDestroy(c.pending[i + 1]);
+    }
+    c.pending.clear();
+    return cudaSuccess;
   }
 };
 
@@ -549,6 +591,9 @@ int build_args(const rmp2_tree* tree, const rmp2_step_io* io, StepArgs& A) {
   if (tree->tab.uses_spheres && io->n_spheres > 0 && !io->spheres)
     return fail(RMP2_ERR_INVALID, "n_spheres > 0 but spheres is NULL");
   if (io->n_spheres < 0) return fail(RMP2_ERR_INVALID, "n_spheres must be >= 0");
+  // sphere rows are read 16 bytes at a time (TMA bulk copies / LDG.128)
+  if (A.spheres && ((uintptr_t)A.spheres % 16) != 0)
+    return fail(RMP2_ERR_INVALID, "io.spheres must be 16-byte aligned (rows of float4)");
   if (io->n_pair_sets != tree->n_pair_sets)
     return fail(RMP2_ERR_INVALID, "io.n_pair_sets (" + std::to_string(io->n_pair_sets) + ") != explicit-pair leaves of the tree (" +
                                       std::to_string(tree->n_pair_sets) + ")");
@@ -565,11 +610,11 @@ int build_args(const rmp2_tree* tree, const rmp2_step_io* io, StepArgs& A) {
   return RMP2_OK;
 }
 
-// One control step over A.B environments on `stream`, with `rec` as scratch for the sphere records.
+// One control step over A.B environments on `stream`; A.rec / A.mf / A.fb are the scratch of this chunk.
 int launch_chunk(rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
   if (A.B == 0) return RMP2_OK;
   const StepTables& T = tree->tab;
-  const int block = pick_block(A.B);
+  const int block = pick_block(tree, A.B);
   cudaError_t e;
   std::string jit_err;
   if (T.n_sphere_slots > 0 && A.n_spheres > 0) {
@@ -594,14 +639,14 @@ int launch_chunk(rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
   {
     ScopedClock clk(tree, 2, stream);
     if (tree->spec)
-      e = rmp2_jit_launch(tree->spec, A.mf ? 2 : 1, A, (unsigned)((A.B + block - 1) / block), block,
+      e = rmp2_jit_launch(tree->spec, A.split ? 2 : 1, A, (unsigned)((A.B + block - 1) / block), block,
                           rmp2_step_smem(T, block), stream, jit_err);
     else
       e = rmp2_launch_step(T, A, block, stream);
   }
   if (e != cudaSuccess) return cuda_fail(e, (std::string("rmp2_step_kernel launch") + (jit_err.empty() ? "" : ": " + jit_err)).c_str());
   g_launches.fetch_add(1);
-  if (A.mf) {
+  if (A.split) {
     {
       ScopedClock clk(tree, 3, stream);
       e = rmp2_launch_resolve(T, A, block, stream);
@@ -609,59 +654,82 @@ int launch_chunk(rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
     if (e != cudaSuccess) return cuda_fail(e, "rmp2_resolve_kernel launch");
     g_launches.fetch_add(1);
   }
+  {
+    ScopedClock clk(tree, 4, stream);
+    e = rmp2_launch_fallback(T, A, 148 * 2, stream);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "rmp2_resolve_fallback_kernel launch");
+  g_launches.fetch_add(1);
   return RMP2_OK;
 }
 
-// Large batches run the resolve as its own kernel (smaller code and register footprint for both
-// halves); small ones keep it fused (one launch less, latency).  RMP2_SPLIT_RESOLVE=0/1 overrides.
-bool split_resolve(long long B) {
-  const char* v = getenv("RMP2_SPLIT_RESOLVE");
-  if (v) return v[0] == '1';
+// Large batches run the resolve as its own kernel (smaller register footprint for both halves); small ones
+// keep it fused (one launch less, latency).  RMP2_OPT_SPLIT_RESOLVE overrides.
+bool split_resolve(const rmp2_tree* tree, long long B) {
+  if (tree->split_resolve >= 0) return tree->split_resolve == 1;
   return B >= 32768;
 }
+
+long long chunk_envs(const rmp2_tree* tree) { return tree->chunk_envs > 0 ? tree->chunk_envs : RMP2_STEP_CHUNK; }
 
 size_t mf_floats_for(const rmp2_tree* tree, long long B) {
   const int N = rmp2_pick_width(tree->tab.n);
   return (size_t)B * (N * N + N);
 }
 
+size_t fb_ints_for(long long B) { return (size_t)B + 4; }
+
 size_t rec_floats_for(const rmp2_tree* tree, long long B, int n_spheres) {
   if (tree->tab.n_sphere_slots == 0 || n_spheres <= 0) return 0;
   return (size_t)B * tree->tab.n_sphere_slots * RMP2_REC_FLOATS;
+}
+
+// Size the tree's scratch for chunks of `chunk` environments.  Stream-ordered (cudaMallocAsync / cudaFreeAsync
+// on the caller's stream): no device-wide stall; inside a stream capture growing is refused -- reserve first.
+int ensure_scratch(rmp2_tree* tree, long long chunk, int n_spheres, cudaStream_t stream) {
+  const size_t need_rec = rec_floats_for(tree, chunk, n_spheres);
+  const size_t need_mf = mf_floats_for(tree, chunk);
+  const size_t need_fb = fb_ints_for(chunk);
+  if (need_rec <= tree->rec_floats && need_mf <= tree->mf_floats && need_fb <= tree->fb_ints) return RMP2_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+    return fail(RMP2_ERR_INVALID, "the tree's scratch must grow but the stream is being captured: call rmp2_tree_reserve "
+                                  "(or run one step) before capturing");
+  cudaError_t e;
+  auto grow = [&](void** ptr, size_t* have, size_t need, size_t elem) -> cudaError_t {
+    if (need <= *have) return cudaSuccess;
+    if (*ptr) {
+      cudaError_t e2 = cudaFreeAsync(*ptr, stream);       // ordered after the steps already queued on this stream
+      if (e2 != cudaSuccess) return e2;
+      *ptr = nullptr;
+      *have = 0;
+    }
+    cudaError_t e2 = cudaMallocAsync(ptr, need * elem, stream);
+    if (e2 == cudaSuccess) *have = need;
+    return e2;
+  };
+  if ((e = grow((void**)&tree->rec, &tree->rec_floats, need_rec, sizeof(float))) != cudaSuccess)
+    return cuda_fail(e, "allocating the sphere-record scratch");
+  if ((e = grow((void**)&tree->mf, &tree->mf_floats, need_mf, sizeof(float))) != cudaSuccess)
+    return cuda_fail(e, "allocating the (M, f) scratch");
+  const size_t had_fb = tree->fb_ints;
+  if ((e = grow((void**)&tree->fb, &tree->fb_ints, need_fb, sizeof(int32_t))) != cudaSuccess)
+    return cuda_fail(e, "allocating the fallback work list");
+  if (tree->fb_ints != had_fb) {
+    e = cudaMemsetAsync(tree->fb, 0, 2 * sizeof(int32_t), stream);      // list length and block ticket
+    if (e != cudaSuccess) return cuda_fail(e, "clearing the fallback work list");
+  }
+  return RMP2_OK;
 }
 
 // Device-pointer step, chunked so that the scratch stays bounded.
 int launch(rmp2_tree* tree, const StepArgs& A0, cudaStream_t stream) {
   const long long B = A0.B;
   if (B == 0) return RMP2_OK;
-  const long long chunk = std::min<long long>(B, RMP2_STEP_CHUNK);
-  const size_t need = rec_floats_for(tree, chunk, A0.n_spheres);
-  if (need > tree->rec_floats) {
-    if (tree->rec) {
-      cudaError_t e = cudaDeviceSynchronize();      // earlier steps may still use the old scratch
-      if (e != cudaSuccess) return cuda_fail(e, "synchronize before growing the scratch");
-      cudaFree(tree->rec);
-      tree->rec = nullptr;
-      tree->rec_floats = 0;
-    }
-    cudaError_t e = cudaMalloc(&tree->rec, need * sizeof(float));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc of the sphere-record scratch");
-    tree->rec_floats = need;
-  }
-  const bool split = split_resolve(chunk);
-  const size_t need_mf = split ? mf_floats_for(tree, chunk) : 0;
-  if (need_mf > tree->mf_floats) {
-    if (tree->mf) {
-      cudaError_t e = cudaDeviceSynchronize();
-      if (e != cudaSuccess) return cuda_fail(e, "synchronize before growing the scratch");
-      cudaFree(tree->mf);
-      tree->mf = nullptr;
-      tree->mf_floats = 0;
-    }
-    cudaError_t e = cudaMalloc(&tree->mf, need_mf * sizeof(float));
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc of the (M, f) scratch");
-    tree->mf_floats = need_mf;
-  }
+  const long long chunk = std::min<long long>(B, chunk_envs(tree));
+  int rc = ensure_scratch(tree, chunk, A0.n_spheres, stream);
+  if (rc != RMP2_OK) return rc;
+  const bool split = split_resolve(tree, chunk);
   const int n = tree->tab.n;
   for (long long e0 = 0; e0 < B; e0 += chunk) {
     StepArgs A = A0;
@@ -675,8 +743,10 @@ int launch(rmp2_tree* tree, const StepArgs& A0, cudaStream_t stream) {
     if (A0.spheres) A.spheres = A0.spheres + e0 * (long long)A0.n_spheres * 4;
     if (A0.pairs) A.pairs = A0.pairs + e0 * (long long)A0.pair_total * RMP2_PAIR_FLOATS;
     A.rec = tree->rec;
-    A.mf = split ? tree->mf : nullptr;
-    int rc = launch_chunk(tree, A, stream);
+    A.mf = tree->mf;
+    A.fb = tree->fb;
+    A.split = split ? 1 : 0;
+    rc = launch_chunk(tree, A, stream);
     if (rc != RMP2_OK) return rc;
   }
   return RMP2_OK;
@@ -686,16 +756,26 @@ int launch(rmp2_tree* tree, const StepArgs& A0, cudaStream_t stream) {
 
 extern "C" {
 
+int rmp2_tree_reserve(rmp2_tree* tree, int64_t B, int32_t n_spheres, void* stream) {
+  if (!tree) return fail(RMP2_ERR_INVALID, "null argument");
+  if (B < 0 || n_spheres < 0) return fail(RMP2_ERR_INVALID, "B and n_spheres must be >= 0");
+  if (B == 0) return RMP2_OK;
+  tree->reserved_envs = std::max<long long>(tree->reserved_envs, B);
+  tree->reserved_spheres = std::max(tree->reserved_spheres, n_spheres);
+  return ensure_scratch(tree, std::min<long long>(B, chunk_envs(tree)), n_spheres, (cudaStream_t)stream);
+}
+
 int rmp2_step(const rmp2_tree* tree, const rmp2_step_io* io, void* stream) {
   StepArgs A;
   int rc = build_args(tree, io, A);
   if (rc != RMP2_OK) return rc;
-  // the handle owns scratch that grows on demand: steps of one tree are serialised by the caller
+  // the handle owns scratch: steps of one tree are serialised by the caller (one stream at a time)
   return launch(const_cast<rmp2_tree*>(tree), A, (cudaStream_t)stream);
 }
 
 int rmp2_rollout(const rmp2_tree* tree, const rmp2_step_io* io, float* q_inout, float* qd_inout, float dt,
                  int32_t n_steps, int32_t control_every, void* stream) {
+  if (!tree || !io) return fail(RMP2_ERR_INVALID, "null argument");
   if (!q_inout || !qd_inout) return fail(RMP2_ERR_INVALID, "q_inout and qd_inout are required");
   if (n_steps <= 0 || control_every <= 0) return fail(RMP2_ERR_INVALID, "n_steps and control_every must be positive");
   rmp2_step_io tmp = *io;
@@ -737,8 +817,14 @@ int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io) {
   const size_t off_pair = off_sph + pad4((size_t)chunk * O * 4);
   const size_t off_rec = off_pair + pad4((size_t)chunk * K * RMP2_PAIR_FLOATS);
   const size_t off_mf = off_rec + pad4(rec_floats_for(tree, chunk, O));
-  const bool split = split_resolve(chunk);
-  const size_t total = off_mf + (split ? pad4(mf_floats_for(tree, chunk)) : 0);
+  const size_t off_fb = off_mf + pad4(mf_floats_for(tree, chunk));
+  const bool split = split_resolve(tree, chunk);
+  const size_t total = off_fb + pad4(fb_ints_for(chunk));
+  // on any error below: wait for the copies already queued on the caller's host buffers before returning
+  auto drain = [&]() {
+    for (auto& s : tree->stage)
+      if (s.stream) cudaStreamSynchronize(s.stream);
+  };
   for (auto& s : tree->stage) {
     if (!s.stream) {
       cudaError_t e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
@@ -752,6 +838,9 @@ int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io) {
       if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc staging");
       s.floats = total;
     }
+    // (re)laid-out staging: the work list of this slot starts empty
+    cudaError_t e = cudaMemsetAsync(s.buf + off_fb, 0, 2 * sizeof(int32_t), s.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "clearing the fallback work list");
   }
   int slot = 0;
   for (long long e0 = 0; e0 < B; e0 += chunk, slot = (slot + 1) % 3) {
@@ -761,7 +850,10 @@ int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io) {
 #define RMP2_H2D(dst, src, count)                                                                         \
   if ((count) > 0) {                                                                                       \
     e = cudaMemcpyAsync(s.buf + (dst), (src), (size_t)(count) * sizeof(float), cudaMemcpyHostToDevice, s.stream); \
-    if (e != cudaSuccess) return cuda_fail(e, "H2D copy");                                                  \
+    if (e != cudaSuccess) {                                                                                 \
+      drain();                                                                                              \
+      return cuda_fail(e, "H2D copy");                                                                      \
+    }                                                                                                       \
   }
     RMP2_H2D(off_q, io->q + e0 * n, cb * n);
     RMP2_H2D(off_qd, io->qd + e0 * n, cb * n);
@@ -778,16 +870,37 @@ int rmp2_step_host(rmp2_tree* tree, const rmp2_step_io* io) {
     A.spheres = O ? s.buf + off_sph : nullptr;
     A.pairs = K ? s.buf + off_pair : nullptr;
     A.rec = s.buf + off_rec;
-    A.mf = split ? s.buf + off_mf : nullptr;
+    A.mf = s.buf + off_mf;
+    A.fb = reinterpret_cast<int32_t*>(s.buf + off_fb);
+    A.split = split ? 1 : 0;
     rc = launch_chunk(tree, A, s.stream);
-    if (rc != RMP2_OK) return rc;
+    if (rc != RMP2_OK) {
+      drain();
+      return rc;
+    }
     e = cudaMemcpyAsync(io->qdd + e0 * n, s.buf + off_qdd, (size_t)cb * n * sizeof(float), cudaMemcpyDeviceToHost, s.stream);
-    if (e != cudaSuccess) return cuda_fail(e, "D2H copy");
+    if (e != cudaSuccess) {
+      drain();
+      return cuda_fail(e, "D2H copy");
+    }
   }
   for (auto& s : tree->stage) {
     cudaError_t e = cudaStreamSynchronize(s.stream);
     if (e != cudaSuccess) return cuda_fail(e, "rmp2_step_host");
   }
+  return RMP2_OK;
+}
+
+int rmp2_pinv_solve(int32_t n, int64_t B, const float* M, const float* f, float* x, int32_t pivot, int32_t mode,
+                    void* stream) {
+  if (!M || !f || !x) return fail(RMP2_ERR_INVALID, "M, f and x are required");
+  if (n <= 0 || n > RMP2_MAX_JOINTS) return fail(RMP2_ERR_INVALID, "n out of range");
+  if (mode != 0 && mode != 1) return fail(RMP2_ERR_INVALID, "mode must be 0 (as in the step) or 1 (Jacobi only)");
+  if (B <= 0) return B == 0 ? RMP2_OK : fail(RMP2_ERR_INVALID, "B must be >= 0");
+  const float rcond = (float)(10.0 * n * 1.1920928955078125e-07);
+  cudaError_t e = rmp2_launch_pinv(n, rcond, pivot != 0, mode, B, M, f, x, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(e, "rmp2_pinv_solve launch");
+  g_launches.fetch_add(1);
   return RMP2_OK;
 }
 
@@ -822,6 +935,8 @@ int rmp2_obstacle_feed(const rmp2_robot* rb, const int32_t* frames, int32_t n_fr
   if (n_frames <= 0 || n_frames > RMP2_MAX_LEAVES) return fail(RMP2_ERR_INVALID, "n_frames out of range");
   if (n_spheres < 0 || n_capsules < 0 || (n_spheres > 0 && !spheres) || (n_capsules > 0 && !capsules))
     return fail(RMP2_ERR_INVALID, "obstacle arrays do not match their counts");
+  if ((spheres && ((uintptr_t)spheres % 16) != 0) || (capsules && ((uintptr_t)capsules % 16) != 0))
+    return fail(RMP2_ERR_INVALID, "spheres and capsules must be 16-byte aligned (rows of float4)");
   if (B <= 0) return B == 0 ? RMP2_OK : fail(RMP2_ERR_INVALID, "B must be >= 0");
   // marker leaves make the tree compiler produce the pruned, depth-first frame table
   std::vector<rmp2_leaf_desc> marks(n_frames);
@@ -883,10 +998,11 @@ int rmp2_leaf_evaluate(const rmp2_leaf_desc* leaf, int32_t m, int64_t K, const f
 int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_spheres, int32_t* regs, int32_t* smem_bytes,
                           int32_t* blocks_per_sm, int32_t* block_threads) {
   if (!tree) return fail(RMP2_ERR_INVALID, "null argument");
-  if (which < 0 || which > 4)
-    return fail(RMP2_ERR_INVALID, "which must be 0 (frames), 1 (spheres), 2 (step, fused), 3 (step, split) or 4 (resolve)");
+  if (which < 0 || which > 5)
+    return fail(RMP2_ERR_INVALID, "which must be 0 (frames), 1 (spheres), 2 (step, fused), 3 (step, split), 4 (resolve) or "
+                                  "5 (resolve fallback)");
   int block = RMP2_BLOCK_THREADS;
-  size_t smem = (which == 4) ? 0 : (which >= 2 ? rmp2_step_smem(tree->tab, block)
+  size_t smem = (which >= 4) ? 0 : (which >= 2 ? rmp2_step_smem(tree->tab, block)
                                                  : (size_t)tree->tab.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float));
   bool use_tma = false;
   if (which == 1) {
@@ -912,11 +1028,29 @@ int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_sphere
 
 int rmp2_tree_set_option(rmp2_tree* tree, int32_t option, int32_t value) {
   if (!tree) return fail(RMP2_ERR_INVALID, "null argument");
-  if (option == RMP2_OPT_EARLY_OUT) {
-    tree->early_out = value != 0;
-    return RMP2_OK;
+  switch (option) {
+    case RMP2_OPT_EARLY_OUT:
+      tree->early_out = value != 0;
+      return RMP2_OK;
+    case RMP2_OPT_TMA:
+      tree->use_tma = value != 0;
+      return RMP2_OK;
+    case RMP2_OPT_SPLIT_RESOLVE:
+      if (value < -1 || value > 1) return fail(RMP2_ERR_INVALID, "RMP2_OPT_SPLIT_RESOLVE takes -1 (by batch size), 0 or 1");
+      tree->split_resolve = value;
+      return RMP2_OK;
+    case RMP2_OPT_BLOCK_THREADS:
+      if (value != 0 && value != 32 && value != 64 && value != 128)
+        return fail(RMP2_ERR_INVALID, "RMP2_OPT_BLOCK_THREADS takes 0 (by batch size), 32, 64 or 128");
+      tree->force_block = value;
+      return RMP2_OK;
+    case RMP2_OPT_CHUNK_ENVS:
+      if (value < 0) return fail(RMP2_ERR_INVALID, "RMP2_OPT_CHUNK_ENVS must be >= 0");
+      tree->chunk_envs = value;
+      return RMP2_OK;
+    default:
+      return fail(RMP2_ERR_INVALID, "unknown option " + std::to_string(option));
   }
-  return fail(RMP2_ERR_INVALID, "unknown option " + std::to_string(option));
 }
 
 int rmp2_tree_profile(rmp2_tree* tree, int32_t enable) {
@@ -927,19 +1061,10 @@ int rmp2_tree_profile(rmp2_tree* tree, int32_t enable) {
 
 int rmp2_tree_profile_read(rmp2_tree* tree, double* ms, int64_t* launches) {
   if (!tree || !ms || !launches) return fail(RMP2_ERR_INVALID, "null argument");
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < RMP2_N_CLOCKS; ++k) {
     KernelClock& c = tree->clock[k];
-    for (size_t i = 0; i + 1 < c.pending.size(); i += 2) {
-      cudaError_t e = cudaEventSynchronize(c.pending[i + 1]);
-      if (e != cudaSuccess) return cuda_fail(e, "rmp2_tree_profile_read");
-      float t = 0.f;
-      cudaEventElapsedTime(&t, c.pending[i], c.pending[i + 1]);
-      c.ms += t;
-      c.launches += 1;
-      cudaEventDestroy(c.pending[i]);
-      cudaEventDestroy(c.pending[i + 1]);
-    }
-    c.pending.clear();
+    cudaError_t e = ScopedClock::drain(c);
+    if (e != cudaSuccess) return cuda_fail(e, "rmp2_tree_profile_read");
     ms[k] = c.ms;
     launches[k] = c.launches;
     c.ms = 0.0;

@@ -28,6 +28,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "rmp2_tree_kernels.cuh"
 #include "rmp2_launch.h"
 
@@ -89,6 +92,9 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 // keep the warps of an SM spread over the phases of the loop.
 #ifndef RMP2_SPHERES_MIN_BLOCKS
 #define RMP2_SPHERES_MIN_BLOCKS 5     // resident blocks per SM the register allocation aims at (<= 102 registers)
+#endif
+#ifndef RMP2_SQRT_NEWTON
+#define RMP2_SQRT_NEWTON 1            // refine the pair distance to correctly-rounded accuracy (4 lane operations per pair)
 #endif
 #ifndef RMP2_SPHERES_STEPS_PER_TRIP
 #define RMP2_SPHERES_STEPS_PER_TRIP 4 // packed (two-sphere) steps per loop trip
@@ -166,7 +172,17 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
     // |r|^2 + 1e-24: a centre on the frame origin stays finite without a separate clamp
     const float2 dc2 = __ffma2_rn(rx, rx, __ffma2_rn(ry, ry, __ffma2_rn(rz, rz, bc2(1e-24f))));
     const float2 inv_dc = make_float2(fast_rsqrt(dc2.x), fast_rsqrt(dc2.y));
+#if RMP2_SQRT_NEWTON
+    // |r| to ~0.5 ulp: one Newton step on dc = dc2 * rsqrt(dc2) (the residual dc2 - dc^2 is exact in an FMA).
+    // MUFU.RSQ alone is good to 2 ulp, and the leaf amplifies an error of the distance by 1 / repulsion_std_dev
+    // (= 100 with the experiments' gains, rmp2.py:189) -- enough to miss the 1e-5 parity bar for close spheres.
+    const float2 dc0 = __fmul2_rn(dc2, inv_dc);
+    const float2 res = __ffma2_rn(neg2(dc0), dc0, dc2);
+    const float2 dc = __ffma2_rn(res, __fmul2_rn(inv_dc, bc2(0.5f)), dc0);
+    const float2 sd = make_float2(dc.x - s0.w, dc.y - s1.w);                                   // signed surface distance
+#else
     const float2 sd = make_float2(fmaf(dc2.x, inv_dc.x, -s0.w), fmaf(dc2.y, inv_dc.y, -s1.w));   // signed surface distance
+#endif
     const float2 sgn = make_float2(copysignf(inv_dc.x, sd.x), copysignf(inv_dc.y, sd.y));       // inside: normal flips
     const float2 d = make_float2(fabsf(sd.x) + 1e-12f, fabsf(sd.y) + 1e-12f);                   // > 0 (FADD, not FMNMX)
     const float2 inv_d = make_float2(fast_rcp(d.x), fast_rcp(d.y));
@@ -237,9 +253,10 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, kSplit ? RMP2_SPLIT_MIN_BL
   step_body<N, kSplit>(T, A);
 }
 
-// -------------------------------------------------------------------------------- resolve kernel
-// kQr: precondition with a pivoted QR (trees without an isotropic metric leaf, i.e. possibly
-// rank-deficient: fewer Jacobi sweeps); well-conditioned trees skip it.
+// -------------------------------------------------------------------------------- resolve kernels
+// Stage 1 (split mode): qdd = pinv(M) f by the direct solves of rmp2_step.cuh, environments that do not qualify
+// are handed to the fallback kernel (see "resolve hand-off" in rmp2_tree_kernels.cuh).
+// kQr: trees without an isotropic metric leaf, i.e. possibly rank deficient (pivoted QR + rank-revealing solve).
 template <int N, bool kQr>
 __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_RESOLVE_MIN_BLOCKS(N))
     rmp2_resolve_kernel(const __grid_constant__ ResolveArgs R, const __grid_constant__ StepArgs A) {
@@ -248,7 +265,7 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_RESOLVE_MIN_BLOCKS(N)
   const long long e = active ? env : A.B - 1;
   const int n = R.n;
   const bool rollout = A.n_sim_steps > 0;
-  float M[N][N], f[N], qdd[N];
+  float M[N][N], f[N];
   const float* in = A.mf + e;
 #pragma unroll
   for (int i = 0; i < N; ++i)
@@ -256,14 +273,90 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_RESOLVE_MIN_BLOCKS(N)
     for (int j = 0; j < N; ++j) M[i][j] = __ldg(in + (size_t)(i * N + j) * A.B);
 #pragma unroll
   for (int i = 0; i < N; ++i) f[i] = __ldg(in + (size_t)(N * N + i) * A.B);
-  resolve_pinv<N, kQr>(M, f, n, R.rcond, qdd);
   float q[N], qd[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
     q[j] = (rollout && j < n) ? A.q_rw[e * n + j] : 0.f;
     qd[j] = (rollout && j < n) ? A.qd_rw[e * n + j] : 0.f;
   }
-  finish_step<N>(A, n, e, active, rollout, q, qd, qdd);
+  resolve_or_defer<N, kQr>(A, M, f, n, R.rcond, e, active, rollout, q, qd);
+}
+
+// Stage 2: truncated SVD by one-sided Jacobi for the environments on the work list, starting from the
+// factorised problem [R | Q^T f | perm] stage 1 left in the (M, f) scratch.  Launched with a fixed grid after
+// every step; blocks beyond the list exit at once, and the last block to finish clears the list for the next
+// step (so a captured CUDA graph replays correctly and no memset is needed).
+template <int N, bool kQr>
+__global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_FALLBACK_MIN_BLOCKS(N))
+    rmp2_resolve_fallback_kernel(const __grid_constant__ ResolveArgs R, const __grid_constant__ StepArgs A) {
+  __shared__ int s_count;
+  if (threadIdx.x == 0) s_count = *reinterpret_cast<volatile int*>(A.fb);
+  __syncthreads();
+  const int count = s_count;
+  const int n = R.n;
+  const bool rollout = A.n_sim_steps > 0;
+  for (int base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;
+    const bool valid = i < count;                // lanes beyond the list idle through the sweeps
+    const long long e = A.fb[2 + (valid ? i : count - 1)];
+    float G[N][N], y[N], xs[N], qdd[N];
+    int perm[N];
+    const float* in = A.mf + e;
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int c = 0; c < N; ++c) G[r][c] = (c >= r) ? in[(size_t)(k++) * A.B] : 0.f;
+#pragma unroll
+    for (int r = 0; r < N; ++r) y[r] = in[(size_t)(k++) * A.B];
+#pragma unroll
+    for (int r = 0; r < N; ++r) perm[r] = __float_as_int(in[(size_t)(k++) * A.B]);
+#pragma unroll
+    for (int r = 0; r < N; ++r) xs[r] = 0.f;
+    resolve_jacobi<N, kQr>(G, y, perm, !valid, xs, R.rcond, qdd);
+    float q[N], qd[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      q[j] = (rollout && j < n) ? A.q_rw[e * n + j] : 0.f;
+      qd[j] = (rollout && j < n) ? A.qd_rw[e * n + j] : 0.f;
+    }
+    finish_step<N>(A, n, e, valid, rollout, q, qd, qdd);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int ticket = atomicAdd(A.fb + 1, 1);
+    if (ticket == (int)gridDim.x - 1) {          // every block has read the length: clear for the next step
+      A.fb[0] = 0;
+      A.fb[1] = 0;
+      __threadfence();
+    }
+  }
+}
+
+// x = pinv(M) f for row-major M [B][n][n], f [B][n] -- the resolve on its own (rmp2_pinv_solve; reference:
+// rmp.py:153-154).  mode 0: as in the step (direct where provable, Jacobi otherwise); mode 1: Jacobi for every
+// environment (cross-check of the two solvers).
+template <int N, bool kQr, bool kDirect>
+__global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
+    rmp2_pinv_kernel(int n, float rcond, long long B, const float* __restrict__ Min, const float* __restrict__ fin,
+                     float* __restrict__ x) {
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = env < B;
+  const long long e = active ? env : B - 1;
+  float M[N][N], f[N], out[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) M[i][j] = (i < n && j < n) ? Min[(e * n + i) * n + j] : 0.f;
+    f[i] = (i < n) ? fin[e * n + i] : 0.f;
+  }
+  resolve_pinv<N, kQr, kDirect>(M, f, n, rcond, out);
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (j < n) x[e * n + j] = out[j];
+  }
 }
 
 // --------------------------------------------------------------------------------- feed kernel
@@ -518,6 +611,20 @@ __global__ void __launch_bounds__(128)
 }
 
 // -------------------------------------------------------------------------------- host launchers
+// Opt a kernel in to `smem` bytes of dynamic shared memory (needed above 48 KB).  The largest size granted per
+// kernel is remembered, so the steady state makes no runtime call (the attribute only ever grows).
+static cudaError_t allow_dynamic_smem(const void* fn, size_t smem) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, size_t> granted;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = granted[fn];
+  if (smem <= have) return cudaSuccess;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) have = smem;
+  return e;
+}
+
 size_t rmp2_step_smem(const StepTables& T, int block) {
   return ((size_t)T.n_slots * RMP2_CHAIN_FLOATS + 6 * (size_t)rmp2_pick_width(T.n)) * block * sizeof(float);
 }
@@ -541,6 +648,11 @@ cudaError_t rmp2_launch_frames(const StepTables& T, const StepArgs& A, int block
   const long long blocks = (A.B + block - 1) / block;
   if (blocks <= 0) return cudaSuccess;
   const size_t smem = (size_t)T.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaSuccess;
+    RMP2_DISPATCH_N(T.n, (e = allow_dynamic_smem((const void*)rmp2_frames_kernel<NN>, smem)));
+    if (e != cudaSuccess) return e;
+  }
   RMP2_DISPATCH_N(T.n, (rmp2_frames_kernel<NN><<<(unsigned)blocks, block, smem, stream>>>(T, A)));
   return cudaGetLastError();
 }
@@ -560,7 +672,7 @@ cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, bool 
   const unsigned nb = (unsigned)blocks;
   if (use_tma) {
     const void* fn = A.early_out ? (const void*)rmp2_spheres_kernel<true, true> : (const void*)rmp2_spheres_kernel<true, false>;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_dynamic_smem(fn, smem);
     if (e != cudaSuccess) return e;
     if (A.early_out) rmp2_spheres_kernel<true, true><<<nb, threads, smem, stream>>>(ST, A);
     else rmp2_spheres_kernel<true, false><<<nb, threads, smem, stream>>>(ST, A);
@@ -575,7 +687,13 @@ cudaError_t rmp2_launch_step(const StepTables& T, const StepArgs& A, int block, 
   const long long blocks = (A.B + block - 1) / block;
   if (blocks <= 0) return cudaSuccess;
   const size_t smem = rmp2_step_smem(T, block);
-  if (A.mf) {
+  cudaError_t e = cudaSuccess;
+  if (smem > 48 * 1024) {
+    if (A.split) { RMP2_DISPATCH_N(T.n, (e = allow_dynamic_smem((const void*)rmp2_step_kernel<NN, true>, smem))); }
+    else { RMP2_DISPATCH_N(T.n, (e = allow_dynamic_smem((const void*)rmp2_step_kernel<NN, false>, smem))); }
+    if (e != cudaSuccess) return e;
+  }
+  if (A.split) {
     RMP2_DISPATCH_N(T.n, (rmp2_step_kernel<NN, true><<<(unsigned)blocks, block, smem, stream>>>(T, A)));
   } else {
     RMP2_DISPATCH_N(T.n, (rmp2_step_kernel<NN, false><<<(unsigned)blocks, block, smem, stream>>>(T, A)));
@@ -593,6 +711,37 @@ cudaError_t rmp2_launch_resolve(const StepTables& T, const StepArgs& A, int bloc
     RMP2_DISPATCH_N(T.n, (rmp2_resolve_kernel<NN, true><<<(unsigned)blocks, block, 0, stream>>>(R, A)));
   } else {
     RMP2_DISPATCH_N(T.n, (rmp2_resolve_kernel<NN, false><<<(unsigned)blocks, block, 0, stream>>>(R, A)));
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t rmp2_launch_fallback(const StepTables& T, const StepArgs& A, int max_blocks, cudaStream_t stream) {
+  const int block = RMP2_BLOCK_THREADS;
+  long long blocks = (A.B + block - 1) / block;
+  if (blocks <= 0) return cudaSuccess;
+  if (blocks > max_blocks) blocks = max_blocks;
+  ResolveArgs R;
+  R.n = T.n;
+  R.rcond = T.rcond;
+  if (T.precondition) {
+    RMP2_DISPATCH_N(T.n, (rmp2_resolve_fallback_kernel<NN, true><<<(unsigned)blocks, block, 0, stream>>>(R, A)));
+  } else {
+    RMP2_DISPATCH_N(T.n, (rmp2_resolve_fallback_kernel<NN, false><<<(unsigned)blocks, block, 0, stream>>>(R, A)));
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t rmp2_launch_pinv(int n, float rcond, bool pivot, int mode, long long B, const float* M, const float* f,
+                             float* x, cudaStream_t stream) {
+  const long long blocks = (B + RMP2_BLOCK_THREADS - 1) / RMP2_BLOCK_THREADS;
+  if (blocks <= 0) return cudaSuccess;
+  const unsigned nb = (unsigned)blocks;
+  if (mode == 1) {
+    if (pivot) { RMP2_DISPATCH_N(n, (rmp2_pinv_kernel<NN, true, false><<<nb, RMP2_BLOCK_THREADS, 0, stream>>>(n, rcond, B, M, f, x))); }
+    else { RMP2_DISPATCH_N(n, (rmp2_pinv_kernel<NN, false, false><<<nb, RMP2_BLOCK_THREADS, 0, stream>>>(n, rcond, B, M, f, x))); }
+  } else {
+    if (pivot) { RMP2_DISPATCH_N(n, (rmp2_pinv_kernel<NN, true, true><<<nb, RMP2_BLOCK_THREADS, 0, stream>>>(n, rcond, B, M, f, x))); }
+    else { RMP2_DISPATCH_N(n, (rmp2_pinv_kernel<NN, false, true><<<nb, RMP2_BLOCK_THREADS, 0, stream>>>(n, rcond, B, M, f, x))); }
   }
   return cudaGetLastError();
 }
@@ -623,10 +772,14 @@ cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, si
     RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_step_kernel<NN, true>),
                         e = (e == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                                                      blocks_per_sm, rmp2_step_kernel<NN, true>, block, smem) : e));
-  } else {
+  } else if (which == 4) {
     RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_resolve_kernel<NN, true>),
                         e = (e == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                                                      blocks_per_sm, rmp2_resolve_kernel<NN, true>, block, 0) : e));
+  } else {
+    RMP2_DISPATCH_N(n, (e = cudaFuncGetAttributes(&attr, rmp2_resolve_fallback_kernel<NN, true>),
+                        e = (e == cudaSuccess) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                                                     blocks_per_sm, rmp2_resolve_fallback_kernel<NN, true>, block, 0) : e));
   }
   if (e != cudaSuccess) return e;
   *regs = attr.numRegs;
@@ -638,6 +791,11 @@ cudaError_t rmp2_launch_feed(const StepTables& T, const FeedArgs& A, cudaStream_
   const long long blocks = (A.B + block - 1) / block;
   if (blocks <= 0) return cudaSuccess;
   const size_t smem = (size_t)T.n_slots * RMP2_CHAIN_FLOATS * block * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaSuccess;
+    RMP2_DISPATCH_N(T.n, (e = allow_dynamic_smem((const void*)rmp2_feed_kernel<NN>, smem)));
+    if (e != cudaSuccess) return e;
+  }
   RMP2_DISPATCH_N(T.n, (rmp2_feed_kernel<NN><<<(unsigned)blocks, block, smem, stream>>>(T, A)));
   return cudaGetLastError();
 }

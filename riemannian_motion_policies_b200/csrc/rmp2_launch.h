@@ -25,7 +25,10 @@ size_t rmp2_spheres_smem(const SphereTables& ST, int n_spheres, bool use_tma);
 cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, bool use_tma, cudaStream_t stream);
 cudaError_t rmp2_launch_step(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);
 cudaError_t rmp2_launch_resolve(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);
-// which: 0 frames, 1 spheres, 2 step (fused resolve), 3 step (split), 4 resolve
+cudaError_t rmp2_launch_fallback(const StepTables& T, const StepArgs& A, int max_blocks, cudaStream_t stream);
+cudaError_t rmp2_launch_pinv(int n, float rcond, bool pivot, int mode, long long B, const float* M, const float* f,
+                             float* x, cudaStream_t stream);
+// which: 0 frames, 1 spheres, 2 step (fused resolve), 3 step (split), 4 resolve, 5 resolve fallback (Jacobi)
 cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, size_t smem, int* regs,
                                    int* blocks_per_sm);
 cudaError_t rmp2_launch_feed(const StepTables& T, const FeedArgs& A, cudaStream_t stream);

@@ -163,6 +163,41 @@ RMP2_DEV void target_attractor(const float* __restrict__ p, const float (&x)[3],
   dir = boost * ((1.f - a) * p[TA_SMIN]);
 }
 
+// ---- orientation task map: xyz Euler angles of a frame ------------------------------------------------
+// theta = (theta_x, theta_y, theta_z) with R = R_z(theta_z) R_y(theta_y) R_x(theta_x)  (reference:
+// kinematics.py:74-96: theta_y = -asin(r20), theta_z = atan2(r10, r00), theta_x = atan2(r21, r22)).  The
+// reference differentiates this through the 4x4 matrix entries by autodiff (taskmap.py:57-67); on rotation
+// matrices that is the Euler-rate map of helper/trigonometry_helper.py:18-38, omega = H(theta) thetadot:
+//     thetadot = E omega,   E = H^-1 = 1/cb [[cg, sg, 0], [-sg cb, cg cb, 0], [cg sb, sg sb, cb]]
+//     c = d/dt(E omega) at zero joint acceleration = Edot omega + E alpha      (w, al: Chain::w, Chain::al)
+// R row-major 3x3.  E row-major.
+RMP2_DEV void euler_map(const float* __restrict__ R, const float (&w)[3], const float (&al)[3], float (&th)[3],
+                        float (&thd)[3], float (&cc)[3], float (&E)[9]) {
+  const float r00 = R[0], r10 = R[3], r20 = R[6], r21 = R[7], r22 = R[8];
+  th[0] = atan2f(r21, r22);
+  th[1] = -asinf(fminf(fmaxf(r20, -1.f), 1.f));
+  th[2] = atan2f(r10, r00);
+  const float sb = -r20;
+  const float cb = fmaxf(sqrtf(fmaxf(fmaf(-r20, r20, 1.f), 0.f)), 1e-6f);   // cos(theta_y) >= 0; gimbal-lock guard
+  const float inv_cb = 1.f / cb;
+  const float inv_h = rsqrtf(fmaxf(fmaf(r00, r00, r10 * r10), 1e-24f));
+  const float cg = r00 * inv_h, sg = r10 * inv_h;
+  const float u = fmaf(cg, w[0], sg * w[1]), v = fmaf(cg, w[1], -sg * w[0]);
+  const float ad = u * inv_cb, bd = v, gd = fmaf(sb, ad, w[2]);
+  thd[0] = ad;
+  thd[1] = bd;
+  thd[2] = gd;
+  const float ud = fmaf(cg, al[0], fmaf(sg, al[1], gd * v));
+  const float vd = fmaf(cg, al[1], fmaf(-sg, al[0], -gd * u));
+  const float add = fmaf(ad * sb, bd, ud) * inv_cb;
+  cc[0] = add;
+  cc[1] = vd;
+  cc[2] = fmaf(sb, add, fmaf(cb * bd, ad, al[2]));
+  E[0] = cg * inv_cb, E[1] = sg * inv_cb, E[2] = 0.f;
+  E[3] = -sg, E[4] = cg, E[5] = 0.f;
+  E[6] = cg * sb * inv_cb, E[7] = sg * sb * inv_cb, E[8] = 1.f;
+}
+
 // ---- ObstacleAvoidance on one closest-point pair --------------------------------------------------
 // n = unit vector obstacle -> link, d = distance (the task coordinate x of the reference),
 // inv_d = 1/d.  v, a = velocity and Jdot*qd of the frame origin, vv = |v|^2.

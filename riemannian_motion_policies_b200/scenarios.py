@@ -16,6 +16,13 @@ PANDA_URDF = os.path.join(URDF_DIR, "panda.urdf")
 PANDA_WO_TOOL_URDF = os.path.join(URDF_DIR, "panda_wo_tool.urdf")
 TWO_JOINT_URDF = os.path.join(URDF_DIR, "two_joint_robot.urdf")
 
+# synthetic test robot: general revolute axes, x/y/z prismatic joints, multi-axis rpy, three branchings (urdf/make_urdf.py);
+# its joint order is scrambled on purpose (kinematics.py:197: q is re-ordered per frame)
+GANTRY_URDF = os.path.join(URDF_DIR, "gantry_arm.urdf")
+GANTRY_ORDER = ["wrist", "slide_x", "aux_tip_joint", "elbow", "finger_z", "shoulder", "probe_slide", "aux_arm", "wrist_roll"]
+GANTRY_PRISMATIC = ("slide_x", "probe_slide", "finger_z")
+GANTRY_EULER_GOAL = [0.3, -0.2, 0.5]
+
 PANDA_ORDER_7 = [f"panda_joint{i}" for i in range(1, 8)]
 PANDA_ORDER_9 = PANDA_ORDER_7 + ["panda_finger_joint1", "panda_finger_joint2"]
 TWO_JOINT_ORDER = ["joint_1", "joint_2"]
@@ -127,9 +134,28 @@ def build_config5(ns, fkine, goal, n, distance_taskmap_for):
     return core
 
 
-BUILDERS = {2: build_config2, 3: build_config3, 4: build_config4, 5: build_config5}
-N_SPHERES = {2: 0, 3: 16, 4: 64, 5: 64}
-SEEDS = {1: 0, 2: 1, 3: 2, 4: 3, 5: 4}
+def euler_taskmap(ns, fkine, frame):
+    return ns.chain_taskmaps([ns.TaskmapByForwardKinematic(fkine, frame), ns.TaskmapFrom4x4ToEuler()])
+
+
+def build_config6(ns, fkine, goal, n, distance_taskmap_for):
+    """Test-only tree on the synthetic gantry arm: position + ORIENTATION (Euler task map, taskmap.py:57-67)
+    targets on the tool tip, a second position target on the other branch, damping, obstacle leaves on every
+    collision frame."""
+    core = ns.RmpCore()
+    core.add_rmp(ns.TargetPolicy(alpha=0.1, beta=0.5, c=0.1, goal=goal, name='target',
+                                 taskmap=ee_position_taskmap(ns, fkine, 'tool')))
+    core.add_rmp(ns.TargetPolicy(alpha=0.2, beta=0.4, c=0.1, goal=GANTRY_EULER_GOAL, name='orientation',
+                                 taskmap=euler_taskmap(ns, fkine, 'tool')))
+    core.add_rmp(target_attractor(ns, fkine, [0.2, 0.3, 0.4], frame='aux_tip_joint'))
+    core.add_rmp(ns.JointDamping(accel_d_gain=1, metric_scalar=0.005, inertia=0.05))
+    add_obstacle_leaves(ns, core, fkine, distance_taskmap_for)
+    return core
+
+
+BUILDERS = {2: build_config2, 3: build_config3, 4: build_config4, 5: build_config5, 6: build_config6}
+N_SPHERES = {2: 0, 3: 16, 4: 64, 5: 64, 6: 8}
+SEEDS = {1: 0, 2: 1, 3: 2, 4: 3, 5: 4, 6: 5}
 FULL_BATCH = {1: 1, 2: 4096, 3: 65536, 4: 1 << 20, 5: 8 << 20}
 
 
@@ -150,6 +176,17 @@ def sample_panda_state(B, n, seed):
     q = rng.uniform(PANDA_Q_LOW[:n], PANDA_Q_HIGH[:n], size=(B, n)).astype(np.float32)
     qd = rng.uniform(-0.3, 0.3, size=(B, n)).astype(np.float32)
     goal = rng.uniform([0.3, -0.7, 0.3], [0.7, 0.7, 0.7], size=(B, 3)).astype(np.float32)
+    return q, qd, goal
+
+
+def sample_gantry_state(B, seed):
+    """revolute joints ~ U(-2.5, 2.5), prismatic ~ U(-0.2, 0.3) in GANTRY_ORDER, qd ~ U(-0.3, 0.3), goal in reach"""
+    rng = np.random.RandomState(seed)
+    lo = np.array([-0.2 if name in GANTRY_PRISMATIC else -2.5 for name in GANTRY_ORDER])
+    hi = np.array([0.3 if name in GANTRY_PRISMATIC else 2.5 for name in GANTRY_ORDER])
+    q = rng.uniform(lo, hi, size=(B, len(GANTRY_ORDER))).astype(np.float32)
+    qd = rng.uniform(-0.3, 0.3, size=(B, len(GANTRY_ORDER))).astype(np.float32)
+    goal = rng.uniform([-0.4, -0.4, 0.2], [0.6, 0.4, 0.8], size=(B, 3)).astype(np.float32)
     return q, qd, goal
 
 

@@ -150,19 +150,19 @@ class TaskmapJointFrame4x4ToSphereDistance(Taskmap):
 
 
 class TaskmapFrom4x4ToEuler(Taskmap):
-    """xyz Euler angles of the rotation block (reference: taskmap.py:57-67, kinematics.py:74-96).
-    Not on the control-step path -- the reference only uses it in tests/test_taskmaps.py -- so the
-    derivatives are written out in closed form as torch ops on CUDA tensors:
+    """xyz Euler angles of the rotation block (reference: taskmap.py:57-67, kinematics.py:74-96):
         theta_y = -asin(r20), theta_z = atan2(r10, r00), theta_x = atan2(r21, r22)
-    (dividing both atan2 arguments by cos(theta_y) > 0 as the reference does leaves the angle unchanged)."""
+    (dividing both atan2 arguments by cos(theta_y) > 0, as the reference does, leaves the angles unchanged).
+    Inside a compiled tree the chain [FK, 4x4ToEuler] is the kernels' RMP2_SPACE_FRAME_EULER (analytic
+    Euler-rate map).  This stand-alone map of the 16 matrix entries has closed-form derivatives too:
+        d theta_y / d r20 = -1 / sqrt(1 - r20^2),   d atan2(y, x) = (x dy - y dx) / (x^2 + y^2),
+    and c = qd^T Hess qd with Hess(-asin) = -r / (1 - r^2)^(3/2) and
+    Hess(atan2) = [[2xy, y^2 - x^2], [y^2 - x^2, -2xy]] / (x^2 + y^2)^2 in (x, y)."""
 
     @staticmethod
     def _angles(T):
         r00, r10, r20, r21, r22 = T[:, 0], T[:, 4], T[:, 8], T[:, 9], T[:, 10]
-        theta_y = -torch.asin(r20)
-        cy = torch.cos(theta_y)
-        safe = torch.where(cy.abs() < 1e-6, torch.ones_like(cy), cy)
-        return torch.stack((torch.atan2(r21 / safe, r22 / safe), theta_y, torch.atan2(r10 / safe, r00 / safe)), dim=-1)
+        return torch.stack((torch.atan2(r21, r22), -torch.asin(r20), torch.atan2(r10, r00)), dim=-1)
 
     def forward(self, input):
         t = to_device(input).reshape(-1, 16)
@@ -170,16 +170,22 @@ class TaskmapFrom4x4ToEuler(Taskmap):
 
     def differentiate(self, q, qd):
         """x [K,3], xd [K,3], J [K,3,16], c [K,3] with q = vec(T) [K,16] and qd its velocity."""
-        from torch.func import jacrev, jvp, vmap
         dev = require_cuda()
-        qt, qdt = to_device(q, dev).reshape(-1, 16), to_device(qd, dev).reshape(-1, 16)
-        one = lambda t: self._angles(t[None])[0]
-        x = self._angles(qt)
-        J = vmap(jacrev(one))(qt)
-        xd = (J @ qdt[..., None])[..., 0]
-        vel = lambda t, td: jvp(one, (t,), (td,))[1]
-        c = vmap(lambda t, td: jvp(lambda u: vel(u, td), (t,), (td,))[1])(qt, qdt)
-        return tuple(like_input(o, q) for o in (x, xd, J, c))
+        T, Td = to_device(q, dev).reshape(-1, 16), to_device(qd, dev).reshape(-1, 16)
+        K = T.shape[0]
+        J = torch.zeros(K, 3, 16, device=dev)
+        c = torch.zeros(K, 3, device=dev)
+        one_m = 1.0 - T[:, 8] * T[:, 8]
+        J[:, 1, 8] = -torch.rsqrt(one_m)
+        c[:, 1] = -T[:, 8] * Td[:, 8] * Td[:, 8] * one_m.pow(-1.5)
+        for row, iy, ix in ((0, 9, 10), (2, 4, 0)):                 # theta_x = atan2(r21, r22), theta_z = atan2(r10, r00)
+            x, y, xd_, yd_ = T[:, ix], T[:, iy], Td[:, ix], Td[:, iy]
+            rho2 = x * x + y * y
+            J[:, row, iy] = x / rho2
+            J[:, row, ix] = -y / rho2
+            c[:, row] = (2 * x * y * (xd_ * xd_ - yd_ * yd_) + 2 * (y * y - x * x) * xd_ * yd_) / (rho2 * rho2)
+        xdot = (J @ Td[..., None])[..., 0]
+        return tuple(like_input(o, q) for o in (self._angles(T), xdot, J, c))
 
 
 class TaskmapRelative4x4(Taskmap):

@@ -39,6 +39,23 @@ TWO_JOINT = [
 ]
 
 
+# Synthetic test robot (not in the reference): everything the Panda files do not exercise -- revolute joints about
+# general unit axes, prismatic joints along x / y / z, constant rotations with all three rpy components (where the
+# reference's R_x R_y R_z order matters, kinematics.py:123-127), and a kinematic tree that branches three times.
+GANTRY = [
+    ("slide_x", "prismatic", "base", "carriage", "0.1 -0.2 0.3", "0 0 0.1", "1 0 0", (-0.2, 0.3, 1.0), True),
+    ("shoulder", "revolute", "carriage", "upper", "0.3 0.4 -0.5", "0.05 0.02 0.2", "0.36 0.48 0.8", (-2.5, 2.5, 2.0), True),
+    ("elbow", "revolute", "upper", "fore", "-0.7 0.2 0.9", "0.3 0 0.05", "0.6 0 0.8", (-2.5, 2.5, 2.0), True),
+    ("aux_arm", "revolute", "upper", "aux_link", "0.4 -0.3 0.2", "-0.1 0.15 0.1", "-0.48 0.6 0.64", (-2.5, 2.5, 2.0), True),
+    ("wrist", "revolute", "fore", "wrist_link", "0.2 -1.1 0.4", "0.25 0.05 0", "0 1 0", (-2.5, 2.5, 2.0), True),
+    ("probe_slide", "prismatic", "fore", "probe", "-0.3 0.6 0.1", "0.1 -0.1 0.05", "0 1 0", (-0.2, 0.3, 1.0), True),
+    ("aux_tip_joint", "revolute", "aux_link", "aux_tip", "0.9 0.1 -0.6", "0.2 0 0", "1 0 0", (-2.5, 2.5, 2.0), True),
+    ("wrist_roll", "revolute", "wrist_link", "hand", "-0.2 0.3 0.7", "0 0 0.12", "0.666666667 0.666666667 0.333333333", (-2.5, 2.5, 2.0), True),
+    ("finger_z", "prismatic", "hand", "finger", "0.1 0.2 -0.3", "0.02 0 0.05", "0 0 1", (-0.2, 0.3, 1.0), True),
+    ("tool", "fixed", "hand", "tool_tip", "0.5 0.5 0.5", "0 0.03 0.1", None, None, False),
+]
+
+
 def emit(robot_name, base_link, joints, base_has_collision=True):
     """Return URDF text: all links first, then joints in chain order."""
     collision = ('    <collision>\n      <geometry>\n        <sphere radius="0.05"/>\n'
@@ -70,6 +87,7 @@ def main():
         "panda.urdf": emit("panda", "panda_link0", PANDA),
         "panda_wo_tool.urdf": emit("panda", "panda_link0", PANDA_WO_TOOL),
         "two_joint_robot.urdf": emit("TwoJointRobot", "base_link", TWO_JOINT),
+        "gantry_arm.urdf": emit("gantry_arm", "base", GANTRY),
     }
     for fname, text in files.items():
         with open(os.path.join(here, fname), "w") as fh:

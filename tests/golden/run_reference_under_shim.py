@@ -139,17 +139,30 @@ def run_fk(ns, n, B):
     return d
 
 
+CONFIG_CASES = ((1, 2, 16), (2, 7, 12), (2, 9, 6), (3, 7, 8), (3, 9, 4), (4, 7, 256), (5, 7, 256))
+
+
 def main():
-    out_dir = sys.argv[1] if len(sys.argv) > 1 else HERE
+    """usage: run_reference_under_shim.py [out_dir] [--only NAME ...]   (NAME e.g. ref_config4_n7; the two
+    256-environment cases take ~10 min each on one core, so they can be run side by side)"""
+    argv = sys.argv[1:]
+    only = None
+    if "--only" in argv:
+        k = argv.index("--only")
+        only, argv = set(argv[k + 1:]), argv[:k]
+    out_dir = argv[0] if argv else HERE
+    want = lambda name: only is None or name[:-4] in only
     ns = reference_namespace()
     import builtins
     real_print, builtins.print = builtins.print, lambda *a, **k: None      # the reference prints on every FK build
     try:
         results = {f"ref_config{c}_n{n}.npz": run_config(ns, c, n, B)
-                   for c, n, B in ((1, 2, 16), (2, 7, 12), (2, 9, 6), (3, 7, 8), (3, 9, 4), (4, 7, 8), (5, 7, 8))}
-        results["ref_v1_two_joint.npz"] = run_v1_two_joint(ns, 8)
+                   for c, n, B in CONFIG_CASES if want(f"ref_config{c}_n{n}.npz")}
+        if want("ref_v1_two_joint.npz"):
+            results["ref_v1_two_joint.npz"] = run_v1_two_joint(ns, 8)
         for n, B in ((2, 4), (9, 3)):
-            results[f"ref_fk_n{n}.npz"] = run_fk(ns, n, B)
+            if want(f"ref_fk_n{n}.npz"):
+                results[f"ref_fk_n{n}.npz"] = run_fk(ns, n, B)
     finally:
         builtins.print = real_print
     for name, d in results.items():

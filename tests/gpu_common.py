@@ -8,7 +8,9 @@ from riemannian_motion_policies_b200 import scenarios as S
 REL_TOL = 1e-5      # BASELINE.json north_star: 1e-5 relative on qddot in fp32
 
 
-def product_fkine(ns, n):
+def product_fkine(ns, n, config=None):
+    if config == 6:
+        return ns.UrdfForwardKinematic(S.GANTRY_URDF, S.GANTRY_ORDER)
     if n == 2:
         return ns.UrdfForwardKinematic(S.TWO_JOINT_URDF, S.TWO_JOINT_ORDER)
     if n == 7:
@@ -26,7 +28,7 @@ def product_core(ns, config, n, fkine):
 
 
 def product_evaluate(ns, config, n, q, qd, goal, spheres=None, fkine=None, core=None):
-    fkine = fkine or product_fkine(ns, n)
+    fkine = fkine or product_fkine(ns, n, config)
     core = core or product_core(ns, config, n, fkine)
     dev = torch.device("cuda")
     out = core.evaluate(torch.as_tensor(q, device=dev), torch.as_tensor(qd, device=dev),
@@ -83,16 +85,60 @@ def assert_parity(got, ref32, ref64, M64=None, n=None, label="", max_excluded=0.
     return stats
 
 
+def spectrum_guards(s, n):
+    """From the singular values s [B,n] of the float64 combined metric: (excluded, kappa) -- excluded where a
+    singular value lies within a factor 4 of tf.linalg.pinv's cutoff, kappa = sigma_max / smallest kept."""
+    eps32 = np.finfo(np.float32).eps
+    cut = 10 * n * eps32 * s[:, :1]
+    ratio = s / np.maximum(cut, 1e-300)
+    excluded = ((ratio > 0.25) & (ratio < 4.0)).any(-1)
+    kappa = s[:, 0] / np.where(s > cut, s, np.inf).min(-1)
+    return excluded, kappa
+
+
+def clause_counts(got, ref32, ref64, s64, n):
+    """How many environments pass which clause of the parity criterion, and the float32 error constants
+    err / (kappa eps32) of the kernel and of the float32 oracle itself (tools/parity_study.py, bench.py)."""
+    eps32 = np.finfo(np.float32).eps
+    e32, e64, yard = rel_err(got, ref32), rel_err(got, ref64), rel_err(ref32, ref64)
+    excluded, kappa = spectrum_guards(s64, n)
+    keep = ~excluded
+    strict = e32 <= REL_TOL
+    fallback = ~strict & (e64 <= np.maximum(REL_TOL, 2 * yard))
+    neither = ~strict & ~fallback
+    q = lambda x: {k: float(np.quantile(x, v)) for k, v in (("q50", .5), ("q90", .9), ("q99", .99), ("q999", .999), ("max", 1.))}
+    return {"envs": int(len(e32)), "excluded_near_cutoff": int(excluded.sum()), "kept": int(keep.sum()),
+            "pass_strict_1e-5_vs_f32": int((strict & keep).sum()),
+            "pass_only_not_worse_than_f32_oracle": int((fallback & keep).sum()),
+            "pass_neither": int((neither & keep).sum()),
+            "frac_strict": float(strict[keep].mean()), "median_kappa": float(np.median(kappa[keep])),
+            "e32": q(e32[keep]), "e64": q(e64[keep]), "yard": q(yard[keep]),
+            "kernel_e64_over_kappa_eps32": q(e64[keep] / (kappa[keep] * eps32)),
+            "oracle_f32_yard_over_kappa_eps32": q(yard[keep] / (kappa[keep] * eps32)),
+            "neither_detail": [dict(e32=float(a), e64=float(b), yard=float(c), kappa=float(k))
+                               for a, b, c, k in zip(e32[neither & keep][:12], e64[neither & keep][:12],
+                                                     yard[neither & keep][:12], kappa[neither & keep][:12])]}
+
+
 def make_inputs(config, n, B, seed=None):
     seed = S.SEEDS[config] if seed is None else seed
     if config == 1:
         q, qd, goal = S.sample_two_joint(B, seed)
         return q, qd, goal, None
-    q, qd, goal = S.sample_panda_state(B, n, seed)
+    if config == 6:
+        fk = H.make_fkine(n, torch.float64, robot="gantry")
+        q, qd, goal = S.sample_gantry_state(4 * B, seed)
+        # keep clear of the Euler map's gimbal lock (cos(theta_y) -> 0: unbounded derivatives in every implementation)
+        r20 = torch.func.vmap(lambda qq: fk.forward(qq[None], "tool")[0, 2, 0])(torch.as_tensor(q).double()).numpy()
+        ok = np.flatnonzero(np.abs(r20) < 0.9)[:B]
+        assert len(ok) == B
+        q, qd, goal = q[ok], qd[ok], goal[ok]
+    else:
+        fk = H.make_fkine(n, torch.float64)
+        q, qd, goal = S.sample_panda_state(B, n, seed)
     O_ = S.N_SPHERES[config]
     if not O_:
         return q, qd, goal, None
-    fk = H.make_fkine(n, torch.float64)
     frames = S.collision_frames(fk)
     origins = torch.func.vmap(lambda qq: H.frame_origins(fk, qq, frames))(torch.as_tensor(q).double()).numpy()
     return q, qd, goal, S.sample_spheres(B, O_, seed, origins)

@@ -234,17 +234,28 @@ def test_edge_cases(ns):
 
 def test_tma_and_direct_paths_agree(ns):
     """The TMA-staged sphere path and the plain global-load path run the same arithmetic."""
+    from riemannian_motion_policies_b200 import _native
     n, B = 7, 1000
     q, qd, goal, sph = make_inputs(4, n, B)
     fk = product_fkine(ns, n)
     core = product_core(ns, 4, n, fk)
-    a = product_evaluate(ns, 4, n, q, qd, goal, sph, fkine=fk, core=core)
-    os.environ["RMP2_DISABLE_TMA"] = "1"
-    try:
-        b = product_evaluate(ns, 4, n, q, qd, goal, sph, fkine=fk, core=core)
-    finally:
-        del os.environ["RMP2_DISABLE_TMA"]
-    np.testing.assert_array_equal(a, b)
+    dev = torch.device("cuda")
+    tree = core.compile(n, goal_leaves=["attractor"])
+    args = [torch.as_tensor(a, device=dev) for a in (q, qd)]
+    goals = torch.as_tensor(goal, device=dev).reshape(B, 1, 3).contiguous()
+    spheres = torch.as_tensor(sph, device=dev)
+    out = {}
+    for tma in (1, 0):
+        tree.set_option(_native.OPT_TMA, tma)
+        qdd = torch.empty(B, n, device=dev)
+        tree.step(args[0], args[1], qdd, goals=goals, spheres=spheres)
+        out[tma] = qdd.cpu().numpy()
+    np.testing.assert_array_equal(out[1], out[0])
+    # a sphere pointer that is not 16-byte aligned is refused (rows are read as float4), not mis-read
+    flat = torch.zeros(B * 64 * 4 + 1, device=dev)
+    shifted = flat[1:].view(B, 64, 4)
+    with pytest.raises(ValueError, match="16-byte aligned"):
+        tree.step(args[0], args[1], torch.empty(B, n, device=dev), goals=goals, spheres=shifted)
 
 
 def test_early_out_is_exact(ns):
