@@ -275,6 +275,198 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+def build_tree(ns, S, fk, config, n, specialize=True):
+    """-> (core, tree, specialisation info) of one BASELINE config on the 7-DOF Panda."""
+    goal0 = [0.5, 0.0, 0.5]
+    sphere_tm = lambda frame: ns.TaskmapJointFrame4x4ToSphereDistance()
+    core = S.build_config2(ns, fk, goal0, n) if config == 2 else S.BUILDERS[config](ns, fk, goal0, n, sphere_tm)
+    tree = core.compile(n, goal_leaves=["target" if config == 2 else "attractor"])
+    info = {"on": False, "nvrtc_seconds": None}
+    if specialize:
+        t_spec = time.perf_counter()
+        try:
+            info = {"on": True, "nvrtc_seconds": tree.specialize(), "wall_seconds": time.perf_counter() - t_spec}
+        except (RuntimeError, NotImplementedError) as exc:   # no NVRTC on this box: the generic CUDA kernels run instead
+            info = {"on": False, "nvrtc_seconds": None, "error": str(exc)[:200]}
+    return core, tree, info
+
+
+def fixture_parity(ns, config, n=7):
+    """Parity on the seeded 4096-environment batch whose oracle outputs are committed
+    (tests/golden/parity_config*_n7.npz): pass counts per clause of the criterion (tests/gpu_common.py)."""
+    path = os.path.join(ROOT, "tests", "golden", f"parity_config{config}_n{n}.npz")
+    if not os.path.exists(path):
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gpu_common import clause_counts, make_inputs, product_evaluate
+    g = np.load(path)
+    B = int(g["B"])
+    q, qd, goal, sph = make_inputs(config, n, B)
+    got = product_evaluate(ns, config, n, q, qd, goal, sph)
+    out = clause_counts(got, g["ref32"], g["ref64"], g["s64"], n)
+    out.pop("neither_detail", None)
+    out["inputs"] = "tests/gpu_common.make_inputs seed, oracle outputs from tests/golden/" + os.path.basename(path)
+    return out
+
+
+def time_steps(fn, steps, torch, warmup=3):
+    """ms per call of fn(i) over `steps` calls, CUDA events on the current stream."""
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def graph_of(fn, torch):
+    """Capture fn() (already warmed up: scratch sized) into a CUDA graph -- the way to run launch-bound batches."""
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    return graph
+
+
+def other_config_lines(ns, S, fk, n, device, steps, torch):
+    """The other BASELINE configs at their own batch sizes on this GPU (N = 1 only): config 5 at 2^20 environments,
+    configs 2 / 3 at 4,096 / 65,536 environments replayed from a CUDA graph (launch-bound sizes)."""
+    out = {}
+    for config, B, graphed in ((5, 1 << 20, False), (2, 4096, True), (3, 65536, True)):
+        core, tree, spec = build_tree(ns, S, fk, config, n)
+        O_ = S.N_SPHERES[config]
+        tree.set_early_out(False)
+        nb = 2 if O_ else 1
+        q, qd, goal, spheres = S.synth_inputs_device(fk, n, B, O_, nb, seed=S.SEEDS[config], device=device)
+        goals = goal.reshape(B, 1, 3).contiguous()
+        qdd = torch.empty(B, n, device=device)
+        step = lambda i: tree.step(q, qd, qdd, goals=goals, spheres=spheres[i % nb] if O_ else None)
+        line = {"workload": WORKLOAD[config], "envs": B, "spheres_per_env": O_, "specialized": spec["on"]}
+        if graphed:
+            step(0)
+            torch.cuda.synchronize()
+            graph = graph_of(lambda: step(0), torch)
+            ms = time_steps(lambda i: graph.replay(), steps, torch)
+            line["launch"] = "CUDA graph replay"
+            line["ms_per_step_eager"] = time_steps(step, steps, torch)
+        else:
+            ms = time_steps(step, steps, torch)
+            line["launch"] = "eager"
+        line["ms_per_step"] = ms
+        line["value"] = B / (ms * 1e-3)
+        line["unit"] = UNIT
+        tree.set_early_out(True)
+        if O_:
+            line["value_early_out"] = B / (time_steps(step, steps, torch) * 1e-3)
+        line["parity"] = fixture_parity(ns, config, n)
+        out[f"config{config}"] = line
+        del tree, core, q, qd, goal, spheres, qdd
+        torch.cuda.empty_cache()
+    return out
+
+
+def rollout_lines(ns, S, fk, n, device, torch):
+    """Closed-loop rollout throughput (rmp2_rollout: 100 simulation steps of dt = 0.01, a control step every 10; full
+    tree = config 5, 64 fixed spheres), replayed from a CUDA graph."""
+    out = {}
+    core, tree, spec = build_tree(ns, S, fk, 5, n)
+    for B in (4096, 1 << 20):
+        q0, qd0, goal, spheres = S.synth_inputs_device(fk, n, B, 64, 1, seed=11, device=device)
+        goals = goal.reshape(B, 1, 3).contiguous()
+        q, qd, qdd = q0.clone(), qd0.clone(), torch.empty(B, n, device=device)
+        sim_steps, every = 100, 10
+        run = lambda: tree.rollout(q, qd, qdd, 0.01, sim_steps, every, goals=goals, spheres=spheres[0])
+        run()
+        torch.cuda.synchronize()
+        graph = graph_of(run, torch)
+        reps = 5 if B > 100000 else 20
+
+        def replay(i):
+            q.copy_(q0)
+            qd.copy_(qd0)
+            graph.replay()
+
+        ms = time_steps(replay, reps, torch, warmup=2)
+        out[f"envs_{B}"] = {"ms_per_rollout": ms, "sim_steps": sim_steps, "control_steps": sim_steps // every,
+                            "control_steps_per_s": B * (sim_steps // every) / (ms * 1e-3),
+                            "sim_steps_per_s": B * sim_steps / (ms * 1e-3), "launch": "CUDA graph replay",
+                            "finite": bool(torch.isfinite(q).all().item())}
+        del q0, qd0, goal, spheres, goals, q, qd, qdd, graph
+        torch.cuda.empty_cache()
+    return out
+
+
+def b1_latency(ns, S, fk, n, torch):
+    """core.evaluate(q, qd) the way the reference's experiments call it: one environment, NumPy in, .numpy() out
+    (experiments/franka_panda/05_obstacle_avoidance.py:96).  Median wall-clock microseconds over 200 calls."""
+    out = {}
+    rng = np.random.RandomState(0)
+    q = rng.uniform(S.PANDA_Q_LOW[:n], S.PANDA_Q_HIGH[:n]).astype(np.float32)
+    qd = rng.uniform(-0.3, 0.3, size=n).astype(np.float32)
+    sph = S.sample_spheres(1, 64, 5)[0]
+    for name, config, kw in (("config2", 2, {}), ("config4_64_spheres", 4, {"spheres": sph})):
+        core, tree, _ = build_tree(ns, S, fk, config, n, specialize=False)
+        core = S.build_config2(ns, fk, [0.5, 0.0, 0.5], n) if config == 2 else \
+            S.build_config4(ns, fk, [0.5, 0.0, 0.5], n, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance())
+        for _ in range(20):
+            core.evaluate(q, qd, **kw).numpy()
+        ts = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            core.evaluate(q, qd, **kw).numpy()
+            ts.append(time.perf_counter() - t0)
+        out[name] = float(np.median(ts) * 1e6)
+    return out
+
+
+def h2d_peak_gbs(torch, device, barrier, nbytes=1 << 30, reps=5):
+    """Pinned host -> device copy rate of this rank, all ranks copying at the same time (plain cudaMemcpyAsync of
+    one 1 GiB buffer per copy)."""
+    host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    dev.copy_(host, non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dev.copy_(host, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    del host, dev
+    return gbs
+
+
+def cpu_vectorised_baseline(config, n, cores, envs=1024):
+    """BASELINE.md section 4 plan C: the same oracle arithmetic vectorised over environments (torch.func.vmap) with
+    all host threads -- the strongest CPU comparator available without TensorFlow."""
+    import torch
+    from oracle import harness as H
+    from riemannian_motion_policies_b200 import scenarios as S
+    old = torch.get_num_threads()
+    torch.set_num_threads(cores)
+    try:
+        O_ = S.N_SPHERES[config]
+        q, qd, goal = S.sample_panda_state(envs, n, 123)
+        sph = S.sample_spheres(envs, O_, 123) if O_ else None
+        H.evaluate_vmap(config, n, q[:64], qd[:64], goal[:64], None if sph is None else sph[:64])      # warm-up
+        t0 = time.perf_counter()
+        H.evaluate_vmap(config, n, q, qd, goal, sph, chunk=256)
+        dt = time.perf_counter() - t0
+    finally:
+        torch.set_num_threads(old)
+    return {"value": envs / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{envs} envs of the same workload, oracle arithmetic under torch.func.vmap in chunks of 256, "
+                      f"torch.set_num_threads({cores}), {dt:.1f} s"}
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -311,21 +503,9 @@ def run_b200_arm(args):
     O_ = S.N_SPHERES[config]
     ns = S.product_namespace()
     fk = ns.UrdfForwardKinematic(S.PANDA_WO_TOOL_URDF, S.PANDA_ORDER_7)
-    goal0 = [0.5, 0.0, 0.5]
-    sphere_tm = lambda frame: ns.TaskmapJointFrame4x4ToSphereDistance()
-    core = S.build_config2(ns, fk, goal0, n) if config == 2 else S.BUILDERS[config](ns, fk, goal0, n, sphere_tm)
-    goal_leaf = "target" if config == 2 else "attractor"
-    tree = core.compile(n, goal_leaves=[goal_leaf])
     # the product's path for large batches: frames / step kernels rebuilt for this tree by NVRTC (one-off,
     # outside the timed region like any warm-up); --no-specialize times the generic table-driven kernels
-    specialized = {"on": False, "nvrtc_seconds": None}
-    if not args.no_specialize:
-        t_spec = time.perf_counter()
-        try:
-            nvrtc_s = tree.specialize()
-            specialized = {"on": True, "nvrtc_seconds": nvrtc_s, "wall_seconds": time.perf_counter() - t_spec}
-        except (RuntimeError, NotImplementedError) as exc:   # no NVRTC on this box: the generic CUDA kernels run instead
-            specialized = {"on": False, "nvrtc_seconds": None, "error": str(exc)[:200]}
+    core, tree, specialized = build_tree(ns, S, fk, config, n, specialize=not args.no_specialize)
     # Headline and roofline: every (frame, sphere) pair goes through the full arithmetic.  The exact
     # early-out of the obstacle kernel (library default) is measured separately below.
     tree.set_early_out(False)
@@ -334,6 +514,7 @@ def run_b200_arm(args):
     q, qd, goal, spheres = S.synth_inputs_device(fk, n, B, O_, n_buffers, seed=S.SEEDS[config] + 17 * rank, device=device)
     goals = goal.reshape(B, 1, 3).contiguous()
     qdd = torch.empty(B, n, device=device)
+    tree.reserve(B, O_)
 
     def step(i):
         tree.step(q, qd, qdd, goals=goals, spheres=spheres[i % n_buffers] if O_ else None)
@@ -342,6 +523,13 @@ def run_b200_arm(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
 
     for i in range(max(3, args.warmup)):
         step(i)
@@ -357,14 +545,10 @@ def run_b200_arm(args):
             step(i)
         stop.record()
         barrier()
-    elapsed_ms = start.elapsed_time(stop)
+    elapsed_ms = max_over_ranks(start.elapsed_time(stop))
     launches = _native.launch_count() - launches0
     kernel_ms = tree.profile_read()         # {kernel: (total ms, launches)} on this rank
     tree.profile(False)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
     per_gpu = B / (ms_per_step * 1e-3)
@@ -382,70 +566,92 @@ def run_b200_arm(args):
             step(i)
         e1.record()
         barrier()
-        ems = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ems], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
+        ems = max_over_ranks(e0.elapsed_time(e1))
         sub = slice(0, min(B, 8192))
         frames = S.collision_frames(fk)
         origins = torch.stack([fk.forward(q[sub], fr)[:, :3, 3] for fr in frames], dim=1)          # [b,K,3]
         sp = spheres[0][sub]
         dist_s = torch.linalg.norm(origins[:, :, None, :] - sp[:, None, :, :3], dim=-1) - sp[:, None, :, 3]
         early = {"value": world * B / (ems / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ems / args.steps,
+                 "speedup_over_all_pairs": ms_per_step / (ems / args.steps),
                  "active_pair_fraction": float((dist_s.abs() <= 0.5).float().mean()),
                  "note": "library default: pairs beyond metric_modulation_radius contribute exactly zero "
                          "(reference rmp2.py:194) and are skipped; results are identical"}
         tree.set_early_out(False)
 
-    # ---- parity spot check on the benchmarked inputs (first 128 envs of rank 0, oracle = checker only)
-    parity = None
-    e2e = None
-    cpu_baseline = None
-    if rank == 0 and not args.skip_checks:
-        from oracle import harness as H
-        sub = slice(0, 128)
-        sph_np = spheres[(args.steps - 1) % n_buffers][sub].cpu().numpy() if O_ else None
-        ref64 = H.evaluate_vmap(config, n, q[sub].cpu().numpy(), qd[sub].cpu().numpy(), goal[sub].cpu().numpy(), sph_np,
-                                dtype=torch.float64)
-        ref32 = H.evaluate_vmap(config, n, q[sub].cpu().numpy(), qd[sub].cpu().numpy(), goal[sub].cpu().numpy(), sph_np,
-                                dtype=torch.float32)
-        got = qdd[sub].cpu().numpy()
-        rel = lambda a, b: np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-30)
-        parity = {"envs": 128, "median_rel_err_vs_oracle_f32": float(np.median(rel(got, ref32))),
-                  "frac_within_1e-5_of_oracle_f32": float((rel(got, ref32) <= 1e-5).mean()),
-                  "median_rel_err_vs_oracle_f64": float(np.median(rel(got, ref64))),
-                  "median_rel_err_oracle_f32_vs_f64": float(np.median(rel(ref32, ref64)))}
+    # ---- result collection (north star: "NCCL allgather only for result collection"): not part of the step
+    collect = None
+    if world > 1:
+        from riemannian_motion_policies_b200 import sharding
+        gathered = torch.empty(world * B, n, device=device)
+        for _ in range(2):
+            sharding.gather_environments(qdd, world * B, out=gathered)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        g0.record()
+        for _ in range(reps):
+            sharding.gather_environments(qdd, world * B, out=gathered)
+        g1.record()
+        barrier()
+        gms = max_over_ranks(g0.elapsed_time(g1)) / reps
+        peer = (rank + 1) % world
+        mine = bool(torch.equal(gathered[rank * B:(rank + 1) * B], qdd))
+        # the neighbour's block must be what the neighbour computed: compare checksums
+        sums = torch.stack([gathered[r * B:(r + 1) * B].double().sum() for r in range(world)])
+        own = qdd.double().sum().reshape(1)
+        all_own = [torch.empty_like(own) for _ in range(world)]
+        dist.all_gather(all_own, own)
+        ok = mine and bool(torch.equal(sums, torch.cat(all_own)))
+        bytes_rank = B * n * 4
+        collect = {"allgather_ms": gms, "bytes_per_rank": bytes_rank, "bytes_received_per_rank": (world - 1) * bytes_rank,
+                   "gbs_per_rank": (world - 1) * bytes_rank / (gms * 1e-3) / 1e9,
+                   "frac_of_nvlink5_900gbs": (world - 1) * bytes_rank / (gms * 1e-3) / 1e9 / 900.0,
+                   "share_of_step": gms / ms_per_step, "blocks_match_owners": ok, "checked_peer": peer,
+                   "note": "dist.all_gather_into_tensor (NCCL) of qdd [B,7] f32 into a preallocated [N*B,7]; outside the step"}
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    e2e = None
     if not args.skip_e2e:
         hb = 2 if O_ else 1
         q_h, qd_h, goals_h = (t.cpu().pin_memory() for t in (q, qd, goals))
         sph_h = [spheres[i].cpu().pin_memory() for i in range(hb)] if O_ else [None]
         qdd_h = torch.empty(B, n).pin_memory()
-        e2e_steps = max(2, min(args.steps, 5))
-        tree.step_host(q_h, qd_h, qdd_h, goals=goals_h, spheres=sph_h[0])           # warm-up (allocates staging)
+        e2e_steps = max(20, min(args.steps, 50))
+        for i in range(2):
+            tree.step_host(q_h, qd_h, qdd_h, goals=goals_h, spheres=sph_h[i % hb])   # warm-up (allocates staging)
         barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
             tree.step_host(q_h, qd_h, qdd_h, goals=goals_h, spheres=sph_h[i % hb])
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(time.perf_counter() - t0)
         h2d = B * (2 * n + 3 + 4 * O_) * 4
         d2h = B * n * 4
+        peak = h2d_peak_gbs(torch, device, barrier)
+        peak_min = -max_over_ranks(-peak)
+        h2d_rate = h2d * e2e_steps / dt / 1e9
         e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": e2e_steps, "note": "RmpCore -> CompiledTree.step_host -> rmp2_step_host, pinned host tensors, "
-                                           "64k-env chunks pipelined over 3 streams",
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "h2d_gbs_per_rank": h2d_rate, "h2d_peak_gbs_per_rank": peak_min,
+               "frac_of_h2d_peak": h2d_rate / peak_min,
+               "h2d_peak_how": f"pinned 1 GiB cudaMemcpyAsync x5 per rank, {world} rank(s) copying concurrently, slowest rank",
+               "note": "RmpCore -> CompiledTree.step_host -> rmp2_step_host, pinned host tensors, 64k-env chunks "
+                       "pipelined over 3 streams; the step is bound by the host-to-device copy of the sphere rows",
                "host_cores_bound_per_rank": numa_cores}
-        same = torch.allclose(qdd_h[:4096], qdd[:4096].cpu(), rtol=0, atol=0) if not O_ else None
-        if same is not None:
-            e2e["matches_device_path"] = bool(same)
+        if not O_:
+            e2e["matches_device_path"] = bool(torch.allclose(qdd_h[:4096], qdd[:4096].cpu(), rtol=0, atol=0))
+        del q_h, qd_h, goals_h, sph_h, qdd_h
 
-    if rank == 0 and not args.skip_checks and world == 1:
+    parity = others = rollout = latency = cpu_baseline = cpu_vec = None
+    if rank == 0 and world == 1 and not args.skip_checks:
+        del spheres, q, qd, goal, goals, qdd
+        torch.cuda.empty_cache()
+        parity = fixture_parity(ns, config, n)
+        if not args.skip_extras:
+            others = other_config_lines(ns, S, fk, n, device, min(args.steps, 30), torch)
+            rollout = rollout_lines(ns, S, fk, n, device, torch)
+            latency = b1_latency(ns, S, fk, n, torch)
         cores = min(host_cores(), 64)
         per_core = max(args.envs_per_core, 24)
         v, total, wall = cpu_reference_throughput(config, n, cores, per_core, O_)
@@ -453,6 +659,9 @@ def run_b200_arm(args):
                         "sample": f"{total} envs of the same workload in rounds of {cores} processes x {per_core} envs "
                                   f"(median round, {wall:.1f} s measured after warm-up), oracle port run one env per "
                                   f"call like the reference"}
+        cpu_vec = cpu_vectorised_baseline(config, n, cores)
+        if latency is not None:
+            latency["cpu_port_us_per_env_per_core"] = 1e6 * cores / v
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
@@ -473,15 +682,16 @@ def run_b200_arm(args):
             dom_bytes = B * BYTES_PER_ENV[config]
             dom_flops = B * FLOPS_PER_ENV[config]
         # measured DRAM traffic of the same kernel at the same size (one ncu --set full capture, profiles/)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as fh:
-                tj = json.load(fh)
-            if tj.get("config") == config and tj.get("envs") == B:
-                for kname, kv in tj["kernels"].items():
-                    if kname.startswith(f"rmp2_{dom}_kernel"):
-                        traffic = kv["dram_bytes_read"] + kv["dram_bytes_write"]
+        traffic, traffic_src = None, None
+        for tname in ("r2_traffic.json", "r1_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if traffic is None and os.path.exists(tpath):
+                with open(tpath) as fh:
+                    tj = json.load(fh)
+                if tj.get("config") == config and tj.get("envs") == B:
+                    for kname, kv in tj["kernels"].items():
+                        if kname.startswith(f"rmp2_{dom}_kernel"):
+                            traffic, traffic_src = kv["dram_bytes_read"] + kv["dram_bytes_write"], "profiles/" + tname
         dom_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
         lanes = None
         if O_:
@@ -514,7 +724,8 @@ def run_b200_arm(args):
                        "l2_policy": f"inputs larger than L2: {n_buffers} rotating sphere buffers of "
                                     f"{B * O_ * 16 / 1e6:.0f} MB each" if O_ else "q/qd/goal re-read each step"},
             "roofline": {"bound": "hbm", "kernel": f"rmp2_{dom}_kernel", "achieved": dom_gbs, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": dom_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
+                         "unit": "GB/s", "frac": dom_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_kind,
                          "kernel_ms_per_launch": dom_ms, "kernel_share_of_step": dom_ms / max(total_kernel_ms, 1e-12),
                          "algorithmic_bytes_per_launch": dom_bytes,
                          "note": "this path is FP32/MUFU-issue bound by design, not HBM bound (see roofline_fp32); the "
@@ -530,7 +741,9 @@ def run_b200_arm(args):
             "kernel_ms": {k: {"ms_per_step": v[0] / args.steps, "launches": int(v[1])} for k, v in kernel_ms.items()},
             "per_gpu_value": per_gpu, "gpu_launches": int(launches), "kernel": info, "specialized": specialized,
             "clocks": clocks.summary(),
-            "early_out": early, "e2e": e2e, "cpu_baseline": cpu_baseline, "parity": parity,
+            "early_out": early, "e2e": e2e, "collect": collect, "cpu_baseline": cpu_baseline,
+            "cpu_baseline_vectorised": cpu_vec, "parity": parity, "other_configs": others, "rollout": rollout,
+            "latency_b1_us": latency,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -551,7 +764,8 @@ def main():
     ap.add_argument("--no-specialize", action="store_true", help="keep the generic (table-interpreting) frames/step kernels")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-early-out", action="store_true")
-    ap.add_argument("--skip-checks", action="store_true", help="skip the oracle parity spot check and the CPU baseline")
+    ap.add_argument("--skip-checks", action="store_true", help="skip the parity block, the CPU baselines and the extras")
+    ap.add_argument("--skip-extras", action="store_true", help="skip other_configs / rollout / latency_b1_us (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -69,7 +69,7 @@ def _single_env_fn(config, n, fkine, dtype, combine=False):
 
 def evaluate_loop(config, n, q, qd, goal, spheres=None, dtype=torch.float32, fkine=None):
     """Reference-style execution: one environment per call.  Inputs are numpy [B,...]."""
-    fkine = fkine or make_fkine(n, dtype)
+    fkine = fkine or make_fkine(n, dtype, robot="gantry" if config == 6 else None)
     one = _single_env_fn(config, n, fkine, dtype)
     out = []
     for b in range(q.shape[0]):
@@ -80,7 +80,7 @@ def evaluate_loop(config, n, q, qd, goal, spheres=None, dtype=torch.float32, fki
 
 def evaluate_vmap(config, n, q, qd, goal, spheres=None, dtype=torch.float32, chunk=1024, fkine=None):
     """Same arithmetic, vectorised over environments with torch.func.vmap."""
-    fkine = fkine or make_fkine(n, dtype)
+    fkine = fkine or make_fkine(n, dtype, robot="gantry" if config == 6 else None)
     one = _single_env_fn(config, n, fkine, dtype)
     B = q.shape[0]
     if spheres is None:
@@ -96,7 +96,7 @@ def evaluate_vmap(config, n, q, qd, goal, spheres=None, dtype=torch.float32, chu
 def combined_vmap(config, n, q, qd, goal, spheres=None, dtype=torch.float64, chunk=1024, fkine=None):
     """(f [B,n], M [B,n,n]) before the resolve -- lets tests measure cond(M) and the singular-value
     gap around the pinv cutoff (SURVEY.md section 8c guards)."""
-    fkine = fkine or make_fkine(n, dtype)
+    fkine = fkine or make_fkine(n, dtype, robot="gantry" if config == 6 else None)
     one = _single_env_fn(config, n, fkine, dtype, combine=True)
     B = q.shape[0]
     if spheres is None:
@@ -109,3 +109,20 @@ def combined_vmap(config, n, q, qd, goal, spheres=None, dtype=torch.float64, chu
         fs.append(f)
         Ms.append(M)
     return torch.cat(fs).numpy(), torch.cat(Ms).numpy()
+
+
+def rollout(config, n, q, qd, goal, spheres, dt, n_steps, control_every, dtype=torch.float64, fkine=None):
+    """Closed loop the way the experiments run it (experiments/franka_panda/05_obstacle_avoidance.py:92-97: control
+    every `control_every` simulation steps, command held in between) with the simulator replaced by the explicit
+    Euler integrator of rmp2_rollout:  qd += qdd dt;  q += qd dt  (velocity first).  Obstacles and goals stay fixed.
+    Inputs numpy [B, ...]; returns (q, qd, last qdd) as numpy in `dtype`."""
+    np_dtype = np.float64 if dtype == torch.float64 else np.float32
+    q, qd = np.array(q, dtype=np_dtype), np.array(qd, dtype=np_dtype)
+    dt = np_dtype(dt)
+    qdd = np.zeros_like(q)
+    for step in range(n_steps):
+        if step % control_every == 0:
+            qdd = evaluate_vmap(config, n, q, qd, goal, spheres, dtype=dtype, fkine=fkine).astype(np_dtype)
+        qd = qd + qdd * dt
+        q = q + qd * dt
+    return q, qd, qdd

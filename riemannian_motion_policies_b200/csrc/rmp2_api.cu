@@ -656,7 +656,7 @@ int launch_chunk(rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
   }
   {
     ScopedClock clk(tree, 4, stream);
-    e = rmp2_launch_fallback(T, A, 148 * 2, stream);
+    e = rmp2_launch_fallback(T, A, 148 * 4, stream);
   }
   if (e != cudaSuccess) return cuda_fail(e, "rmp2_resolve_fallback_kernel launch");
   g_launches.fetch_add(1);

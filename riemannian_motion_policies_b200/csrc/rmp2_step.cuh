@@ -359,9 +359,9 @@ RMP2_DEV bool qr_solve_if_well_conditioned(float (&G)[N][N], float (&y)[N], int 
 
 // Rank-revealing direct solve for trees whose metric may be rank deficient (after qr_column_pivoting).
 // With M P = Q [R11 R12; 0 R22] and r = the number of leading columns for which
-//     sigma_min(R11) >= 1 / |R11^-1|_F > 4 rcond |R|_F >= 4 rcond sigma_max            (r-th singular value clear of the cutoff)
+//     sigma_min(R11) >= 1 / |R11^-1|_F > 2 rcond |R|_F >= 2 rcond sigma_max            (r-th singular value clear of the cutoff)
 // the remaining singular values are bounded by |R22|_F (interlacing).  If additionally
-//     |R22|_F <= rcond |R_11| / 4  <= rcond sigma_max / 4      (all of them clear below the cutoff)
+//     |R22|_F <= rcond |R_11| / 2  <= rcond sigma_max / 2      (all of them clear below the cutoff)
 //     |R22|_F |R11^-1|_F <= 1e-3                                (gap: second-order term <= 1e-6)
 // then tf.linalg.pinv (rmp.py:153) keeps exactly r singular values and the truncated-SVD solution equals, up
 // to (|R22| / sigma_r)^2, the minimum-norm solution of [R11 R12] z = (Q^T f)_1 (complete orthogonal
@@ -369,9 +369,11 @@ RMP2_DEV bool qr_solve_if_well_conditioned(float (&G)[N][N], float (&y)[N], int 
 //     b = R11^-1 y1,  C = R11^-1 R12,  z2 = (I + C^T C)^-1 C^T b,  z1 = b - C z2,  x = P z.
 // (I + C^T C is SPD with eigenvalues >= 1: Cholesky without pivoting; column pivoting keeps |C_ij| = O(1).)
 // r differs per lane, so every loop runs at full width N and r acts through selects: the instruction stream
-// is uniform across the warp.  On the config-4 tree (target + joint limits + obstacles: rank 5..7, a continuum
-// of singular values down to zero) 97 % of the environments qualify; measured against the exact
-// truncated-SVD solution of the same float32 matrix the deviation is <= 7.4e-7 (median 7e-15, 4096 envs).
+// is uniform across the warp.  The factor 2 on either side of the cutoff is what float32 needs: the bounds are
+// rigorous for the computed R, whose singular values differ from those of M by ~eps32 sigma_max, 70 times less than
+// the cutoff itself.  On the config-4 tree (target + joint limits + obstacles: rank 5..7, a continuum of singular
+// values down to zero) 98.5 % of the environments qualify; measured against the exact truncated-SVD solution of
+// the same float32 matrix the deviation is <= 7.4e-7 (median 7e-15, 4096 envs).
 // G, y, perm are left untouched: lanes that do not qualify continue with the Jacobi sweeps on them.
 // Returns true when x holds the solution.
 template <int N>
@@ -404,8 +406,8 @@ RMP2_DEV bool cod_solve_if_gap(const float (&G)[N][N], const float (&y)[N], cons
       cs[j] = fmaf(W[i][j], W[i][j], cs[j]);
     }
   }
-  // r = leading columns with 1 / |R11^-1|_F > 4 rcond |R|_F   (NaN / inf compare false and end the count)
-  const float thr = 16.f * rcond * rcond * nF2;
+  // r = leading columns with 1 / |R11^-1|_F > 2 rcond |R|_F   (NaN / inf compare false and end the count)
+  const float thr = 4.f * rcond * rcond * nF2;
   int r = 0;
   bool alive = true;
   float F2 = 0.f, F2r = 0.f;
@@ -419,7 +421,7 @@ RMP2_DEV bool cod_solve_if_gap(const float (&G)[N][N], const float (&y)[N], cons
   float tail2 = 0.f;
 #pragma unroll
   for (int i = 0; i < N; ++i) tail2 += (i >= r) ? rn[i] : 0.f;
-  const bool ok = (16.f * tail2 <= rcond * rcond * G[0][0] * G[0][0]) && (tail2 * F2r <= 1e-6f);
+  const bool ok = (4.f * tail2 <= rcond * rcond * G[0][0] * G[0][0]) && (tail2 * F2r <= 1e-6f);
   // b = R11^-1 y1 and C = R11^-1 R12, masked by selects (entries of W beyond column r may be inf / NaN)
   float b[N];
 #pragma unroll

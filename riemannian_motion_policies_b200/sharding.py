@@ -49,18 +49,30 @@ def shard(t, world_size, rank):
     return t[lo:hi]
 
 
-def gather_environments(local, B, group=None):
-    """All-gather per-rank blocks [b_r, ...] into the full [B, ...] tensor on every rank.
-    Blocks may differ by one row; they are padded to the largest block for the collective."""
+def gather_environments(local, B, group=None, out=None):
+    """All-gather per-rank blocks [b_r, ...] into the full [B, ...] tensor on every rank (NCCL on GPUs: result
+    collection only, never on the step path).  Equal blocks (B divisible by the world size) gather straight into
+    `out` (allocated when not given) with one collective and no staging copy; blocks that differ by one row are
+    padded to the largest block for the collective."""
     world = dist.get_world_size(group)
     sizes = [shard_bounds(B, world, r) for r in range(world)]
     longest = max(hi - lo for lo, hi in sizes)
-    padded = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    tail = tuple(local.shape[1:])
+    if all(hi - lo == longest for lo, hi in sizes) and local.is_contiguous():
+        if out is None:
+            out = torch.empty((B,) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+    padded = torch.zeros((longest,) + tail, dtype=local.dtype, device=local.device)
     padded[: local.shape[0]] = local
-    out = torch.empty((world * longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, padded, group=group)
-    out = out.reshape((world, longest) + tuple(local.shape[1:]))
-    return torch.cat([out[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+    buf = torch.empty((world * longest,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, padded, group=group)
+    buf = buf.reshape((world, longest) + tail)
+    res = torch.cat([buf[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 class ShardedStep:

@@ -98,7 +98,8 @@ def test_host_buffer_path_matches_device_path(world):
 def test_rollout_equals_stepwise_euler(world):
     """rmp2_rollout (control every 10 steps, dt = 0.01; the 100 Hz / 10 Hz loop of
     experiments/franka_panda/05_obstacle_avoidance.py:92-97 with an Euler integrator) equals the same
-    loop written with single steps on the host side."""
+    loop written with single steps on the host side (consistency of the two entry points; the check against
+    the oracle's trajectory is test_rollout_against_oracle_trajectory)."""
     w = world
     ns, fk, dev = w["ns"], w["fk"], w["dev"]
     # the damped full tree (config 5): a closed loop without a damping leaf is not a meaningful rollout
@@ -121,6 +122,93 @@ def test_rollout_equals_stepwise_euler(world):
     # steps stays far below these bounds
     torch.testing.assert_close(q, q2, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(qd, qd2, rtol=1e-3, atol=1e-4)
+
+
+def test_rollout_against_oracle_trajectory(world):
+    """rmp2_rollout vs the ORACLE'S closed loop (oracle/harness.rollout, float64): 256 environments of the full tree,
+    100 simulation steps, a control step every 10 (tests/golden/rollout_config5_n7.npz).  The float32 oracle
+    trajectory is the yardstick for what float32 costs over a trajectory.  Error-growth bound: every control step
+    contributes a command error of ~1e-6 |qdd| (the single-step parity bar), integrated twice over at most 1 s:
+    |dq| <= 10 steps x 1e-5 x max|qdd| x T^2 / 2 -- with max|qdd| ~ 50 rad/s^2 on this batch, 2.5e-3; the measured
+    maxima are two orders below that."""
+    import os
+    from conftest import GOLDEN
+    w = world
+    ns, fk, dev = w["ns"], w["fk"], w["dev"]
+    g = np.load(os.path.join(GOLDEN, "rollout_config5_n7.npz"))
+    core = S.build_config5(ns, fk, [0.5, 0.0, 0.5], N, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance())
+    tree = core.compile(N, goal_leaves=["attractor"])
+    Br = g["q0"].shape[0]
+    q, qd = torch.as_tensor(g["q0"], device=dev).clone(), torch.as_tensor(g["qd0"], device=dev).clone()
+    goals = torch.as_tensor(g["goal"], device=dev).reshape(Br, 1, 3).contiguous()
+    sph = torch.as_tensor(g["spheres"], device=dev)
+    qdd = torch.empty(Br, N, device=dev)
+    tree.rollout(q, qd, qdd, float(g["dt"]), int(g["n_steps"]), int(g["control_every"]), goals=goals, spheres=sph)
+    q, qd = q.cpu().numpy().astype(np.float64), qd.cpu().numpy().astype(np.float64)
+    err_q, err_qd = np.abs(q - g["q64"]).max(axis=1), np.abs(qd - g["qd64"]).max(axis=1)
+    yard_q, yard_qd = np.abs(g["q32"] - g["q64"]).max(axis=1), np.abs(g["qd32"] - g["qd64"]).max(axis=1)
+    stats = dict(median_err_q=float(np.median(err_q)), max_err_q=float(err_q.max()), median_yard_q=float(np.median(yard_q)),
+                 max_yard_q=float(yard_q.max()), median_err_qd=float(np.median(err_qd)), max_err_qd=float(err_qd.max()),
+                 median_yard_qd=float(np.median(yard_qd)), max_yard_qd=float(yard_qd.max()))
+    print("rollout vs oracle:", stats)
+    assert np.isfinite(q).all()
+    assert err_q.max() <= 2.5e-3 and err_qd.max() <= 2.5e-2, stats
+    assert np.median(err_q) <= 3 * np.median(yard_q) + 1e-7 and np.median(err_qd) <= 3 * np.median(yard_qd) + 1e-6, stats
+    assert np.quantile(err_q, 0.99) <= 4 * np.quantile(yard_q, 0.99) + 1e-6, stats
+
+
+def test_closed_loop_reaches_the_goal_without_penetration(world):
+    """The reference's success criterion (experiments/franka_panda/06_cluttered_environment.py:120-131: control at
+    10 Hz, simulate at 100 Hz until |x_ee - x_goal| < 0.02 m) on the GPU: the cluttered-environment tree of that
+    script (TargetAttractor, JointVelocityCap, JointDamping, CSpaceBiasing, ObstacleAvoidance on every collision
+    frame), from the ready pose, with sphere obstacles around and goals inside the arm's workspace.  Every
+    environment must reach its goal and no collision-frame origin may ever be inside a sphere."""
+    w = world
+    ns, fk, dev = w["ns"], w["fk"], w["dev"]
+    Bc, O_, dt, every = 512, 8, 0.01, 10
+    rng = np.random.RandomState(7)
+    goal = rng.uniform([0.3, -0.35, 0.25], [0.6, 0.35, 0.65], size=(Bc, 3)).astype(np.float32)
+    q0 = np.tile(S.PANDA_Q_READY[:N], (Bc, 1)) + rng.uniform(-0.05, 0.05, size=(Bc, N))
+    q = torch.as_tensor(q0.astype(np.float32), device=dev)
+    qd = torch.zeros(Bc, N, device=dev)
+    frames = S.collision_frames(fk)
+    ee = lambda: fk.forward(q, S.EE_FRAME)[:, :3, 3]
+    origins = lambda: torch.stack([fk.forward(q, fr)[:, :3, 3] for fr in frames], dim=1)            # [B,K,3]
+    # spheres: anywhere in the workspace, but not within 0.12 m of the start pose's frames or of the goal
+    sph = np.zeros((Bc, O_, 4), np.float32)
+    start = origins().cpu().numpy()
+    for b in range(Bc):
+        k = 0
+        while k < O_:
+            c = rng.uniform([-0.2, -0.6, 0.0], [0.8, 0.6, 1.0])
+            r = rng.uniform(0.03, 0.08)
+            if (np.linalg.norm(start[b] - c, axis=1) - r).min() > 0.12 and np.linalg.norm(goal[b] - c) - r > 0.12:
+                sph[b, k] = (*c, r)
+                k += 1
+    spheres = torch.as_tensor(sph, device=dev)
+    goals = torch.as_tensor(goal, device=dev).reshape(Bc, 1, 3).contiguous()
+    core = S.build_config3(ns, fk, [0.5, 0.0, 0.5], N, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance())
+    tree = core.compile(N, goal_leaves=["attractor"])
+    qdd = torch.empty(Bc, N, device=dev)
+    reached_at = torch.full((Bc,), -1.0, device=dev)
+    clearance = torch.full((Bc,), 1e9, device=dev)
+    t, horizon = 0.0, 60.0
+    while t < horizon:
+        tree.rollout(q, qd, qdd, dt, 50, every, goals=goals, spheres=spheres)                        # 0.5 s of simulated time
+        t += 0.5
+        dist = torch.linalg.norm(ee() - goals[:, 0], dim=1)
+        reached_at = torch.where((reached_at < 0) & (dist < 0.02), torch.full_like(reached_at, t), reached_at)
+        d = torch.linalg.norm(origins()[:, :, None, :] - spheres[:, None, :, :3], dim=-1) - spheres[:, None, :, 3]
+        clearance = torch.minimum(clearance, d.reshape(Bc, -1).min(dim=1).values)
+        if bool((reached_at >= 0).all()):
+            break
+    done = (reached_at >= 0).float().mean().item()
+    print(f"closed loop: {100 * done:.1f} % of {Bc} environments within 0.02 m after {t:.1f} s simulated "
+          f"(median {reached_at[reached_at >= 0].median().item():.1f} s), minimum clearance {clearance.min().item():.4f} m, "
+          f"final |qd| max {qd.abs().max().item():.3f}")
+    assert torch.isfinite(q).all()
+    assert clearance.min().item() > 0.0, "a collision-frame origin entered a sphere"
+    assert done >= 0.97, f"only {100 * done:.1f} % reached the goal"
 
 
 def test_rollout_is_cuda_graph_capturable(world):

@@ -39,6 +39,28 @@ def test_fk_differentiate_every_frame(ns, n):
         np.testing.assert_array_equal(T.reshape(-1, 16), x)
 
 
+def test_fk_general_axes_prismatic_xyz_and_branches(ns):
+    """The synthetic gantry arm (urdf/make_urdf.py): revolute joints about general unit axes (the full Rodrigues
+    branch of chain_advance, reference kinematics.py:99-121), prismatic joints along x, y and z, constant rotations
+    with all three rpy components (R_x R_y R_z order, kinematics.py:123-127), a tree that branches three times and a
+    scrambled joint order -- x, xd, J, c of every frame against the float64 autodiff oracle, computed live."""
+    fk = ns.UrdfForwardKinematic(S.GANTRY_URDF, S.GANTRY_ORDER)
+    ofk = H.make_fkine(9, torch.float64, robot="gantry")
+    assert fk.frame_names == ofk.frame_names
+    q, qd, _ = S.sample_gantry_state(6, seed=31)
+    qd = (3 * qd).astype(np.float32)
+    tq, tqd = torch.as_tensor(q).cuda(), torch.as_tensor(qd).cuda()
+    for frame in fk.frame_names:
+        x, xd, J, c = (t.cpu().numpy() for t in fk.differentiate(tq, tqd, frame))
+        for b in range(q.shape[0]):
+            xo, xdo, Jo, co = (t[0].numpy() for t in ofk.differentiate(torch.as_tensor(q[b:b + 1]).double(),
+                                                                         torch.as_tensor(qd[b:b + 1]).double(), frame))
+            np.testing.assert_allclose(x[b], xo, atol=2e-6, err_msg=frame)
+            np.testing.assert_allclose(J[b], Jo, atol=2e-6, err_msg=frame)
+            np.testing.assert_allclose(xd[b], xdo, atol=5e-6, err_msg=frame)
+            np.testing.assert_allclose(c[b], co, atol=3e-5, err_msg=frame)
+
+
 def test_fk_reference_call_shapes(ns):
     """q [1,n] numpy in -> [1,4,4] host tensor out, callable alias (taskmap.py:28)."""
     fk = product_fkine(ns, 9)

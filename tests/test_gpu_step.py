@@ -69,7 +69,7 @@ def test_reference_source_vectors_v1(ns):
     assert_parity(np.stack(got), g["qdd_ref"], ref64, label="reference-source v1 CollisionAvoidance")
 
 
-@pytest.mark.parametrize("config,n,B", [(1, 2, 1000), (2, 7, 4096), (3, 7, 2048), (4, 7, 1024), (5, 7, 1024), (5, 9, 256)])
+@pytest.mark.parametrize("config,n,B", [(1, 2, 1000), (2, 7, 4096), (3, 7, 2048), (4, 7, 1024), (5, 7, 1024), (5, 9, 256), (6, 9, 512)])
 def test_seeded_batches_against_oracle(ns, config, n, B):
     """Same seeded inputs through the oracle (vmap, f32 and f64) and the kernel."""
     q, qd, goal, sph = make_inputs(config, n, B)
@@ -82,6 +82,10 @@ def test_seeded_batches_against_oracle(ns, config, n, B):
     print(f"config{config} n{n} B{B}: {stats}")
     if config in (2, 3, 5):      # mostly well-conditioned trees: the strict 1e-5 bar holds almost everywhere
         assert stats["frac_strict"] > 0.95, stats
+    # config 6 = the synthetic gantry arm: revolute joints about general axes (the non-z Rodrigues branch of
+    # chain_advance), prismatic joints along x / y / z, multi-axis rpy constants, three kinematic branchings (chain
+    # state slots, > 48 KB of dynamic shared memory), scrambled joint order, and an orientation leaf on the Euler
+    # task map (RMP2_SPACE_FRAME_EULER)
 
 
 def test_reference_style_single_env_call(ns):
@@ -477,10 +481,10 @@ def test_specialized_kernels_match(ns, config, n):
     np.testing.assert_allclose(small.cpu().numpy(), special[:64].cpu().numpy(), rtol=2e-3, atol=1e-5)
 
 
-def test_leaf_update_drops_the_specialization(ns):
-    """The tables are baked into the specialised kernels, so changing a leaf parameter (reference idiom:
-    ``target_rmp.goal = ...``, 06_cluttered_environment.py:142) must fall back to the generic kernels -- and give
-    the new goal's answer -- until specialize() is called again."""
+def test_leaf_update_keeps_the_specialization(ns):
+    """The tables are compile-time constants of the specialised kernels, so changing a leaf parameter (reference
+    idiom: ``target_rmp.goal = ...``, 06_cluttered_environment.py:142) rebuilds them: the next step gives the new
+    goal's answer and still runs the specialised kernels."""
     n, B = 7, 256
     q, qd, goal, _ = make_inputs(2, n, B)
     fk = product_fkine(ns, n)
@@ -493,11 +497,8 @@ def test_leaf_update_drops_the_specialization(ns):
     assert core.compile(n).specialized_seconds() is not None
     core.rmps["target"].goal = [0.3, 0.2, 0.6]
     b = core.evaluate(tq, tqd).cpu().numpy()
-    assert core.compile(n).specialized_seconds() is None
+    assert core.compile(n).specialized_seconds() is not None
     assert np.abs(a - b).max() > 1e-4
-    fresh = product_core(ns, 2, n, fk)
+    fresh = product_core(ns, 2, n, fk)                      # generic kernels, same goal
     fresh.rmps["target"].goal = [0.3, 0.2, 0.6]
-    np.testing.assert_array_equal(fresh.evaluate(tq, tqd).cpu().numpy(), b)
-    core.compile(n).specialize()
-    c = core.evaluate(tq, tqd).cpu().numpy()
-    np.testing.assert_allclose(c, b, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(fresh.evaluate(tq, tqd).cpu().numpy(), b, rtol=1e-5, atol=1e-6)
