@@ -106,23 +106,46 @@ RMP2_DEV void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64
                : "memory");
 }
 
+// Early-out variant (kSkip, library default): pairs beyond the leaf's metric radius contribute exactly zero in
+// the reference as well (rmp2.py:194), so only the others go through the pair arithmetic.  Three phases:
+//   1. every thread tests its owner's (environment, obstacle leaf) spheres with a packed squared-distance test
+//      (conservative by 1e-5) into two bit masks, even and odd spheres;
+//   2. the owners of the block are SORTED by the number of packed steps they need (counting sort through shared
+//      memory) and re-dealt to the threads in that order: the lanes of a warp then carry similar amounts of work
+//      and the warp's trip count is close to its lanes' mean instead of their maximum over a random sample
+//      (config 4, 20 % active pairs: 9.0 instead of 12.0 packed steps per warp, 7.6 being the mean);
+//   3. the full pair only for the set bits, an even with an odd sphere per packed step (the shorter list is padded
+//      with a sphere 1e15 m away, which adds exactly zero).
+// Lane x of every accumulator still takes the even spheres of its owner in increasing order and lane y the odd
+// ones -- which thread does the work changes, the sums do not: bit-identical to the all-pairs variant
+// (tests/test_gpu_step.py::test_early_out_is_exact).
+struct SkipOwner {                  // what travels with an owner when it is re-dealt (phase 2)
+  float p[3], v[3], a[3], vv;
+  uint32_t mask_even, mask_odd;
+  int32_t thread;                   // the owner's home thread: slot = thread / E, environment = thread % E
+};
+
 template <bool kTma, bool kSkip>
 __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 128 / RMP2_SPHERES_BLOCK)
     rmp2_spheres_kernel(const __grid_constant__ SphereTables ST, const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int L = ST.n_slots, E = ST.envs_per_block;
   const int t = threadIdx.x;
-  const int slot = t / E, e_local = t - slot * E;   // consecutive lanes = consecutive environments
+  int slot = t / E, e_local = t - slot * E;         // consecutive lanes = consecutive environments
   const long long env0 = (long long)blockIdx.x * E;
-  const long long env = env0 + e_local;
+  long long env = env0 + e_local;
   const int O = A.n_spheres;
-  const bool active = (slot < L) && (env < A.B);
+  bool active = (slot < L) && (env < A.B);
+  const bool sorted = kSkip && O <= 64;             // one mask word per parity: owners can be re-dealt
 
   uint32_t row = 0;                                 // shared-memory address of this thread's sphere row
+  uint32_t tile = 0;                                // ... of the tile's first row
+  uint64_t* bar = nullptr;
+  const uint32_t pitch = (uint32_t)O * 16u + 16u;
   if (kTma) {
-    const uint32_t row_bytes = (uint32_t)O * 16u, pitch = row_bytes + 16u;
+    const uint32_t row_bytes = (uint32_t)O * 16u;
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    uint64_t* bar = reinterpret_cast<uint64_t*>(base + (size_t)E * pitch);
+    bar = reinterpret_cast<uint64_t*>(base + (size_t)E * pitch);
     const long long rows = (A.B - env0 < E) ? (A.B - env0) : E;
     if (t == 0) {
       mbar_init(bar, 1);
@@ -132,25 +155,26 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
     for (int e = t; e < rows; e += blockDim.x)    // lane e copies row e (one warp's worth for E <= 32)
       bulk_load_1d(smem_u32(base) + (uint32_t)e * pitch,
                    reinterpret_cast<const unsigned char*>(A.spheres) + (size_t)(env0 + e) * row_bytes, row_bytes, bar);
-    if (!active) return;
-    row = smem_u32(base) + (uint32_t)e_local * pitch;
-  } else {
-    if (!active) return;
+    tile = smem_u32(base);
+    row = tile + (uint32_t)e_local * pitch;
   }
+  if (!sorted && !active) return;                   // (the sorted variant keeps every thread for its barriers)
 
   // this thread's frame record and leaf parameters (loads in flight while the rows land)
   float* rec = A.rec + (size_t)slot * A.B + env;
   const size_t fstride = (size_t)L * A.B;
-  const float px = rec[0 * fstride], py = rec[1 * fstride], pz = rec[2 * fstride];
-  const float v[3] = {rec[3 * fstride], rec[4 * fstride], rec[5 * fstride]};
-  const float a[3] = {rec[6 * fstride], rec[7 * fstride], rec[8 * fstride]};
-  const float vv = rec[9 * fstride];
+  float px = 0.f, py = 0.f, pz = 0.f, vv = 0.f;
+  float v[3] = {0.f, 0.f, 0.f}, a[3] = {0.f, 0.f, 0.f};
+  if (active) {
+    px = rec[0 * fstride], py = rec[1 * fstride], pz = rec[2 * fstride];
+    v[0] = rec[3 * fstride], v[1] = rec[4 * fstride], v[2] = rec[5 * fstride];
+    a[0] = rec[6 * fstride], a[1] = rec[7 * fstride], a[2] = rec[8 * fstride];
+    vv = rec[9 * fstride];
+  }
   float p[SP_COUNT];
 #pragma unroll
-  for (int i = 0; i < SP_COUNT; ++i) p[i] = ST.p[slot][i];
+  for (int i = 0; i < SP_COUNT; ++i) p[i] = ST.p[active ? slot : 0][i];
   if (kTma) {
-    uint64_t* bar = reinterpret_cast<uint64_t*>(((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127)) +
-                                                (size_t)E * ((size_t)O * 16 + 16));
     mbar_wait(bar, 0);
     // the sphere loads below are plain (non-volatile) asm so that the scheduler may hoist them over
     // arithmetic; making their address depend on this statement keeps them after the wait
@@ -188,11 +212,11 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
     const float2 inv_d = make_float2(fast_rcp(d.x), fast_rcp(d.y));
     obstacle_pair2(p, __fmul2_rn(rx, sgn), __fmul2_rn(ry, sgn), __fmul2_rn(rz, sgn), d, inv_d, v, a, vv, S, g);
   };
-  // a sphere that contributes exactly zero (beyond every metric radius; d ~ 1e15 keeps all terms finite)
-  const float4 far_away = make_float4(px + 1e15f, py, pz, 0.f);
   const float4* gs = reinterpret_cast<const float4*>(A.spheres) + (size_t)env * O;
   auto load_sphere = [&](int o) -> float4 { return kTma ? lds128(row + (uint32_t)o * 16u) : __ldg(gs + o); };
   if (!kSkip) {
+    // a sphere that contributes exactly zero (beyond every metric radius; d ~ 1e15 keeps all terms finite)
+    const float4 far_away = make_float4(px + 1e15f, py, pz, 0.f);
     constexpr int kStep = 2 * RMP2_SPHERES_STEPS_PER_TRIP;      // spheres per loop trip
     int o = 0;
     for (; o + kStep <= O; o += kStep) {
@@ -202,18 +226,15 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
     for (; o + 1 < O; o += 2) two_spheres(load_sphere(o), load_sphere(o + 1));
     if (o < O) two_spheres(load_sphere(o), far_away);
   } else {
-    // Exact early-out (reference: rmp2.py:194 -- a pair beyond the metric radius has M = 0 and adds
-    // exactly nothing): first a cheap squared-distance test of every sphere into two bit masks (even
-    // and odd spheres), then the full pair only for the set bits, an even with an odd sphere per packed
-    // step (the shorter list is padded with far_away).  The test is conservative (1e-5 wider than the
-    // leaf's own test).
-    const float reach = p[SP_REACH];
-    for (int o0 = 0; o0 < O; o0 += 64) {
-      uint32_t mask_even = 0u, mask_odd = 0u;
+    // phase 1: which spheres are within reach (conservative), 64 at a time
+    auto reach_masks = [&](int o0, uint32_t& mask_even, uint32_t& mask_odd) {
+      const float reach = p[SP_REACH];
+      const float4 nowhere = make_float4(px + 1e15f, py, pz, 0.f);
+      mask_even = 0u, mask_odd = 0u;
       const int cnt = min(64, O - o0);
       for (int o = 0; o < cnt; o += 2) {
         const float4 s0 = load_sphere(o0 + o);
-        const float4 s1 = (o + 1 < cnt) ? load_sphere(o0 + o + 1) : far_away;
+        const float4 s1 = (o + 1 < cnt) ? load_sphere(o0 + o + 1) : nowhere;
         const float2 rx = make_float2(px - s0.x, px - s1.x);
         const float2 ry = make_float2(py - s0.y, py - s1.y);
         const float2 rz = make_float2(pz - s0.z, pz - s1.z);
@@ -223,6 +244,10 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
         mask_even |= (uint32_t)(dc2.x <= lim2.x) << (o >> 1);
         mask_odd |= (uint32_t)(dc2.y <= lim2.y) << (o >> 1);
       }
+    };
+    // phase 3: the pairs of the set bits, an even with an odd sphere per packed step
+    auto masked_pairs = [&](int o0, uint32_t mask_even, uint32_t mask_odd) {
+      const float4 far_away = make_float4(px + 1e15f, py, pz, 0.f);
       while (mask_even | mask_odd) {
         float4 s0 = far_away, s1 = far_away;
         if (mask_even) {
@@ -237,6 +262,56 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
         }
         two_spheres(s0, s1);
       }
+    };
+    if (!sorted) {
+      for (int o0 = 0; o0 < O; o0 += 64) {
+        uint32_t me, mo;
+        reach_masks(o0, me, mo);
+        masked_pairs(o0, me, mo);
+      }
+    } else {
+      __shared__ SkipOwner owners[RMP2_SPHERES_BLOCK];
+      __shared__ int hist[36], first[36];
+      uint32_t me = 0u, mo = 0u;
+      if (active) reach_masks(0, me, mo);
+      const int steps = max(__popc(me), __popc(mo));            // 0 .. 32
+      if (t < 36) hist[t] = 0;
+      __syncthreads();
+      const int rank = atomicAdd(&hist[steps], 1);
+      __syncthreads();
+      if (t < 33) {                                               // heaviest owners first
+        int before = 0;
+        for (int s = t + 1; s <= 32; ++s) before += hist[s];
+        first[t] = before;
+      }
+      __syncthreads();
+      {
+        SkipOwner& w = owners[first[steps] + rank];
+        w.p[0] = px, w.p[1] = py, w.p[2] = pz;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) w.v[i] = v[i], w.a[i] = a[i];
+        w.vv = vv;
+        w.mask_even = me, w.mask_odd = mo;
+        w.thread = active ? t : -1;
+      }
+      __syncthreads();
+      const SkipOwner& r = owners[t];
+      px = r.p[0], py = r.p[1], pz = r.p[2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) v[i] = r.v[i], a[i] = r.a[i];
+      vv = r.vv;
+      me = r.mask_even, mo = r.mask_odd;
+      const int home = r.thread;
+      active = home >= 0;
+      if (!active) return;                                        // no barrier below this line
+      slot = home / E, e_local = home - slot * E;
+      env = env0 + e_local;
+      rec = A.rec + (size_t)slot * A.B + env;
+      gs = reinterpret_cast<const float4*>(A.spheres) + (size_t)env * O;
+      if (kTma) row = tile + (uint32_t)e_local * pitch;
+#pragma unroll
+      for (int i = 0; i < SP_COUNT; ++i) p[i] = ST.p[slot][i];
+      masked_pairs(0, me, mo);
     }
   }
 #pragma unroll

@@ -35,7 +35,8 @@ def reference_frames():
     out = {}
     for key, rel in (("panda", "urdf/franka_panda/panda.urdf"),
                      ("panda_wo_tool", "urdf/franka_panda/panda_wo_tool.urdf"),
-                     ("two_joint", "urdf/TwoJointRobot_wo_fixedJoints.urdf")):
+                     ("two_joint", "urdf/TwoJointRobot_wo_fixedJoints.urdf"),
+                     ("gantry", S.GANTRY_URDF)):          # this repo's synthetic test robot through the reference's parser
         tree = UrdfTree(os.path.join(REFERENCE, rel))
         frames = []
         for path in tree.get_backward_paths():

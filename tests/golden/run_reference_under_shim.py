@@ -51,6 +51,8 @@ URDFS = {2: ("urdf/TwoJointRobot_wo_fixedJoints.urdf", S.TWO_JOINT_ORDER),
 
 
 def run_config(ns, config, n, B):
+    if config == 6:
+        return run_gantry(ns, B)
     path, order = URDFS[n]
     fk = ns.UrdfForwardKinematic(os.path.join(REFERENCE, path), order)
     ofk = H.make_fkine(n, torch.float64)
@@ -64,7 +66,8 @@ def run_config(ns, config, n, B):
     frames = S.collision_frames(ofk)
     spheres = np.zeros((B, max(O_, 1), 4), np.float32)
     out = []
-    for b in range(B):
+    n_eval = min(B, LIMIT) if LIMIT else B          # --limit: the first environments of the SAME seeded input set
+    for b in range(n_eval):
         if O_:
             origins = H.frame_origins(ofk, torch.as_tensor(q[b]).double(), frames).numpy()
             sph = S.sample_spheres(1, O_, seed + b, origins[None])[0]
@@ -80,10 +83,34 @@ def run_config(ns, config, n, B):
         res = core.evaluate(q[b], qd[b])
         assert res.numpy().dtype == np.float32      # accumulators become float32 tensors
         out.append(res.numpy())
-    d = dict(q=q, qd=qd, goal=goal, qdd_ref=np.stack(out))
+    d = dict(q=q[:n_eval], qd=qd[:n_eval], goal=goal[:n_eval], qdd_ref=np.stack(out))
     if O_:
-        d["spheres"] = spheres
+        d["spheres"] = spheres[:n_eval]
     return d
+
+
+def run_gantry(ns, B):
+    """config 6: this repo's synthetic gantry arm (general axes, x/y/z prismatic joints, multi-axis rpy, three
+    branchings) read by the reference's own URDF parser, with an ORIENTATION leaf on the reference's
+    TaskmapFrom4x4ToEuler (taskmap.py:57-67) -- scenarios.build_config6 with the reference's classes."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gpu_common import make_inputs
+    fk = ns.UrdfForwardKinematic(S.GANTRY_URDF, S.GANTRY_ORDER)
+    ofk = H.make_fkine(9, torch.float64, robot="gantry")
+    fk.has_collision = ofk.has_collision
+    frames = S.collision_frames(ofk)
+    q, qd, goal, spheres = make_inputs(6, 9, B, seed=S.SEEDS[6] + 50)
+    out = []
+    B = min(B, LIMIT) if LIMIT else B
+    q, qd, goal, spheres = q[:B], qd[:B], goal[:B], spheres[:B]
+    for b in range(B):
+        origins = H.frame_origins(ofk, torch.as_tensor(q[b]).double(), frames).numpy()
+        on_link, on_obst = S.closest_points_on_spheres(origins, spheres[b])
+        idx = {fr: i for i, fr in enumerate(frames)}
+        tm_for = lambda fr: ns.TaskmapJointFrame4x4ToDistance(tf.constant(on_link[idx[fr]]), tf.constant(on_obst[idx[fr]]))
+        core = S.build_config6(ns, fk, goal[b], 9, tm_for)
+        out.append(core.evaluate(q[b], qd[b]).numpy())
+    return dict(q=q, qd=qd, goal=goal, spheres=spheres, qdd_ref=np.stack(out))
 
 
 def run_v1_two_joint(ns, B):
@@ -93,6 +120,8 @@ def run_v1_two_joint(ns, B):
     rng = np.random.RandomState(77)
     q_all, qd_all, goal_all = S.sample_two_joint(B, seed=78)
     rows, outs = [], []
+    B = min(B, LIMIT) if LIMIT else B
+    q_all, qd_all, goal_all = q_all[:B], qd_all[:B], goal_all[:B]
     for b in range(B):
         q, qd, goal = q_all[b], qd_all[b], goal_all[b]
         distance_data = []
@@ -139,13 +168,20 @@ def run_fk(ns, n, B):
     return d
 
 
-CONFIG_CASES = ((1, 2, 16), (2, 7, 12), (2, 9, 6), (3, 7, 8), (3, 9, 4), (4, 7, 256), (5, 7, 256))
+LIMIT = 0
+CONFIG_CASES = ((1, 2, 16), (2, 7, 12), (2, 9, 6), (3, 7, 8), (3, 9, 4), (4, 7, 256), (5, 7, 256), (6, 9, 12))
 
 
 def main():
-    """usage: run_reference_under_shim.py [out_dir] [--only NAME ...]   (NAME e.g. ref_config4_n7; the two
-    256-environment cases take ~10 min each on one core, so they can be run side by side)"""
+    """usage: run_reference_under_shim.py [out_dir] [--limit K] [--only NAME ...]   (NAME e.g. ref_config4_n7; the two
+    256-environment cases take 10-30 s per environment -- the shim's batch_jacobian loops over the 64 pairs of a
+    frame -- so they can be run side by side; --limit K evaluates only the first K environments of each case)"""
+    global LIMIT
     argv = sys.argv[1:]
+    if "--limit" in argv:
+        k = argv.index("--limit")
+        LIMIT = int(argv[k + 1])
+        del argv[k:k + 2]
     only = None
     if "--only" in argv:
         k = argv.index("--only")

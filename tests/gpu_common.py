@@ -41,41 +41,52 @@ def rel_err(a, b):
     return np.linalg.norm(a - b, axis=-1) / np.maximum(np.linalg.norm(b, axis=-1), 1e-30)
 
 
-def assert_parity(got, ref32, ref64, M64=None, n=None, label="", max_excluded=0.05):
-    """Parity criterion (made explicit).  Per environment, with
-    e32 = |got - ref32|/|ref32|, e64 = |got - ref64|/|ref64|, yard = |ref32 - ref64|/|ref64| (the float32
-    restatement's own distance from the float64 truth) and kappa = sigma_max / smallest kept singular
-    value of the combined metric M:
+# float32 floor of the resolve, MEASURED (tools/parity_study.py on a B200 -> profiles/r2_parity_study.json, 4096
+# config-4 environments): with kappa = sigma_max / smallest kept singular value of the combined metric, the error of
+# a float32 evaluation against the float64 truth divided by kappa * eps32 reaches 0.97 for LAPACK gesdd applied to the
+# SAME float32 (M, f) (gesvd 0.81, this library's solver 0.81), and 3.83 for the whole float32 oracle pipeline (q999:
+# 1.95); the CUDA step stays below 1.65 (q999: 1.43).  The constant is the oracle's own maximum, rounded up.
+KAPPA_FLOOR = 4.0
 
-        e32 <= 1e-5                                   the north-star bar, or
-        e64 <= max(1e-5, 2 * yard)                    not worse than the float32 reference itself, or
-        e64 <= 64 * kappa * eps32                     backward-stable float32 bound for this env's M
 
-    plus, over the batch, the kernel must be statistically as close to the truth as the float32
-    restatement is: median(e64) <= 2 median(yard), q99(e64) <= 3 q99(yard).  Environments with a singular
-    value within a factor 4 of the pinv cutoff are excluded (the truncation is discontinuous there);
-    they must stay below 5 % of the batch (10 % for the rank-deficient config 4 tree, whose weak
-    obstacle metrics put a continuum of singular values around the cutoff)."""
+def assert_parity(got, ref32, ref64, M64=None, n=None, label="", max_excluded=0.05, s64=None):
+    """Parity criterion.  Per environment, with e32 = |got - ref32|/|ref32|,
+    e64 = |got - ref64|/|ref64|, yard = |ref32 - ref64|/|ref64| (the float32 restatement's own distance from the
+    float64 truth) and kappa = sigma_max / smallest kept singular value of the combined metric M:
+
+        (a) e32 <= 1e-5                               the north-star bar, or
+        (b) e64 <= max(1e-5, 2 * yard)                SURVEY's fallback: not worse than the float32 reference itself, or
+        (c) e64 <= KAPPA_FLOOR * kappa * eps32        the measured float32 floor for this environment's metric
+
+    plus, over the batch, the kernel must be statistically as close to the truth as the float32 restatement is:
+    median(e64) <= 2 median(yard), q99(e64) <= 3 q99(yard).  Environments with a singular value within a factor 4
+    of the pinv cutoff are excluded (the truncation is discontinuous there); they must stay below 5 % of the batch
+    (10 % for the rank-deficient config 4 tree, whose weak obstacle metrics put a continuum of singular values
+    around the cutoff).  The returned stats carry the pass count of every clause.  M64 [B,n,n] or its singular
+    values s64 [B,n] supply kappa; without either kappa = 1 and clause (c) is inert."""
     eps32 = np.finfo(np.float32).eps
     e32 = rel_err(got, ref32)
     e64 = rel_err(got, ref64)
     yard = rel_err(ref32, ref64)
     excluded = np.zeros(e32.shape, dtype=bool)
     kappa = np.ones(e32.shape)
-    if M64 is not None:
-        s = np.linalg.svd(M64, compute_uv=False)
-        cut = 10 * n * eps32 * s[:, :1]
-        ratio = s / np.maximum(cut, 1e-300)
-        excluded = ((ratio > 0.25) & (ratio < 4.0)).any(-1)
-        kept = np.where(s > cut, s, np.inf)
-        kappa = s[:, 0] / kept.min(-1)
-    ok = (e32 <= REL_TOL) | (e64 <= np.maximum(REL_TOL, 2 * yard)) | (e64 <= 64 * kappa * eps32)
-    bad = ~ok & ~excluded
+    if s64 is None and M64 is not None:
+        s64 = np.linalg.svd(M64, compute_uv=False)
+    if s64 is not None:
+        excluded, kappa = spectrum_guards(s64, n)
+    pass_a = e32 <= REL_TOL
+    pass_b = e64 <= np.maximum(REL_TOL, 2 * yard)
+    pass_c = e64 <= KAPPA_FLOOR * kappa * eps32
+    bad = ~(pass_a | pass_b | pass_c) & ~excluded
     keep = ~excluded
-    stats = dict(envs=int(len(e32)), frac_strict=float((e32[keep] <= REL_TOL).mean()), median_e32=float(np.median(e32[keep])),
+    stats = dict(envs=int(len(e32)), kept=int(keep.sum()), excluded=int(excluded.sum()),
+                 pass_a_strict=int((pass_a & keep).sum()), pass_b_only=int((~pass_a & pass_b & keep).sum()),
+                 pass_c_only=int((~pass_a & ~pass_b & pass_c & keep).sum()),
+                 frac_strict=float(pass_a[keep].mean()), median_e32=float(np.median(e32[keep])),
                  median_e64=float(np.median(e64[keep])), median_yard=float(np.median(yard[keep])),
                  q99_e64=float(np.quantile(e64[keep], 0.99)), q99_yard=float(np.quantile(yard[keep], 0.99)),
-                 median_kappa=float(np.median(kappa[keep])), excluded=int(excluded.sum()))
+                 median_kappa=float(np.median(kappa[keep])))
+    print(f"[parity] {label}: {stats}")
     assert not bad.any(), (f"{label}: {int(bad.sum())}/{len(bad)} envs out of tolerance; worst e32={e32[bad].max():.3e} "
                            f"e64={e64[bad].max():.3e} yard={yard[bad].max():.3e} kappa={kappa[bad].max():.3e} {stats}")
     assert excluded.mean() < max_excluded, f"{label}: too many envs near the pinv cutoff ({excluded.mean():.3f})"
@@ -142,3 +153,25 @@ def make_inputs(config, n, B, seed=None):
     frames = S.collision_frames(fk)
     origins = torch.func.vmap(lambda qq: H.frame_origins(fk, qq, frames))(torch.as_tensor(q).double()).numpy()
     return q, qd, goal, S.sample_spheres(B, O_, seed, origins)
+
+
+def closed_loop_scene(B, n_spheres, seed, n=7):
+    """A scene the closed loop is well behaved in (the situation of experiments/franka_panda/06_cluttered_environment.py):
+    start near the ready pose at rest, a goal inside the workspace, spheres anywhere around but at least 0.12 m
+    (surface) from every collision frame of the start pose and from the goal.  -> q0, qd0, goal, spheres (float32)."""
+    rng = np.random.RandomState(seed)
+    goal = rng.uniform([0.3, -0.35, 0.25], [0.6, 0.35, 0.65], size=(B, 3)).astype(np.float32)
+    q0 = (np.tile(S.PANDA_Q_READY[:n], (B, 1)) + rng.uniform(-0.05, 0.05, size=(B, n))).astype(np.float32)
+    fk = H.make_fkine(n, torch.float64)
+    frames = S.collision_frames(fk)
+    start = torch.func.vmap(lambda qq: H.frame_origins(fk, qq, frames))(torch.as_tensor(q0).double()).numpy()
+    sph = np.zeros((B, n_spheres, 4), np.float32)
+    for b in range(B):
+        k = 0
+        while k < n_spheres:
+            c = rng.uniform([-0.2, -0.6, 0.0], [0.8, 0.6, 1.0])
+            r = rng.uniform(0.03, 0.08)
+            if (np.linalg.norm(start[b] - c, axis=1) - r).min() > 0.12 and np.linalg.norm(goal[b] - c) - r > 0.12:
+                sph[b, k] = (*c, r)
+                k += 1
+    return q0, np.zeros_like(q0), goal, sph

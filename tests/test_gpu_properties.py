@@ -125,12 +125,12 @@ def test_rollout_equals_stepwise_euler(world):
 
 
 def test_rollout_against_oracle_trajectory(world):
-    """rmp2_rollout vs the ORACLE'S closed loop (oracle/harness.rollout, float64): 256 environments of the full tree,
-    100 simulation steps, a control step every 10 (tests/golden/rollout_config5_n7.npz).  The float32 oracle
+    """rmp2_rollout vs the ORACLE'S closed loop (oracle/harness.rollout, float64): 256 well-behaved scenes
+    (tests/gpu_common.closed_loop_scene) of the full tree, 100 simulation steps, a control step every 10 (tests/golden/rollout_config5_n7.npz).  The float32 oracle
     trajectory is the yardstick for what float32 costs over a trajectory.  Error-growth bound: every control step
     contributes a command error of ~1e-6 |qdd| (the single-step parity bar), integrated twice over at most 1 s:
-    |dq| <= 10 steps x 1e-5 x max|qdd| x T^2 / 2 -- with max|qdd| ~ 50 rad/s^2 on this batch, 2.5e-3; the measured
-    maxima are two orders below that."""
+    |dq| <= 10 steps x 1e-5 x max|qdd| x T^2 / 2 -- with max|qdd| ~ 50 rad/s^2, 2.5e-3; the measured
+    maxima are far below that."""
     import os
     from conftest import GOLDEN
     w = world
@@ -165,26 +165,13 @@ def test_closed_loop_reaches_the_goal_without_penetration(world):
     environment must reach its goal and no collision-frame origin may ever be inside a sphere."""
     w = world
     ns, fk, dev = w["ns"], w["fk"], w["dev"]
+    from gpu_common import closed_loop_scene
     Bc, O_, dt, every = 512, 8, 0.01, 10
-    rng = np.random.RandomState(7)
-    goal = rng.uniform([0.3, -0.35, 0.25], [0.6, 0.35, 0.65], size=(Bc, 3)).astype(np.float32)
-    q0 = np.tile(S.PANDA_Q_READY[:N], (Bc, 1)) + rng.uniform(-0.05, 0.05, size=(Bc, N))
-    q = torch.as_tensor(q0.astype(np.float32), device=dev)
-    qd = torch.zeros(Bc, N, device=dev)
+    q0, qd0, goal, sph = closed_loop_scene(Bc, O_, seed=7)
+    q, qd = torch.as_tensor(q0, device=dev), torch.as_tensor(qd0, device=dev)
     frames = S.collision_frames(fk)
     ee = lambda: fk.forward(q, S.EE_FRAME)[:, :3, 3]
     origins = lambda: torch.stack([fk.forward(q, fr)[:, :3, 3] for fr in frames], dim=1)            # [B,K,3]
-    # spheres: anywhere in the workspace, but not within 0.12 m of the start pose's frames or of the goal
-    sph = np.zeros((Bc, O_, 4), np.float32)
-    start = origins().cpu().numpy()
-    for b in range(Bc):
-        k = 0
-        while k < O_:
-            c = rng.uniform([-0.2, -0.6, 0.0], [0.8, 0.6, 1.0])
-            r = rng.uniform(0.03, 0.08)
-            if (np.linalg.norm(start[b] - c, axis=1) - r).min() > 0.12 and np.linalg.norm(goal[b] - c) - r > 0.12:
-                sph[b, k] = (*c, r)
-                k += 1
     spheres = torch.as_tensor(sph, device=dev)
     goals = torch.as_tensor(goal, device=dev).reshape(Bc, 1, 3).contiguous()
     core = S.build_config3(ns, fk, [0.5, 0.0, 0.5], N, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance())

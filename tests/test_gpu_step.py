@@ -29,7 +29,7 @@ def test_golden_fixtures(ns, config, n):
     print(f"config{config} n{n}: {stats}")
 
 
-@pytest.mark.parametrize("config,n", [(1, 2), (2, 7), (2, 9), (3, 7), (3, 9), (4, 7), (5, 7)])
+@pytest.mark.parametrize("config,n", [(1, 2), (2, 7), (2, 9), (3, 7), (3, 9), (4, 7), (5, 7), (6, 9)])
 def test_reference_source_vectors(ns, config, n):
     """tests/golden/ref_*.npz: outputs of the REFERENCE'S OWN source files run under the TensorFlow-API shim
     (tests/golden/run_reference_under_shim.py).  The kernel must match them like it matches the oracle."""
@@ -86,6 +86,26 @@ def test_seeded_batches_against_oracle(ns, config, n, B):
     # chain_advance), prismatic joints along x / y / z, multi-axis rpy constants, three kinematic branchings (chain
     # state slots, > 48 KB of dynamic shared memory), scrambled joint order, and an orientation leaf on the Euler
     # task map (RMP2_SPACE_FRAME_EULER)
+
+
+@pytest.mark.parametrize("config", [4, 5])
+def test_large_seeded_batches_against_committed_oracle_outputs(ns, config):
+    """4096 seeded environments of the two 64-sphere trees against oracle outputs computed in the build container
+    (tests/golden/make_parity_fixtures.py -> parity_config*_n7.npz: the oracle needs minutes for these).  The inputs
+    are regenerated from the seed and checked against the fixture's digest."""
+    import hashlib
+    g = np.load(os.path.join(GOLDEN, f"parity_config{config}_n7.npz"))
+    B = int(g["B"])
+    q, qd, goal, sph = make_inputs(config, 7, B)
+    h = hashlib.sha256()
+    for a in (q, qd, goal, sph):
+        h.update(np.ascontiguousarray(a).tobytes())
+    assert h.hexdigest() == str(g["digest"]), "seeded inputs differ from the ones the fixture was computed for"
+    got = product_evaluate(ns, config, 7, q, qd, goal, sph)
+    stats = assert_parity(got, g["ref32"], g["ref64"], n=7, s64=g["s64"], label=f"config{config} B{B} (fixture)",
+                          max_excluded=0.10 if config == 4 else 0.05)
+    if config == 5:
+        assert stats["frac_strict"] >= 0.97, stats
 
 
 def test_reference_style_single_env_call(ns):
@@ -220,7 +240,7 @@ def test_edge_cases(ns):
                         goals=torch.zeros(0, 3, device=dev), spheres=torch.zeros(0, 16, 4, device=dev))
     assert out.shape == (0, n)
     # ragged sizes: B not a multiple of the warp / block, O not a multiple of 8 (non-TMA path), O = 0
-    for B, O_ in ((1, 16), (33, 16), (129, 5), (200, 0), (77, 40), (50, 64)):
+    for B, O_ in ((1, 16), (33, 16), (129, 5), (200, 0), (77, 40), (50, 64), (40, 100)):   # O > 64: the chunked early-out
         q, qd, goal = S.sample_panda_state(B, n, seed=20 + B)
         ofk = H.make_fkine(n, torch.float64)
         frames = S.collision_frames(ofk)

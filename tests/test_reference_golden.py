@@ -18,7 +18,7 @@ from oracle import harness as H
 from oracle import rmp_oracle as O
 from riemannian_motion_policies_b200 import scenarios as S
 
-CASES = [(1, 2), (2, 7), (2, 9), (3, 7), (3, 9), (4, 7), (5, 7)]
+CASES = [(1, 2), (2, 7), (2, 9), (3, 7), (3, 9), (4, 7), (5, 7), (6, 9)]
 
 
 def _rel(a, b):
@@ -29,8 +29,14 @@ def _rel(a, b):
 def test_oracle_matches_reference_source(config, n):
     g = np.load(os.path.join(GOLDEN, f"ref_config{config}_n{n}.npz"))
     sph = g["spheres"] if "spheres" in g else None
-    got32 = H.evaluate_loop(config, n, g["q"], g["qd"], g["goal"], sph, dtype=torch.float32)
-    got64 = H.evaluate_loop(config, n, g["q"], g["qd"], g["goal"], sph, dtype=torch.float64)
+    # one environment per call, the way the reference runs, for the first 16; the 256-environment files go through
+    # the same single-environment function under vmap (identical arithmetic, oracle/harness.py)
+    head = slice(0, 16)
+    loop32 = H.evaluate_loop(config, n, g["q"][head], g["qd"][head], g["goal"][head], None if sph is None else sph[head],
+                             dtype=torch.float32)
+    got32 = H.evaluate_vmap(config, n, g["q"], g["qd"], g["goal"], sph, dtype=torch.float32)
+    got64 = H.evaluate_vmap(config, n, g["q"], g["qd"], g["goal"], sph, dtype=torch.float64)
+    assert (_rel(loop32, g["qdd_ref"][head]) <= np.maximum(1e-5, 4 * _rel(g["qdd_ref"][head], got64[head]))).all()
     e = _rel(got32, g["qdd_ref"])
     yard = _rel(g["qdd_ref"], got64)            # the reference's own float32 distance from the float64 truth
     # same float32 algorithm, possibly different reduction order inside BLAS/SVD: rounding-level agreement,
@@ -87,8 +93,12 @@ def test_fixtures_regenerate_from_the_reference_checkout(tmp_path):
     if not os.path.isdir("/root/reference"):
         pytest.skip("reference checkout not present (GPU box)")
     script = os.path.join(ROOT, "tests", "golden", "run_reference_under_shim.py")
-    res = subprocess.run([sys.executable, script, str(tmp_path)], capture_output=True, text=True, timeout=600)
+    names = ("ref_config1_n2", "ref_config3_n7", "ref_config4_n7", "ref_config6_n9", "ref_v1_two_joint")
+    res = subprocess.run([sys.executable, script, str(tmp_path), "--limit", "2", "--only", *names],
+                         capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stderr[-2000:]
-    for name in ("ref_config3_n7.npz", "ref_config4_n7.npz", "ref_v1_two_joint.npz"):
-        a, b = np.load(os.path.join(GOLDEN, name)), np.load(os.path.join(str(tmp_path), name))
-        np.testing.assert_allclose(a["qdd_ref"], b["qdd_ref"], rtol=1e-5, atol=1e-7)
+    for name in names:
+        a, b = np.load(os.path.join(GOLDEN, name + ".npz")), np.load(os.path.join(str(tmp_path), name + ".npz"))
+        k = b["qdd_ref"].shape[0]
+        np.testing.assert_array_equal(a["q"][:k], b["q"])
+        np.testing.assert_allclose(a["qdd_ref"][:k], b["qdd_ref"], rtol=1e-5, atol=1e-7)

@@ -17,7 +17,8 @@ from riemannian_motion_policies_b200.urdf_model import UrdfModel
 with open(os.path.join(GOLDEN, "urdf_frames.json")) as fh:
     REF = json.load(fh)
 
-FILES = {"panda": S.PANDA_URDF, "panda_wo_tool": S.PANDA_WO_TOOL_URDF, "two_joint": S.TWO_JOINT_URDF}
+FILES = {"panda": S.PANDA_URDF, "panda_wo_tool": S.PANDA_WO_TOOL_URDF, "two_joint": S.TWO_JOINT_URDF,
+         "gantry": S.GANTRY_URDF}
 REFERENCE_FILES = {"panda": "/root/reference/urdf/franka_panda/panda.urdf",
                    "panda_wo_tool": "/root/reference/urdf/franka_panda/panda_wo_tool.urdf",
                    "two_joint": "/root/reference/urdf/TwoJointRobot_wo_fixedJoints.urdf"}
@@ -50,7 +51,7 @@ def test_product_reader_matches_reference_parser(key):
                              [f.xyz for f in m.frames], [f.axis for f in m.frames], [f.has_collision for f in m.frames], paths)
 
 
-@pytest.mark.parametrize("key", sorted(FILES))
+@pytest.mark.parametrize("key", sorted(REFERENCE_FILES))
 def test_readers_on_the_reference_urdfs_when_present(key):
     """In the build container the reference's full URDFs (meshes, inertias) are read directly."""
     path = REFERENCE_FILES[key]
