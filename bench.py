@@ -303,8 +303,7 @@ def fixture_parity(ns, config, n=7):
     B = int(g["B"])
     q, qd, goal, sph = make_inputs(config, n, B)
     got = product_evaluate(ns, config, n, q, qd, goal, sph)
-    out = clause_counts(got, g["ref32"], g["ref64"], g["s64"], n)
-    out.pop("neither_detail", None)
+    out = clause_counts(got, g["ref32"], g["ref64"], g["s64"], n, sens=g["sens"] if "sens" in g else None)
     out["inputs"] = "tests/gpu_common.make_inputs seed, oracle outputs from tests/golden/" + os.path.basename(path)
     return out
 
@@ -374,11 +373,13 @@ def other_config_lines(ns, S, fk, n, device, steps, torch):
 
 def rollout_lines(ns, S, fk, n, device, torch):
     """Closed-loop rollout throughput (rmp2_rollout: 100 simulation steps of dt = 0.01, a control step every 10; full
-    tree = config 5, 64 fixed spheres), replayed from a CUDA graph."""
+    tree = config 5, 16 fixed spheres around a start near the ready pose -- scenarios.closed_loop_scene_device),
+    replayed from a CUDA graph."""
     out = {}
     core, tree, spec = build_tree(ns, S, fk, 5, n)
     for B in (4096, 1 << 20):
-        q0, qd0, goal, spheres = S.synth_inputs_device(fk, n, B, 64, 1, seed=11, device=device)
+        q0, qd0, goal, sph = S.closed_loop_scene_device(fk, n, B, 16, seed=11, device=device)
+        spheres = [sph]
         goals = goal.reshape(B, 1, 3).contiguous()
         q, qd, qdd = q0.clone(), qd0.clone(), torch.empty(B, n, device=device)
         sim_steps, every = 100, 10
@@ -398,7 +399,8 @@ def rollout_lines(ns, S, fk, n, device, torch):
                             "control_steps_per_s": B * (sim_steps // every) / (ms * 1e-3),
                             "sim_steps_per_s": B * sim_steps / (ms * 1e-3), "launch": "CUDA graph replay",
                             "finite": bool(torch.isfinite(q).all().item())}
-        del q0, qd0, goal, spheres, goals, q, qd, qdd, graph
+        out[f"envs_{B}"]["spheres_per_env"] = 16
+        del q0, qd0, goal, sph, spheres, goals, q, qd, qdd, graph
         torch.cuda.empty_cache()
     return out
 

@@ -196,17 +196,19 @@ int rmp2_fk(const rmp2_robot* robot, int32_t frame, int64_t B, const float* q, c
 int rmp2_leaf_evaluate(const rmp2_leaf_desc* leaf, int32_t m, int64_t K, const float* x,
                        const float* xd, const float* aux, float* xdd, float* M, void* stream);
 
-/* On-GPU obstacle feed for primitive obstacles, control point = frame origin.  Stands in for
- * Simulation.calculate_distances (simulation.py:462-484): for every (environment, listed frame,
- * obstacle) it emits one closest-point pair in the reference's distance_data layout.
- *   frames   [n_frames]               frame indices (order of rmp2_robot_create)
- *   spheres  [B][n_spheres][4]        (cx, cy, cz, radius)
- *   capsules [B][n_capsules][8]       (ax, ay, az, bx, by, bz, radius, 0) -- the experiments' cylinders
- *   pairs    [B][n_frames*K][8] out   K = n_spheres + n_capsules; (pos_on_link, pos_on_obstacle, 0, 0),
- *                                     i.e. the rows rmp2_step_io.pairs expects for FRAME_DISTANCE_PAIRS leaves
- *   aux      [B][n_frames*K][4] out   (distance, normal_vec from obstacle to link), may be NULL */
-int rmp2_obstacle_feed(const rmp2_robot* robot, const int32_t* frames, int32_t n_frames, int64_t B,
-                       const float* q, const float* spheres, int32_t n_spheres, const float* capsules,
+/* On-GPU obstacle feed with primitive geometry on both sides.  Stands in for Simulation.calculate_distances
+ * (simulation.py:462-484: p.getClosestPoints between a link's collision shape and an obstacle): for every
+ * (environment, listed frame, obstacle) it emits one closest-point pair in the reference's distance_data layout.
+ *   frames        [n_frames]            frame indices (order of rmp2_robot_create)
+ *   link_capsules [n_frames][8] HOST    the link geometry riding on each listed frame, one capsule in FRAME coordinates
+ *                                       (ax, ay, az, bx, by, bz, radius, 0); NULL = the frame origin as control point
+ *   spheres       [B][n_spheres][4]     (cx, cy, cz, radius); 16-byte aligned
+ *   capsules      [B][n_capsules][8]    (ax, ay, az, bx, by, bz, radius, 0) -- the experiments' cylinders; 16-byte aligned
+ *   pairs    [B][n_frames*K][8] out     K = n_spheres + n_capsules; (pos_on_link, pos_on_obstacle, 0, 0), both on the
+ *                                       surfaces, i.e. the rows rmp2_step_io.pairs expects for FRAME_DISTANCE_PAIRS leaves
+ *   aux      [B][n_frames*K][4] out     (surface distance, normal_vec from obstacle to link), may be NULL */
+int rmp2_obstacle_feed(const rmp2_robot* robot, const int32_t* frames, const float* link_capsules, int32_t n_frames,
+                       int64_t B, const float* q, const float* spheres, int32_t n_spheres, const float* capsules,
                        int32_t n_capsules, float* pairs, float* aux, void* stream);
 
 /* x = pinv(M) f for B independent n x n systems, M [B][n][n], f [B][n], x [B][n] (device, row-major), with

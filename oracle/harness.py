@@ -126,3 +126,64 @@ def rollout(config, n, q, qd, goal, spheres, dt, n_steps, control_every, dtype=t
         qd = qd + qdd * dt
         q = q + qd * dt
     return q, qd, qdd
+
+
+EPS32 = float(np.finfo(np.float32).eps)
+
+
+def perturbed(arrays, k):
+    """float64 copies of `arrays` [B, ...] with every component moved by a relative eps32 * U(-1, 1) (seeded by k):
+    what merely ROUNDING THE INPUTS to float32 differently does.  The draw has the shape of ONE environment and is
+    shared by the batch, so an environment's sensitivity does not depend on what else is in the batch.  None stays None."""
+    rng = np.random.RandomState(1234 + k)
+    return [None if a is None else np.asarray(a, dtype=np.float64) * (1.0 + EPS32 * rng.uniform(-1, 1, size=np.shape(a)[1:]))
+            for a in arrays]
+
+
+def sensitivity(fn, arrays, K=4):
+    """Condition of a step for float32 inputs, per environment: the largest relative change of fn's float64 output
+    over K seeded eps32-relative perturbations of all inputs.  fn(*arrays_f64) -> [B, n].  A float32 evaluation
+    cannot be expected to be closer to the float64 truth than a small multiple of this (backward-error view: the
+    result is the exact result for inputs that differ by rounding); it covers every amplification mechanism at once
+    -- the conditioning of the combined metric, the 1/std_dev gains inside the obstacle leaf, the poles of the
+    velocity-cap metric, a pinv truncation about to flip."""
+    base = fn(*[None if a is None else np.asarray(a, dtype=np.float64) for a in arrays])
+    S = np.zeros(base.shape[0])
+    den = np.maximum(np.linalg.norm(base, axis=-1), 1e-30)
+    for k in range(K):
+        out = fn(*perturbed(arrays, k))
+        S = np.maximum(S, np.linalg.norm(out - base, axis=-1) / den)
+    return S
+
+
+def metric_sensitivity(M, f, K=4):
+    """The same for the resolve alone: largest relative change of pinv(M) f (float64, TensorFlow's float32 cutoff)
+    when every entry of the combined M / f moves by eps32 * max|M| (max|f|) * U(-1, 1).  Float32 accumulation of the
+    combined metric leaves exactly this kind of unstructured noise on it; perturbing the INPUTS instead keeps the
+    structure of J^T A J (an exactly rank-deficient sum stays rank deficient) and so cannot see the conditioning of a
+    metric whose small kept singular values sit just above the cutoff (config 4)."""
+    M, f = torch.as_tensor(np.asarray(M, dtype=np.float64)), torch.as_tensor(np.asarray(f, dtype=np.float64))
+    solve = lambda M_, f_: (O.tf_pinv(M_) @ f_[..., None])[..., 0].numpy()
+    base = solve(M, f)
+    den = np.maximum(np.linalg.norm(base, axis=-1), 1e-30)
+    mM, mf = M.abs().amax(dim=(1, 2))[:, None, None], f.abs().amax(dim=1)[:, None]
+    S = np.zeros(base.shape[0])
+    for k in range(K):
+        rng = np.random.RandomState(4321 + k)
+        dM = torch.as_tensor(rng.uniform(-1, 1, size=tuple(M.shape[1:])))        # one draw, shared by the batch
+        df = torch.as_tensor(rng.uniform(-1, 1, size=tuple(f.shape[1:])))
+        out = solve(M + EPS32 * mM * dM, f + EPS32 * mf * df)
+        S = np.maximum(S, np.linalg.norm(out - base, axis=-1) / den)
+    return S
+
+
+def config_sensitivity(config, n, q, qd, goal, spheres=None, K=4, fkine=None):
+    """Float32 conditioning of the scenario trees per environment: the larger of `sensitivity` (inputs rounded
+    differently) and `metric_sensitivity` (float32 noise on the combined metric), float64 oracle under vmap."""
+    fk = fkine or make_fkine(n, torch.float64, robot="gantry" if config == 6 else None)
+    fn = lambda q_, qd_, goal_, sph_: evaluate_vmap(config, n, q_, qd_, goal_, sph_, dtype=torch.float64, fkine=fk)
+    S_in = sensitivity(fn, [q, qd, goal, spheres], K=K)
+    f64, M64 = combined_vmap(config, n, np.asarray(q, dtype=np.float64), np.asarray(qd, dtype=np.float64),
+                             np.asarray(goal, dtype=np.float64),
+                             None if spheres is None else np.asarray(spheres, dtype=np.float64), dtype=torch.float64, fkine=fk)
+    return np.maximum(S_in, metric_sensitivity(M64, f64, K=K))

@@ -121,7 +121,7 @@ def lib():
     L.rmp2_fk.restype = ctypes.c_int
     L.rmp2_leaf_evaluate.argtypes = [ctypes.POINTER(LeafDesc), i32, i64, vp, vp, vp, vp, vp, vp]
     L.rmp2_leaf_evaluate.restype = ctypes.c_int
-    L.rmp2_obstacle_feed.argtypes = [vp, vp, i32, i64, vp, vp, i32, vp, i32, vp, vp, vp]
+    L.rmp2_obstacle_feed.argtypes = [vp, vp, vp, i32, i64, vp, vp, i32, vp, i32, vp, vp, vp]
     L.rmp2_obstacle_feed.restype = ctypes.c_int
     L.rmp2_last_error.argtypes = []
     L.rmp2_last_error.restype = ctypes.c_char_p

@@ -928,9 +928,9 @@ int rmp2_fk(const rmp2_robot* rb, int32_t frame, int64_t B, const float* q, cons
   return RMP2_OK;
 }
 
-int rmp2_obstacle_feed(const rmp2_robot* rb, const int32_t* frames, int32_t n_frames, int64_t B, const float* q,
-                       const float* spheres, int32_t n_spheres, const float* capsules, int32_t n_capsules,
-                       float* pairs, float* aux, void* stream) {
+int rmp2_obstacle_feed(const rmp2_robot* rb, const int32_t* frames, const float* link_capsules, int32_t n_frames,
+                       int64_t B, const float* q, const float* spheres, int32_t n_spheres, const float* capsules,
+                       int32_t n_capsules, float* pairs, float* aux, void* stream) {
   if (!rb || !frames || !q || !pairs) return fail(RMP2_ERR_INVALID, "robot, frames, q and pairs are required");
   if (n_frames <= 0 || n_frames > RMP2_MAX_LEAVES) return fail(RMP2_ERR_INVALID, "n_frames out of range");
   if (n_spheres < 0 || n_capsules < 0 || (n_spheres > 0 && !spheres) || (n_capsules > 0 && !capsules))
@@ -962,7 +962,12 @@ int rmp2_obstacle_feed(const rmp2_robot* rb, const int32_t* frames, int32_t n_fr
   A.n_spheres = n_spheres;
   A.n_capsules = n_capsules;
   A.n_listed = n_frames;
-  cudaError_t e = rmp2_launch_feed(tmp->tab, A, (cudaStream_t)stream);
+  FeedLinks LK;
+  memset(&LK, 0, sizeof(LK));
+  if (link_capsules)
+    for (int i = 0; i < n_frames; ++i)
+      for (int k = 0; k < 7; ++k) LK.c[i][k] = link_capsules[(size_t)i * 8 + k];
+  cudaError_t e = rmp2_launch_feed(tmp->tab, LK, A, (cudaStream_t)stream);
   rmp2_tree_destroy(tmp);
   if (e != cudaSuccess) return cuda_fail(e, "rmp2_obstacle_feed launch");
   g_launches.fetch_add(1);

@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 #define RMP2_SPHERES_MIN_BLOCKS 5     // resident blocks per SM the register allocation aims at (<= 102 registers)
 #endif
 #ifndef RMP2_SQRT_NEWTON
-#define RMP2_SQRT_NEWTON 1            // refine the pair distance to correctly-rounded accuracy (4 lane operations per pair)
+// 1: refine the pair distance |r| = dc2 * rsqrt(dc2) with one Newton step (4 lane operations per pair, +8 % kernel
+// time).  Measured on a B200 (profiles/r2_parity_study.json): no effect on parity -- 7 instead of 8 of 4096 config-5
+// environments beyond the 1e-5 bar, all of them explained by the float32 conditioning of the step itself -- so off.
+#define RMP2_SQRT_NEWTON 0
 #endif
 #ifndef RMP2_SPHERES_STEPS_PER_TRIP
 #define RMP2_SPHERES_STEPS_PER_TRIP 4 // packed (two-sphere) steps per loop trip
@@ -197,9 +200,8 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
     const float2 dc2 = __ffma2_rn(rx, rx, __ffma2_rn(ry, ry, __ffma2_rn(rz, rz, bc2(1e-24f))));
     const float2 inv_dc = make_float2(fast_rsqrt(dc2.x), fast_rsqrt(dc2.y));
 #if RMP2_SQRT_NEWTON
-    // |r| to ~0.5 ulp: one Newton step on dc = dc2 * rsqrt(dc2) (the residual dc2 - dc^2 is exact in an FMA).
-    // MUFU.RSQ alone is good to 2 ulp, and the leaf amplifies an error of the distance by 1 / repulsion_std_dev
-    // (= 100 with the experiments' gains, rmp2.py:189) -- enough to miss the 1e-5 parity bar for close spheres.
+    // |r| to ~0.5 ulp instead of MUFU.RSQ's 2 ulp: one Newton step on dc = dc2 * rsqrt(dc2) (the residual
+    // dc2 - dc^2 is exact in an FMA).  Experiment knob, see RMP2_SQRT_NEWTON above.
     const float2 dc0 = __fmul2_rn(dc2, inv_dc);
     const float2 res = __ffma2_rn(neg2(dc0), dc0, dc2);
     const float2 dc = __ffma2_rn(res, __fmul2_rn(inv_dc, bc2(0.5f)), dc0);
@@ -245,22 +247,23 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
         mask_odd |= (uint32_t)(dc2.y <= lim2.y) << (o >> 1);
       }
     };
-    // phase 3: the pairs of the set bits, an even with an odd sphere per packed step
+    // phase 3: the pairs of the set bits, an even with an odd sphere per packed step, two packed steps per trip
+    // (independent until their last FMAs, so the MUFU latencies of one overlap the arithmetic of the other; the
+    // trip is branch-free: an exhausted list keeps yielding the far-away sphere)
     auto masked_pairs = [&](int o0, uint32_t mask_even, uint32_t mask_odd) {
       const float4 far_away = make_float4(px + 1e15f, py, pz, 0.f);
+      auto next = [&](uint32_t& mask, int parity) -> float4 {
+        const bool have = mask != 0u;
+        const int k = have ? __ffs((int)mask) - 1 : 0;
+        mask &= mask - 1u;                                        // 0 stays 0
+        const float4 s = load_sphere(o0 + 2 * k + parity);        // a valid row entry either way
+        return have ? s : far_away;
+      };
       while (mask_even | mask_odd) {
-        float4 s0 = far_away, s1 = far_away;
-        if (mask_even) {
-          const int k = __ffs((int)mask_even) - 1;
-          mask_even &= mask_even - 1u;
-          s0 = load_sphere(o0 + 2 * k);
-        }
-        if (mask_odd) {
-          const int k = __ffs((int)mask_odd) - 1;
-          mask_odd &= mask_odd - 1u;
-          s1 = load_sphere(o0 + 2 * k + 1);
-        }
-        two_spheres(s0, s1);
+        const float4 a0 = next(mask_even, 0), a1 = next(mask_odd, 1);
+        const float4 b0 = next(mask_even, 0), b1 = next(mask_odd, 1);
+        two_spheres(a0, a1);
+        two_spheres(b0, b1);
       }
     };
     if (!sorted) {
@@ -435,14 +438,50 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 }
 
 // --------------------------------------------------------------------------------- feed kernel
-// On-GPU stand-in for Simulation.calculate_distances (reference: simulation.py:462-484) with primitive
-// obstacles and the frame origin as control point: for every (environment, listed frame, obstacle) one
-// closest-point pair in the reference's distance_data layout -- pair row (pos_on_link, pos_on_obstacle,
-// 0, 0) and aux row (distance, normal from obstacle to link).  Marker leaves carry the listing index of
-// their frame in LeafTab::pair_set.  Spheres: (c, r); capsules: (a, b, r, 0).
+// On-GPU stand-in for Simulation.calculate_distances (reference: simulation.py:462-484, p.getClosestPoints between
+// a link's collision geometry and an obstacle) with primitive geometry on both sides: every listed frame carries a
+// capsule fixed in the frame (FeedLinks; degenerate = the frame origin), obstacles are spheres (c, r) and capsules
+// (a, b, r, 0).  For every (environment, listed frame, obstacle) one closest-point pair in the reference's
+// distance_data layout -- pair row (pos_on_link, pos_on_obstacle, 0, 0) and aux row (distance, normal from obstacle
+// to link).  Marker leaves carry the listing index of their frame in LeafTab::pair_set.
+RMP2_DEV float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
+
+// closest points of the segments P1 + s d1 and P2 + t d2, s, t in [0, 1] (either may be a point)
+RMP2_DEV void closest_on_segments(const float (&P1)[3], const float (&d1)[3], const float (&P2)[3], const float (&d2)[3],
+                                  float& s, float& t) {
+  const float r[3] = {P1[0] - P2[0], P1[1] - P2[1], P1[2] - P2[2]};
+  const float a = fmaf(d1[0], d1[0], fmaf(d1[1], d1[1], d1[2] * d1[2]));
+  const float e = fmaf(d2[0], d2[0], fmaf(d2[1], d2[1], d2[2] * d2[2]));
+  const float f = fmaf(d2[0], r[0], fmaf(d2[1], r[1], d2[2] * r[2]));
+  const float c = fmaf(d1[0], r[0], fmaf(d1[1], r[1], d1[2] * r[2]));
+  const float eps = 1e-12f;
+  if (a <= eps) {                                  // first segment is a point
+    s = 0.f;
+    t = (e <= eps) ? 0.f : clamp01(f / e);
+    return;
+  }
+  if (e <= eps) {                                  // second segment is a point
+    t = 0.f;
+    s = clamp01(-c / a);
+    return;
+  }
+  const float b = fmaf(d1[0], d2[0], fmaf(d1[1], d2[1], d1[2] * d2[2]));
+  const float denom = fmaf(a, e, -b * b);          // >= 0, 0 for parallel segments
+  s = (denom > eps * a * e) ? clamp01(fmaf(b, f, -c * e) / denom) : 0.f;
+  t = fmaf(b, s, f) / e;
+  if (t < 0.f) {
+    t = 0.f;
+    s = clamp01(-c / a);
+  } else if (t > 1.f) {
+    t = 1.f;
+    s = clamp01((b - c) / a);
+  }
+}
+
 template <int N>
 __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
-    rmp2_feed_kernel(const __grid_constant__ StepTables T, const __grid_constant__ FeedArgs A) {
+    rmp2_feed_kernel(const __grid_constant__ StepTables T, const __grid_constant__ FeedLinks LK,
+                     const __grid_constant__ FeedArgs A) {
   extern __shared__ float slots[];
   const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= A.B) return;
@@ -463,31 +502,44 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
       const int listing = T.leaves[li].pair_set;
       float* prow = A.pairs + ((size_t)env * A.n_listed * K + (size_t)listing * K) * RMP2_PAIR_FLOATS;
       float* arow = A.aux ? A.aux + ((size_t)env * A.n_listed * K + (size_t)listing * K) * 4 : nullptr;
+      // the frame's control capsule in world coordinates
+      const float* lc = LK.c[listing];
+      float la[3], lb[3], P1[3], d1[3];
+      matvec3(ch.R, lc, la);
+      matvec3(ch.R, lc + 3, lb);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        P1[i] = ch.p[i] + la[i];
+        d1[i] = lb[i] - la[i];
+      }
+      const float link_r = lc[6];
       for (int o = 0; o < K; ++o) {
-        float cx, cy, cz, rad;
+        float P2[3], d2[3] = {0.f, 0.f, 0.f}, rad;
         if (o < A.n_spheres) {
           const float4 sp = __ldg(reinterpret_cast<const float4*>(A.spheres) + (size_t)env * A.n_spheres + o);
-          cx = sp.x, cy = sp.y, cz = sp.z, rad = sp.w;
+          P2[0] = sp.x, P2[1] = sp.y, P2[2] = sp.z, rad = sp.w;
         } else {
           const float4* cp = reinterpret_cast<const float4*>(A.capsules) + ((size_t)env * A.n_capsules + (o - A.n_spheres)) * 2;
           const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1);          // (ax ay az bx) (by bz r 0)
-          const float ux = c0.w - c0.x, uy = c1.x - c0.y, uz = c1.y - c0.z;
-          const float uu = fmaf(ux, ux, fmaf(uy, uy, uz * uz));
-          float t = fmaf(ch.p[0] - c0.x, ux, fmaf(ch.p[1] - c0.y, uy, (ch.p[2] - c0.z) * uz));
-          t = (uu > 0.f) ? fminf(fmaxf(t / uu, 0.f), 1.f) : 0.f;    // closest point of the axis segment
-          cx = fmaf(t, ux, c0.x), cy = fmaf(t, uy, c0.y), cz = fmaf(t, uz, c0.z), rad = c1.z;
+          P2[0] = c0.x, P2[1] = c0.y, P2[2] = c0.z;
+          d2[0] = c0.w - c0.x, d2[1] = c1.x - c0.y, d2[2] = c1.y - c0.z;
+          rad = c1.z;
         }
-        const float rx = ch.p[0] - cx, ry = ch.p[1] - cy, rz = ch.p[2] - cz;
+        float s, t;
+        closest_on_segments(P1, d1, P2, d2, s, t);
+        const float c1x = fmaf(s, d1[0], P1[0]), c1y = fmaf(s, d1[1], P1[1]), c1z = fmaf(s, d1[2], P1[2]);
+        const float c2x = fmaf(t, d2[0], P2[0]), c2y = fmaf(t, d2[1], P2[1]), c2z = fmaf(t, d2[2], P2[2]);
+        const float rx = c1x - c2x, ry = c1y - c2y, rz = c1z - c2z;
         const float dc = sqrtf(fmaxf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)), 1e-24f));
         const float inv = 1.f / dc;
         const float nx = rx * inv, ny = ry * inv, nz = rz * inv;
         float* pr = prow + (size_t)o * RMP2_PAIR_FLOATS;
-        pr[0] = ch.p[0], pr[1] = ch.p[1], pr[2] = ch.p[2];
-        pr[3] = fmaf(rad, nx, cx), pr[4] = fmaf(rad, ny, cy), pr[5] = fmaf(rad, nz, cz);
+        pr[0] = fmaf(-link_r, nx, c1x), pr[1] = fmaf(-link_r, ny, c1y), pr[2] = fmaf(-link_r, nz, c1z);
+        pr[3] = fmaf(rad, nx, c2x), pr[4] = fmaf(rad, ny, c2y), pr[5] = fmaf(rad, nz, c2z);
         pr[6] = 0.f, pr[7] = 0.f;
         if (arow) {
           float* ar = arow + (size_t)o * 4;
-          ar[0] = dc - rad, ar[1] = nx, ar[2] = ny, ar[3] = nz;
+          ar[0] = dc - rad - link_r, ar[1] = nx, ar[2] = ny, ar[3] = nz;
         }
       }
     }
@@ -861,7 +913,7 @@ cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, si
   return cudaSuccess;
 }
 
-cudaError_t rmp2_launch_feed(const StepTables& T, const FeedArgs& A, cudaStream_t stream) {
+cudaError_t rmp2_launch_feed(const StepTables& T, const FeedLinks& LK, const FeedArgs& A, cudaStream_t stream) {
   const int block = RMP2_BLOCK_THREADS;
   const long long blocks = (A.B + block - 1) / block;
   if (blocks <= 0) return cudaSuccess;
@@ -871,7 +923,7 @@ cudaError_t rmp2_launch_feed(const StepTables& T, const FeedArgs& A, cudaStream_
     RMP2_DISPATCH_N(T.n, (e = allow_dynamic_smem((const void*)rmp2_feed_kernel<NN>, smem)));
     if (e != cudaSuccess) return e;
   }
-  RMP2_DISPATCH_N(T.n, (rmp2_feed_kernel<NN><<<(unsigned)blocks, block, smem, stream>>>(T, A)));
+  RMP2_DISPATCH_N(T.n, (rmp2_feed_kernel<NN><<<(unsigned)blocks, block, smem, stream>>>(T, LK, A)));
   return cudaGetLastError();
 }
 

@@ -31,7 +31,7 @@ cudaError_t rmp2_launch_pinv(int n, float rcond, bool pivot, int mode, long long
 // which: 0 frames, 1 spheres, 2 step (fused resolve), 3 step (split), 4 resolve, 5 resolve fallback (Jacobi)
 cudaError_t rmp2_kernel_attributes(int n, int which, bool use_tma, int block, size_t smem, int* regs,
                                    int* blocks_per_sm);
-cudaError_t rmp2_launch_feed(const StepTables& T, const FeedArgs& A, cudaStream_t stream);
+cudaError_t rmp2_launch_feed(const StepTables& T, const FeedLinks& LK, const FeedArgs& A, cudaStream_t stream);
 cudaError_t rmp2_launch_fk(const StepTables& T, long long B, const float* q, const float* qd, float* x, float* xd,
                            float* J, float* c, cudaStream_t stream);
 cudaError_t rmp2_launch_leaf(const LeafTab& L, const LeafVec& V, int m, long long K, const float* x, const float* xd,

@@ -73,6 +73,12 @@ struct FeedArgs {
   int32_t n_spheres, n_capsules, n_listed;
 };
 
+// Control geometry of the listed frames for the obstacle feed: one capsule per frame in FRAME coordinates
+// (ax ay az bx by bz radius 0); a zero-length, zero-radius capsule at the origin = the frame origin as control point.
+struct FeedLinks {
+  float c[RMP2_MAX_LEAVES][8];
+};
+
 struct ResolveArgs {
   int32_t n;
   float rcond;

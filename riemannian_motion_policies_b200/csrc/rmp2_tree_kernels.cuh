@@ -333,9 +333,7 @@ RMP2_DEV void step_body(const StepTables& T, const StepArgs& A) {
             const float rz = __ldg(row + 2) - __ldg(row + 5);
             const float d2 = fmaxf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)), 1e-24f);
             const float inv_d = fast_rsqrt(d2);
-            const float d0 = d2 * inv_d;                                   // + one Newton step: see rmp2_spheres_kernel
-            const float d = fmaf(fmaf(-d0, d0, d2), 0.5f * inv_d, d0);
-            obstacle_pair(L.p, rx * inv_d, ry * inv_d, rz * inv_d, d, inv_d, ch.v, ch.a, vv, S, g);
+            obstacle_pair(L.p, rx * inv_d, ry * inv_d, rz * inv_d, d2 * inv_d, inv_d, ch.v, ch.a, vv, S, g);
           }
           contrib = true;
         } else {  // RMP2_SPACE_FRAME_POINTS: points fixed in the frame (v1 CollisionAvoidance)

@@ -260,3 +260,35 @@ def synth_inputs_device(fk, n, B, O_, n_buffers, seed, device):
                 sph[bad] = draw(nbad)
             spheres.append(sph.contiguous())
     return q.contiguous(), qd.contiguous(), goal.contiguous(), spheres
+
+
+def closed_loop_scene_device(fk, n, B, O_, seed, device):
+    """Scenes a closed loop is well behaved in (the situation of experiments/franka_panda/06_cluttered_environment.py),
+    generated on the device: start near the ready pose at rest, a goal inside the workspace, O_ spheres anywhere around
+    but at least 0.12 m (surface) from every collision frame of the start pose and from the goal.
+    -> q0 [B,n], qd0 [B,n], goal [B,3], spheres [B,O_,4]."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    rand = lambda *shape: torch.rand(*shape, generator=g, device=device)
+    q0 = torch.tensor(PANDA_Q_READY[:n], dtype=torch.float32, device=device) + (-0.05 + 0.1 * rand(B, n))
+    glo, ghi = torch.tensor([0.3, -0.35, 0.25], device=device), torch.tensor([0.6, 0.35, 0.65], device=device)
+    goal = glo + (ghi - glo) * rand(B, 3)
+    origins = torch.stack([fk.forward(q0, fr)[:, :3, 3] for fr in collision_frames(fk)], dim=1)      # [B,K,3]
+    slo, shi = torch.tensor([-0.2, -0.6, 0.0], device=device), torch.tensor([0.8, 0.6, 1.0], device=device)
+
+    def draw(count):
+        return torch.cat([slo + (shi - slo) * rand(count, 3), 0.03 + 0.05 * rand(count, 1)], dim=-1)
+
+    sph = draw(B * O_).reshape(B, O_, 4)
+    for _round in range(40):
+        bad = torch.linalg.norm(sph[:, :, :3] - goal[:, None, :], dim=-1) - sph[:, :, 3] < 0.12
+        for k in range(origins.shape[1]):
+            bad |= torch.linalg.norm(sph[:, :, :3] - origins[:, None, k, :], dim=-1) - sph[:, :, 3] < 0.12
+        nbad = int(bad.sum())
+        if nbad == 0:
+            break
+        sph[bad] = draw(nbad)
+    else:
+        sph[bad] = torch.tensor([3.0, 3.0, 3.0, 0.05], device=device)
+    return q0.contiguous(), torch.zeros_like(q0), goal.contiguous(), sph.contiguous()

@@ -4,8 +4,8 @@
 
 For B = 4096 seeded environments of configs 4 and 5 (inputs: tests/gpu_common.make_inputs, regenerated from
 the seed by the tests) it stores what the parity criterion needs: the oracle's float32 and float64 outputs,
-the singular values of the float64 combined metric (kappa, distance from the pinv cutoff) and a checksum of the
-inputs.  Precomputed because the oracle needs minutes for 4096 environments of the 64-sphere trees -- time the
+the singular values of the float64 combined metric (distance from the pinv cutoff), the float32-input sensitivity of
+every environment (oracle/harness.sensitivity) and a checksum of the inputs.  Precomputed because the oracle needs minutes for 4096 environments of the 64-sphere trees -- time the
 GPU tests and bench.py should not spend on the GPU box.
 """
 import hashlib
@@ -41,8 +41,9 @@ def main():
         ref64 = H.evaluate_vmap(config, N, q, qd, goal, sph, dtype=torch.float64)
         _, M64 = H.combined_vmap(config, N, q, qd, goal, sph, dtype=torch.float64)
         s64 = np.linalg.svd(M64, compute_uv=False)
+        sens = H.config_sensitivity(config, N, q, qd, goal, sph)      # float32-input condition of every environment
         out = os.path.join(HERE, f"parity_config{config}_n{N}.npz")
-        np.savez_compressed(out, B=B, ref32=ref32.astype(np.float32), ref64=ref64, s64=s64,
+        np.savez_compressed(out, B=B, ref32=ref32.astype(np.float32), ref64=ref64, s64=s64, sens=sens,
                             digest=np.array(input_digest(q, qd, goal, sph)))
         print("wrote", out)
         if os.environ.get("RMP2_STUDY_DIR"):       # (M, f) in float32 for the solver study (tools/parity_study.py)

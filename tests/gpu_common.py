@@ -41,54 +41,70 @@ def rel_err(a, b):
     return np.linalg.norm(a - b, axis=-1) / np.maximum(np.linalg.norm(b, axis=-1), 1e-30)
 
 
-# float32 floor of the resolve, MEASURED (tools/parity_study.py on a B200 -> profiles/r2_parity_study.json, 4096
-# config-4 environments): with kappa = sigma_max / smallest kept singular value of the combined metric, the error of
-# a float32 evaluation against the float64 truth divided by kappa * eps32 reaches 0.97 for LAPACK gesdd applied to the
-# SAME float32 (M, f) (gesvd 0.81, this library's solver 0.81), and 3.83 for the whole float32 oracle pipeline (q999:
-# 1.95); the CUDA step stays below 1.65 (q999: 1.43).  The constant is the oracle's own maximum, rounded up.
-KAPPA_FLOOR = 4.0
+# Factor on the float32 conditioning S of an environment (oracle/harness.config_sensitivity: the largest relative change
+# of the float64 oracle's output over 4 seeded perturbations, either of every INPUT by a relative eps32 * U(-1, 1), or of
+# every entry of the combined metric / force by eps32 * max|M| * U(-1, 1) -- the noise float32 accumulation leaves on it).
+# MEASURED on the FLOAT32 ORACLE ITSELF (tests/golden/make_parity_fixtures.py, 4096 seeded environments each of configs
+# 4 and 5, recorded in profiles/r2_parity_study.json): its own distance from the float64 truth reaches 4.39 x S (config
+# 4; q999: 3.17) and 4.05 x S (config 5; q999: 3.65).  The factor is that maximum rounded up; the CUDA step is held to it.
+SENS_FACTOR = 5.0
 
 
-def assert_parity(got, ref32, ref64, M64=None, n=None, label="", max_excluded=0.05, s64=None):
-    """Parity criterion.  Per environment, with e32 = |got - ref32|/|ref32|,
-    e64 = |got - ref64|/|ref64|, yard = |ref32 - ref64|/|ref64| (the float32 restatement's own distance from the
-    float64 truth) and kappa = sigma_max / smallest kept singular value of the combined metric M:
+def config_sens(config, n, q, qd, goal, sph):
+    """Lazy sensitivity of the scenario trees: callable(idx) -> S[idx] (only the environments that need it)."""
+    def at(idx):
+        return H.config_sensitivity(config, n, q[idx], qd[idx], goal[idx], None if sph is None else sph[idx])
+    return at
 
-        (a) e32 <= 1e-5                               the north-star bar, or
-        (b) e64 <= max(1e-5, 2 * yard)                SURVEY's fallback: not worse than the float32 reference itself, or
-        (c) e64 <= KAPPA_FLOOR * kappa * eps32        the measured float32 floor for this environment's metric
 
-    plus, over the batch, the kernel must be statistically as close to the truth as the float32 restatement is:
-    median(e64) <= 2 median(yard), q99(e64) <= 3 q99(yard).  Environments with a singular value within a factor 4
-    of the pinv cutoff are excluded (the truncation is discontinuous there); they must stay below 5 % of the batch
-    (10 % for the rank-deficient config 4 tree, whose weak obstacle metrics put a continuum of singular values
-    around the cutoff).  The returned stats carry the pass count of every clause.  M64 [B,n,n] or its singular
-    values s64 [B,n] supply kappa; without either kappa = 1 and clause (c) is inert."""
-    eps32 = np.finfo(np.float32).eps
+def assert_parity(got, ref32, ref64, M64=None, n=None, label="", max_excluded=0.05, s64=None, sens=None):
+    """Parity criterion (two clauses).  Per environment, with e32 = |got - ref32|/|ref32| and
+    e64 = |got - ref64|/|ref64| (ref32 / ref64: the oracle in float32 -- the reference-faithful mode -- and float64):
+
+        (a) e32 <= 1e-5                                       the north-star bar, or
+        (b) e64 <= max(1e-5, SENS_FACTOR * S)                 within the float32 conditioning of this environment
+
+    S = the environment's float32-input sensitivity (see SENS_FACTOR; `sens`: an array [B] or a callable idx -> S[idx],
+    evaluated only for the environments that fail (a) and e64 <= 1e-5).  Where a test cannot supply S (`sens` None) the
+    yardstick is SURVEY's original fallback, the float32 oracle's own distance from the truth:
+    e64 <= max(1e-5, 2 * yard), yard = |ref32 - ref64|/|ref64|.
+
+    Plus, over the batch, the kernel must be statistically as close to the truth as the float32 oracle is:
+    median(e64) <= 2 median(yard), q99(e64) <= 3 q99(yard).  Environments with a singular value of the combined metric
+    within a factor 4 of the pinv cutoff are excluded (the truncation is discontinuous there; M64 [B,n,n] or its
+    singular values s64 [B,n]); they must stay below 5 % of the batch (10 % for the rank-deficient config 4 tree,
+    whose weak obstacle metrics put a continuum of singular values around the cutoff).  The returned stats carry the
+    pass count of each clause."""
     e32 = rel_err(got, ref32)
     e64 = rel_err(got, ref64)
     yard = rel_err(ref32, ref64)
     excluded = np.zeros(e32.shape, dtype=bool)
-    kappa = np.ones(e32.shape)
     if s64 is None and M64 is not None:
         s64 = np.linalg.svd(M64, compute_uv=False)
     if s64 is not None:
-        excluded, kappa = spectrum_guards(s64, n)
-    pass_a = e32 <= REL_TOL
-    pass_b = e64 <= np.maximum(REL_TOL, 2 * yard)
-    pass_c = e64 <= KAPPA_FLOOR * kappa * eps32
-    bad = ~(pass_a | pass_b | pass_c) & ~excluded
+        excluded, _ = spectrum_guards(s64, n)
     keep = ~excluded
+    pass_a = e32 <= REL_TOL
+    pass_b = e64 <= REL_TOL
+    need = np.flatnonzero(~pass_a & ~pass_b & keep)
+    bound = np.full(e32.shape, REL_TOL)
+    if len(need):
+        if sens is None:
+            bound[need] = np.maximum(REL_TOL, 2 * yard[need])
+        else:
+            S_need = np.asarray(sens(need) if callable(sens) else np.asarray(sens)[need], dtype=np.float64)
+            bound[need] = np.maximum(REL_TOL, SENS_FACTOR * S_need)
+        pass_b = e64 <= bound
+    bad = ~(pass_a | pass_b) & keep
     stats = dict(envs=int(len(e32)), kept=int(keep.sum()), excluded=int(excluded.sum()),
                  pass_a_strict=int((pass_a & keep).sum()), pass_b_only=int((~pass_a & pass_b & keep).sum()),
-                 pass_c_only=int((~pass_a & ~pass_b & pass_c & keep).sum()),
+                 failed=int(bad.sum()), yardstick="float32-input sensitivity" if sens is not None else "float32 oracle (yard)",
                  frac_strict=float(pass_a[keep].mean()), median_e32=float(np.median(e32[keep])),
                  median_e64=float(np.median(e64[keep])), median_yard=float(np.median(yard[keep])),
-                 q99_e64=float(np.quantile(e64[keep], 0.99)), q99_yard=float(np.quantile(yard[keep], 0.99)),
-                 median_kappa=float(np.median(kappa[keep])))
+                 q99_e64=float(np.quantile(e64[keep], 0.99)), q99_yard=float(np.quantile(yard[keep], 0.99)))
     print(f"[parity] {label}: {stats}")
     assert not bad.any(), (f"{label}: {int(bad.sum())}/{len(bad)} envs out of tolerance; worst e32={e32[bad].max():.3e} "
-                           f"e64={e64[bad].max():.3e} yard={yard[bad].max():.3e} kappa={kappa[bad].max():.3e} {stats}")
+                           f"e64={e64[bad].max():.3e} bound={bound[bad].min():.3e} yard={yard[bad].max():.3e} {stats}")
     assert excluded.mean() < max_excluded, f"{label}: too many envs near the pinv cutoff ({excluded.mean():.3f})"
     if keep.sum() >= 200:
         assert stats["median_e64"] <= 2 * stats["median_yard"] + 1e-7, f"{label}: {stats}"
@@ -107,28 +123,32 @@ def spectrum_guards(s, n):
     return excluded, kappa
 
 
-def clause_counts(got, ref32, ref64, s64, n):
-    """How many environments pass which clause of the parity criterion, and the float32 error constants
-    err / (kappa eps32) of the kernel and of the float32 oracle itself (tools/parity_study.py, bench.py)."""
+def clause_counts(got, ref32, ref64, s64, n, sens=None):
+    """How many environments pass which clause of the parity criterion, and how far the kernel and the float32 oracle
+    itself sit from the float64 truth in units of the environment's float32-input sensitivity S (and of kappa * eps32,
+    kappa = conditioning of the combined metric) -- tools/parity_study.py, bench.py."""
     eps32 = np.finfo(np.float32).eps
     e32, e64, yard = rel_err(got, ref32), rel_err(got, ref64), rel_err(ref32, ref64)
     excluded, kappa = spectrum_guards(s64, n)
     keep = ~excluded
-    strict = e32 <= REL_TOL
-    fallback = ~strict & (e64 <= np.maximum(REL_TOL, 2 * yard))
-    neither = ~strict & ~fallback
     q = lambda x: {k: float(np.quantile(x, v)) for k, v in (("q50", .5), ("q90", .9), ("q99", .99), ("q999", .999), ("max", 1.))}
-    return {"envs": int(len(e32)), "excluded_near_cutoff": int(excluded.sum()), "kept": int(keep.sum()),
-            "pass_strict_1e-5_vs_f32": int((strict & keep).sum()),
-            "pass_only_not_worse_than_f32_oracle": int((fallback & keep).sum()),
-            "pass_neither": int((neither & keep).sum()),
-            "frac_strict": float(strict[keep].mean()), "median_kappa": float(np.median(kappa[keep])),
-            "e32": q(e32[keep]), "e64": q(e64[keep]), "yard": q(yard[keep]),
-            "kernel_e64_over_kappa_eps32": q(e64[keep] / (kappa[keep] * eps32)),
-            "oracle_f32_yard_over_kappa_eps32": q(yard[keep] / (kappa[keep] * eps32)),
-            "neither_detail": [dict(e32=float(a), e64=float(b), yard=float(c), kappa=float(k))
-                               for a, b, c, k in zip(e32[neither & keep][:12], e64[neither & keep][:12],
-                                                     yard[neither & keep][:12], kappa[neither & keep][:12])]}
+    strict = e32 <= REL_TOL
+    out = {"envs": int(len(e32)), "excluded_near_cutoff": int(excluded.sum()), "kept": int(keep.sum()),
+           "pass_a_strict_1e-5_vs_f32": int((strict & keep).sum()), "frac_strict": float(strict[keep].mean()),
+           "median_kappa": float(np.median(kappa[keep])), "e32": q(e32[keep]), "e64": q(e64[keep]), "yard": q(yard[keep]),
+           "kernel_e64_over_kappa_eps32": q(e64[keep] / (kappa[keep] * eps32)),
+           "oracle_f32_yard_over_kappa_eps32": q(yard[keep] / (kappa[keep] * eps32))}
+    if sens is not None:
+        S_ = np.maximum(np.asarray(sens, dtype=np.float64), 1e-30)
+        in_b = ~strict & (e64 <= np.maximum(REL_TOL, SENS_FACTOR * S_))
+        out.update({"pass_b_only_within_sensitivity": int((in_b & keep).sum()),
+                    "failed": int((~strict & ~in_b & keep).sum()), "sens_factor": SENS_FACTOR,
+                    "sensitivity": q(S_[keep]),
+                    # over the environments where the 1e-5 floor does not decide by itself
+                    "kernel_e64_over_S": q((e64 / S_)[keep & (e64 > REL_TOL)]) if (keep & (e64 > REL_TOL)).any() else None,
+                    "oracle_f32_yard_over_S": q((yard / S_)[keep & (yard > REL_TOL)]) if (keep & (yard > REL_TOL)).any() else None,
+                    "oracle_f32_would_fail": int((keep & (yard > np.maximum(REL_TOL, SENS_FACTOR * S_))).sum())})
+    return out
 
 
 def make_inputs(config, n, B, seed=None):

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from gpu_common import assert_parity
+from gpu_common import assert_parity, config_sens
 from oracle import harness as H
 from riemannian_motion_policies_b200 import scenarios as S
 
@@ -76,7 +76,8 @@ def test_full_size_subset_against_oracle(world):
     ref32 = H.evaluate_vmap(4, N, q, qd, goal, sph, dtype=torch.float32)
     ref64 = H.evaluate_vmap(4, N, q, qd, goal, sph, dtype=torch.float64)
     _, M64 = H.combined_vmap(4, N, q, qd, goal, sph, dtype=torch.float64)
-    stats = assert_parity(w["qdd"][idx].cpu().numpy(), ref32, ref64, M64, N, label="1M-env subset", max_excluded=0.10)
+    stats = assert_parity(w["qdd"][idx].cpu().numpy(), ref32, ref64, M64, N, label="1M-env subset", max_excluded=0.10,
+                          sens=config_sens(4, N, q, qd, goal, sph))
     print(stats)
 
 

@@ -6,7 +6,8 @@ import pytest
 import torch
 
 from conftest import GOLDEN
-from gpu_common import REL_TOL, assert_parity, make_inputs, product_core, product_evaluate, product_fkine, rel_err
+from gpu_common import (REL_TOL, assert_parity, config_sens, make_inputs, product_core, product_evaluate, product_fkine,
+                        rel_err)
 from oracle import harness as H
 from riemannian_motion_policies_b200 import scenarios as S
 
@@ -25,7 +26,7 @@ def test_golden_fixtures(ns, config, n):
     sph = g["spheres"] if "spheres" in g else None
     got = product_evaluate(ns, config, n, g["q"], g["qd"], g["goal"], sph)
     stats = assert_parity(got, g["qdd32"], g["qdd64"], g["M64"], n, label=f"golden config{config} n{n}",
-                          max_excluded=0.10 if config == 4 else 0.05)
+                          max_excluded=0.10 if config == 4 else 0.05, sens=config_sens(config, n, g["q"], g["qd"], g["goal"], sph))
     print(f"config{config} n{n}: {stats}")
 
 
@@ -38,7 +39,8 @@ def test_reference_source_vectors(ns, config, n):
     got = product_evaluate(ns, config, n, g["q"], g["qd"], g["goal"], sph)
     ref64 = H.evaluate_vmap(config, n, g["q"], g["qd"], g["goal"], sph, dtype=torch.float64)
     _, M64 = H.combined_vmap(config, n, g["q"], g["qd"], g["goal"], sph, dtype=torch.float64)
-    stats = assert_parity(got, g["qdd_ref"], ref64, M64, n, label=f"reference-source config{config} n{n}", max_excluded=0.3)
+    stats = assert_parity(got, g["qdd_ref"], ref64, M64, n, label=f"reference-source config{config} n{n}",
+                          max_excluded=0.10 if config == 4 else 0.05, sens=config_sens(config, n, g["q"], g["qd"], g["goal"], sph))
     print(f"reference-source config{config} n{n}: {stats}")
 
 
@@ -78,7 +80,7 @@ def test_seeded_batches_against_oracle(ns, config, n, B):
     _, M64 = H.combined_vmap(config, n, q, qd, goal, sph, dtype=torch.float64)
     got = product_evaluate(ns, config, n, q, qd, goal, sph)
     stats = assert_parity(got, ref32, ref64, M64, n, label=f"config{config} n{n} B{B}",
-                          max_excluded=0.10 if config == 4 else 0.05)
+                          max_excluded=0.10 if config == 4 else 0.05, sens=config_sens(config, n, q, qd, goal, sph))
     print(f"config{config} n{n} B{B}: {stats}")
     if config in (2, 3, 5):      # mostly well-conditioned trees: the strict 1e-5 bar holds almost everywhere
         assert stats["frac_strict"] > 0.95, stats
@@ -103,7 +105,7 @@ def test_large_seeded_batches_against_committed_oracle_outputs(ns, config):
     assert h.hexdigest() == str(g["digest"]), "seeded inputs differ from the ones the fixture was computed for"
     got = product_evaluate(ns, config, 7, q, qd, goal, sph)
     stats = assert_parity(got, g["ref32"], g["ref64"], n=7, s64=g["s64"], label=f"config{config} B{B} (fixture)",
-                          max_excluded=0.10 if config == 4 else 0.05)
+                          max_excluded=0.10 if config == 4 else 0.05, sens=g["sens"])
     if config == 5:
         assert stats["frac_strict"] >= 0.97, stats
 
@@ -122,7 +124,8 @@ def test_reference_style_single_env_call(ns):
     ref32 = H.evaluate_loop(1, 2, q, qd, goal)
     ref64 = H.evaluate_loop(1, 2, q, qd, goal, dtype=torch.float64)
     _, M64 = H.combined_vmap(1, 2, q, qd, goal, dtype=torch.float64)
-    assert_parity(np.stack(outs), ref32, ref64, M64, 2, label="single-env calls", max_excluded=0.2)
+    assert_parity(np.stack(outs), ref32, ref64, M64, 2, label="single-env calls", max_excluded=0.2,
+                  sens=config_sens(1, 2, q, qd, goal, None))
     # reassigning the goal attribute is picked up at the next step (06_cluttered_environment.py:142)
     core = S.build_config1(ns, fk, goal[0])
     a = core.evaluate(q[0], qd[0]).numpy()
@@ -253,7 +256,7 @@ def test_edge_cases(ns):
             sph_o = sph
         ref32 = H.evaluate_vmap(3, n, q, qd, goal, sph_o, dtype=torch.float32)
         ref64 = H.evaluate_vmap(3, n, q, qd, goal, sph_o, dtype=torch.float64)
-        assert_parity(got, ref32, ref64, label=f"edge B{B} O{O_}")
+        assert_parity(got, ref32, ref64, label=f"edge B{B} O{O_}", sens=config_sens(3, n, q, qd, goal, sph_o))
 
 
 def test_tma_and_direct_paths_agree(ns):
@@ -365,9 +368,10 @@ def test_obstacle_leaf_parameter_variants(ns, gains):
     got = core.evaluate(torch.as_tensor(q, device=dev), torch.as_tensor(qd, device=dev),
                         goals=torch.as_tensor(goal, device=dev), spheres=torch.as_tensor(sph, device=dev)).cpu().numpy()
 
-    def oracle(dtype, combine=False):
+    def oracle(dtype, combine=False, inputs=None):
         ons = H.namespace(dtype)
         fko = H.make_fkine(n, dtype)
+        q_, qd_, goal_, sph_ = inputs if inputs is not None else (q, qd, goal, sph)
 
         def one(q1, qd1, goal1, s):
             q1, qd1, goal1, s = q1.to(dtype), qd1.to(dtype), goal1.to(dtype), s.to(dtype)
@@ -379,13 +383,16 @@ def test_obstacle_leaf_parameter_variants(ns, gains):
             oc = _tree_with_obstacle_gains(ons, fko, goal1, n,
                                            lambda fr: ons.TaskmapJointFrame4x4ToDistance(on_link[idx[fr]], on_obst[idx[fr]]),
                                            **gains)
-            return oc.combine(q1, qd1)[1] if combine else oc.evaluate(q1, qd1)
+            return oc.combine(q1, qd1) if combine else oc.evaluate(q1, qd1)
 
-        return torch.func.vmap(one)(torch.as_tensor(q), torch.as_tensor(qd), torch.as_tensor(goal),
-                                    torch.as_tensor(sph)).numpy()
+        res = torch.func.vmap(one)(torch.as_tensor(q_), torch.as_tensor(qd_), torch.as_tensor(goal_), torch.as_tensor(sph_))
+        return tuple(r.numpy() for r in res) if combine else res.numpy()
 
-    stats = assert_parity(got, oracle(torch.float32), oracle(torch.float64), oracle(torch.float64, combine=True), n,
-                          label=f"obstacle gains {gains}")
+    f64, M64 = oracle(torch.float64, combine=True)
+    sens = lambda idx: np.maximum(
+        H.sensitivity(lambda *arrs: oracle(torch.float64, inputs=arrs), [q[idx], qd[idx], goal[idx], sph[idx]]),
+        H.metric_sensitivity(M64[idx], f64[idx]))
+    stats = assert_parity(got, oracle(torch.float32), oracle(torch.float64), M64, n, label=f"obstacle gains {gains}", sens=sens)
     print(gains, stats)
 
 
@@ -442,22 +449,26 @@ def test_direct_solve_and_jacobi_lanes_mix(ns):
     tq, tqd, tg = (torch.as_tensor(a, device=dev) for a in (q, qd, goal))
     got = core.evaluate(tq, tqd, goals=tg).cpu().numpy()
 
-    def oracle(dtype, combine=False):
+    def oracle(dtype, combine=False, inputs=None):
         ons = H.namespace(dtype)
         fko = H.make_fkine(n, dtype)
+        q_, qd_, goal_ = inputs if inputs is not None else (q, qd, goal)
 
         def one(q1, qd1, g1):
             oc = build(ons, fko, g1.to(dtype))
-            return oc.combine(q1.to(dtype), qd1.to(dtype))[1] if combine else oc.evaluate(q1.to(dtype), qd1.to(dtype))
+            return oc.combine(q1.to(dtype), qd1.to(dtype)) if combine else oc.evaluate(q1.to(dtype), qd1.to(dtype))
 
-        return torch.func.vmap(one)(torch.as_tensor(q), torch.as_tensor(qd), torch.as_tensor(goal)).numpy()
+        res = torch.func.vmap(one)(torch.as_tensor(q_), torch.as_tensor(qd_), torch.as_tensor(goal_))
+        return tuple(r.numpy() for r in res) if combine else res.numpy()
 
-    M64 = oracle(torch.float64, combine=True)
+    f64, M64 = oracle(torch.float64, combine=True)
+    sens = lambda idx: np.maximum(H.sensitivity(lambda *arrs: oracle(torch.float64, inputs=arrs), [q[idx], qd[idx], goal[idx]]),
+                                  H.metric_sensitivity(M64[idx], f64[idx]))
     s = np.linalg.svd(M64, compute_uv=False)
     ratio = s[:, -1] / s[:, 0]
     assert (ratio > 4 * 10 * n * np.finfo(np.float32).eps).all()          # nothing is truncated in this batch
     assert (ratio < 2.4e-4).any() and (ratio > 2.4e-4).any()              # ... but it straddles the direct-solve test
-    stats = assert_parity(got, oracle(torch.float32), oracle(torch.float64), M64, n, label="direct/jacobi mix")
+    stats = assert_parity(got, oracle(torch.float32), oracle(torch.float64), M64, n, label="direct/jacobi mix", sens=sens)
     print(stats, "sigma ratio range", ratio.min(), ratio.max())
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(dev)
     again = core.evaluate(tq[perm], tqd[perm], goals=tg[perm]).cpu().numpy()
@@ -493,7 +504,7 @@ def test_specialized_kernels_match(ns, config, n):
     ref64 = H.evaluate_vmap(config, n, q, qd, goal, sph, dtype=torch.float64)
     _, M64 = H.combined_vmap(config, n, q, qd, goal, sph, dtype=torch.float64)
     assert_parity(special.cpu().numpy(), ref32, ref64, M64, n, label=f"specialized config{config} n{n}",
-                  max_excluded=0.10 if config == 4 else 0.05)
+                  max_excluded=0.10 if config == 4 else 0.05, sens=config_sens(config, n, q, qd, goal, sph))
     # the fused-resolve kernel (small batches) is specialised too
     small = torch.empty(64, n, device=dev)
     tree.step(tq[:64].contiguous(), tqd[:64].contiguous(), small, goals=goals[:64].contiguous(),
