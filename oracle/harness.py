@@ -156,34 +156,26 @@ def sensitivity(fn, arrays, K=4):
     return S
 
 
-def metric_sensitivity(M, f, K=4):
-    """The same for the resolve alone: largest relative change of pinv(M) f (float64, TensorFlow's float32 cutoff)
-    when every entry of the combined M / f moves by eps32 * max|M| (max|f|) * U(-1, 1).  Float32 accumulation of the
-    combined metric leaves exactly this kind of unstructured noise on it; perturbing the INPUTS instead keeps the
-    structure of J^T A J (an exactly rank-deficient sum stays rank deficient) and so cannot see the conditioning of a
-    metric whose small kept singular values sit just above the cutoff (config 4)."""
-    M, f = torch.as_tensor(np.asarray(M, dtype=np.float64)), torch.as_tensor(np.asarray(f, dtype=np.float64))
-    solve = lambda M_, f_: (O.tf_pinv(M_) @ f_[..., None])[..., 0].numpy()
-    base = solve(M, f)
-    den = np.maximum(np.linalg.norm(base, axis=-1), 1e-30)
-    mM, mf = M.abs().amax(dim=(1, 2))[:, None, None], f.abs().amax(dim=1)[:, None]
-    S = np.zeros(base.shape[0])
-    for k in range(K):
-        rng = np.random.RandomState(4321 + k)
-        dM = torch.as_tensor(rng.uniform(-1, 1, size=tuple(M.shape[1:])))        # one draw, shared by the batch
-        df = torch.as_tensor(rng.uniform(-1, 1, size=tuple(f.shape[1:])))
-        out = solve(M + EPS32 * mM * dM, f + EPS32 * mf * df)
-        S = np.maximum(S, np.linalg.norm(out - base, axis=-1) / den)
-    return S
+def metric_conditioning(M):
+    """kappa * eps32 per environment, kappa = sigma_max / smallest singular value tf.linalg.pinv keeps (float32
+    cutoff): how far pinv(M) f moves, relatively, when float32 accumulation leaves its unstructured eps32 * |M| noise
+    on the combined metric.  Perturbing the INPUTS instead (`sensitivity`) keeps the structure of J^T A J -- an exactly
+    rank-deficient sum stays rank deficient -- and so cannot see the conditioning of a metric whose small kept singular
+    values sit just above the cutoff (config 4)."""
+    s = np.linalg.svd(np.asarray(M, dtype=np.float64), compute_uv=False)
+    n = s.shape[-1]
+    cut = 10 * n * EPS32 * s[:, :1]
+    kappa = s[:, 0] / np.where(s > cut, s, np.inf).min(-1)
+    return kappa * EPS32
 
 
 def config_sensitivity(config, n, q, qd, goal, spheres=None, K=4, fkine=None):
     """Float32 conditioning of the scenario trees per environment: the larger of `sensitivity` (inputs rounded
-    differently) and `metric_sensitivity` (float32 noise on the combined metric), float64 oracle under vmap."""
+    differently) and `metric_conditioning` (float32 noise on the combined metric), float64 oracle under vmap."""
     fk = fkine or make_fkine(n, torch.float64, robot="gantry" if config == 6 else None)
     fn = lambda q_, qd_, goal_, sph_: evaluate_vmap(config, n, q_, qd_, goal_, sph_, dtype=torch.float64, fkine=fk)
     S_in = sensitivity(fn, [q, qd, goal, spheres], K=K)
     f64, M64 = combined_vmap(config, n, np.asarray(q, dtype=np.float64), np.asarray(qd, dtype=np.float64),
                              np.asarray(goal, dtype=np.float64),
                              None if spheres is None else np.asarray(spheres, dtype=np.float64), dtype=torch.float64, fkine=fk)
-    return np.maximum(S_in, metric_sensitivity(M64, f64, K=K))
+    return np.maximum(S_in, metric_conditioning(M64))

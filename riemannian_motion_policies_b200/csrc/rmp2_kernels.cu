@@ -99,6 +99,12 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 // environments beyond the 1e-5 bar, all of them explained by the float32 conditioning of the step itself -- so off.
 #define RMP2_SQRT_NEWTON 0
 #endif
+#ifndef RMP2_SKIP_UNROLL
+#define RMP2_SKIP_UNROLL 1            // packed steps per trip of the early-out pair loop (2: measured slower, 1.236 vs 1.170 ms/step)
+#endif
+#ifndef RMP2_SKIP_SORT
+#define RMP2_SKIP_SORT 1              // re-deal the owners of a block by work before the early-out pair loop
+#endif
 #ifndef RMP2_SPHERES_STEPS_PER_TRIP
 #define RMP2_SPHERES_STEPS_PER_TRIP 4 // packed (two-sphere) steps per loop trip
 #endif
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
   long long env = env0 + e_local;
   const int O = A.n_spheres;
   bool active = (slot < L) && (env < A.B);
-  const bool sorted = kSkip && O <= 64;             // one mask word per parity: owners can be re-dealt
+  const bool sorted = kSkip && RMP2_SKIP_SORT && O <= 64;   // one mask word per parity: owners can be re-dealt
 
   uint32_t row = 0;                                 // shared-memory address of this thread's sphere row
   uint32_t tile = 0;                                // ... of the tile's first row
@@ -261,9 +267,13 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
       };
       while (mask_even | mask_odd) {
         const float4 a0 = next(mask_even, 0), a1 = next(mask_odd, 1);
+#if RMP2_SKIP_UNROLL >= 2
         const float4 b0 = next(mask_even, 0), b1 = next(mask_odd, 1);
         two_spheres(a0, a1);
         two_spheres(b0, b1);
+#else
+        two_spheres(a0, a1);
+#endif
       }
     };
     if (!sorted) {

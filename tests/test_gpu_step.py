@@ -391,7 +391,7 @@ def test_obstacle_leaf_parameter_variants(ns, gains):
     f64, M64 = oracle(torch.float64, combine=True)
     sens = lambda idx: np.maximum(
         H.sensitivity(lambda *arrs: oracle(torch.float64, inputs=arrs), [q[idx], qd[idx], goal[idx], sph[idx]]),
-        H.metric_sensitivity(M64[idx], f64[idx]))
+        H.metric_conditioning(M64[idx]))
     stats = assert_parity(got, oracle(torch.float32), oracle(torch.float64), M64, n, label=f"obstacle gains {gains}", sens=sens)
     print(gains, stats)
 
@@ -463,7 +463,7 @@ def test_direct_solve_and_jacobi_lanes_mix(ns):
 
     f64, M64 = oracle(torch.float64, combine=True)
     sens = lambda idx: np.maximum(H.sensitivity(lambda *arrs: oracle(torch.float64, inputs=arrs), [q[idx], qd[idx], goal[idx]]),
-                                  H.metric_sensitivity(M64[idx], f64[idx]))
+                                  H.metric_conditioning(M64[idx]))
     s = np.linalg.svd(M64, compute_uv=False)
     ratio = s[:, -1] / s[:, 0]
     assert (ratio > 4 * 10 * n * np.finfo(np.float32).eps).all()          # nothing is truncated in this batch
