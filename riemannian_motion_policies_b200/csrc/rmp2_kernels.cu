@@ -99,6 +99,13 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 // environments beyond the 1e-5 bar, all of them explained by the float32 conditioning of the step itself -- so off.
 #define RMP2_SQRT_NEWTON 0
 #endif
+#ifndef RMP2_SPHERES_SKIP_MIN_BLOCKS
+#define RMP2_SPHERES_SKIP_MIN_BLOCKS 7  // the early-out variant is latency bound (shared-memory scoreboard): more warps help it
+                                        // (measured 5 / 6 / 7 / 8 blocks: 1.070 / 1.068 / 1.028 / 1.065 ms per step)
+#endif
+#ifndef RMP2_SKIP_MIN_SPHERES
+#define RMP2_SKIP_MIN_SPHERES 32      // rows shorter than this run every pair even with RMP2_OPT_EARLY_OUT set
+#endif
 #ifndef RMP2_SKIP_UNROLL
 #define RMP2_SKIP_UNROLL 1            // packed steps per trip of the early-out pair loop (2: measured slower, 1.236 vs 1.170 ms/step)
 #endif
@@ -135,7 +142,7 @@ struct SkipOwner {                  // what travels with an owner when it is re-
 };
 
 template <bool kTma, bool kSkip>
-__global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 128 / RMP2_SPHERES_BLOCK)
+__global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP_MIN_BLOCKS : RMP2_SPHERES_MIN_BLOCKS) * 128 / RMP2_SPHERES_BLOCK)
     rmp2_spheres_kernel(const __grid_constant__ SphereTables ST, const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int L = ST.n_slots, E = ST.envs_per_block;
@@ -166,6 +173,10 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
                    reinterpret_cast<const unsigned char*>(A.spheres) + (size_t)(env0 + e) * row_bytes, row_bytes, bar);
     tile = smem_u32(base);
     row = tile + (uint32_t)e_local * pitch;
+    // the 16 pad bytes behind every row hold a sphere that contributes exactly zero (beyond every metric radius;
+    // 1e15 m away keeps all terms finite): index O of a row, what an exhausted list of the early-out loop yields
+    if (kSkip && slot == 0 && e_local < E)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %2, %2};" ::"r"(row + (uint32_t)O * 16u), "f"(1e15f), "f"(0.f) : "memory");
   }
   if (!sorted && !active) return;                   // (the sorted variant keeps every thread for its barriers)
 
@@ -253,16 +264,53 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
         mask_odd |= (uint32_t)(dc2.y <= lim2.y) << (o >> 1);
       }
     };
-    // phase 3: the pairs of the set bits, an even with an odd sphere per packed step, two packed steps per trip
-    // (independent until their last FMAs, so the MUFU latencies of one overlap the arithmetic of the other; the
-    // trip is branch-free: an exhausted list keeps yielding the far-away sphere)
+    // phase 1 for O <= 64, fully unrolled: per sphere one LDS.128, two FFMA2 on the register pairs the load delivers
+    // -- (x, y) -> (px - x, py - y) and (z, r) -> (pz - z, reach + r) --, two FMUL2 for the four squares, three FADD for
+    // w = |r|^2 - (reach + radius)^2, and one funnel shift that pushes the SIGN of w into the mask: 9 instructions
+    // where the generic loop needs 15.  (w = +0 exactly on the boundary counts as outside: the reach carries a
+    // 1e-5 relative margin, and a pair wrongly kept would contribute exactly zero anyway.)
+    auto reach_masks_64 = [&](uint32_t& mask_even, uint32_t& mask_odd) {
+      const float2 pxy = make_float2(px, py), pzr = make_float2(pz, p[SP_REACH]);
+      const float2 mm = make_float2(-1.f, -1.f), mp = make_float2(-1.f, 1.f);
+      uint32_t acc_even = 0u, acc_odd = 0u;                          // bit 31 - k <-> sphere pair k, reversed at the end
+      auto margin = [&](const float4 s) -> uint32_t {
+        const float2 a = __ffma2_rn(make_float2(s.x, s.y), mm, pxy);
+        const float2 b = __ffma2_rn(make_float2(s.z, s.w), mp, pzr);
+        const float2 a2 = __fmul2_rn(a, a), b2 = __fmul2_rn(b, b);
+        return __float_as_uint((a2.x + a2.y) + (b2.x - b2.y));       // < 0 inside the reach
+      };
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {                                  // 8 spheres per chunk, one bounds check per chunk
+        if (8 * c + 8 <= O) {
+#pragma unroll
+          for (int k = 4 * c; k < 4 * c + 4; ++k) {
+            acc_even = __funnelshift_l(margin(load_sphere(2 * k)), acc_even, 1);
+            acc_odd = __funnelshift_l(margin(load_sphere(2 * k + 1)), acc_odd, 1);
+          }
+        } else if (8 * c < O) {
+#pragma unroll
+          for (int k = 4 * c; k < 4 * c + 4; ++k) {
+            acc_even = __funnelshift_l((2 * k < O) ? margin(load_sphere(2 * k)) : 0u, acc_even, 1);
+            acc_odd = __funnelshift_l((2 * k + 1 < O) ? margin(load_sphere(2 * k + 1)) : 0u, acc_odd, 1);
+          }
+        } else {
+          acc_even <<= 4;
+          acc_odd <<= 4;
+        }
+      }
+      mask_even = __brev(acc_even);
+      mask_odd = __brev(acc_odd);
+    };
+    // phase 3: the pairs of the set bits, an even with an odd sphere per packed step; an exhausted list yields the
+    // far-away sphere (staged rows: the pad slot, index O -- one select on the index instead of four on the data)
     auto masked_pairs = [&](int o0, uint32_t mask_even, uint32_t mask_odd) {
       const float4 far_away = make_float4(px + 1e15f, py, pz, 0.f);
       auto next = [&](uint32_t& mask, int parity) -> float4 {
         const bool have = mask != 0u;
-        const int k = have ? __ffs((int)mask) - 1 : 0;
+        const int k = __ffs((int)mask) - 1;
         mask &= mask - 1u;                                        // 0 stays 0
-        const float4 s = load_sphere(o0 + 2 * k + parity);        // a valid row entry either way
+        if (kTma && o0 == 0) return load_sphere(have ? 2 * k + parity : O);
+        const float4 s = load_sphere(o0 + (have ? 2 * k + parity : 0));
         return have ? s : far_away;
       };
       while (mask_even | mask_odd) {
@@ -286,7 +334,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, RMP2_SPHERES_MIN_BLOCKS * 
       __shared__ SkipOwner owners[RMP2_SPHERES_BLOCK];
       __shared__ int hist[36], first[36];
       uint32_t me = 0u, mo = 0u;
-      if (active) reach_masks(0, me, mo);
+      if (active) reach_masks_64(me, mo);
       const int steps = max(__popc(me), __popc(mo));            // 0 .. 32
       if (t < 36) hist[t] = 0;
       __syncthreads();
@@ -807,14 +855,18 @@ cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, bool 
   const int threads = ((ST.envs_per_block * ST.n_slots + 31) / 32) * 32;
   const size_t smem = rmp2_spheres_smem(ST, A.n_spheres, use_tma);
   const unsigned nb = (unsigned)blocks;
+  // the early-out variant pays a reach test per pair and a re-deal of the block's work: below ~32 spheres per
+  // environment that costs more than the skipped pairs save (measured, config 3 with 16 spheres: 0.8x), so short
+  // rows run every pair -- the results are identical either way
+  const bool skip = A.early_out && A.n_spheres >= RMP2_SKIP_MIN_SPHERES;
   if (use_tma) {
-    const void* fn = A.early_out ? (const void*)rmp2_spheres_kernel<true, true> : (const void*)rmp2_spheres_kernel<true, false>;
+    const void* fn = skip ? (const void*)rmp2_spheres_kernel<true, true> : (const void*)rmp2_spheres_kernel<true, false>;
     cudaError_t e = allow_dynamic_smem(fn, smem);
     if (e != cudaSuccess) return e;
-    if (A.early_out) rmp2_spheres_kernel<true, true><<<nb, threads, smem, stream>>>(ST, A);
+    if (skip) rmp2_spheres_kernel<true, true><<<nb, threads, smem, stream>>>(ST, A);
     else rmp2_spheres_kernel<true, false><<<nb, threads, smem, stream>>>(ST, A);
   } else {
-    if (A.early_out) rmp2_spheres_kernel<false, true><<<nb, threads, 0, stream>>>(ST, A);
+    if (skip) rmp2_spheres_kernel<false, true><<<nb, threads, 0, stream>>>(ST, A);
     else rmp2_spheres_kernel<false, false><<<nb, threads, 0, stream>>>(ST, A);
   }
   return cudaGetLastError();
