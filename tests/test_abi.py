@@ -127,3 +127,70 @@ def test_specialization_compiles_without_a_gpu():
         core = build(ns, fk, [0.5, 0.0, 0.5], n, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance())
         tree = core.compile(n, goal_leaves=["attractor"])
         assert tree.specialize(compile_only=True) is None        # compiled, nothing loaded
+
+
+def test_gantry_tree_with_orientation_leaf_compiles_and_specializes(native_lib):
+    """The synthetic gantry arm (general axes, three branchings, nine scrambled joints) with an orientation leaf on
+    the Euler task map (RMP2_SPACE_FRAME_EULER): host-side compilation and the NVRTC build need no GPU."""
+    ns = S.product_namespace()
+    fk = ns.UrdfForwardKinematic(S.GANTRY_URDF, S.GANTRY_ORDER)
+    core = S.build_config6(ns, fk, [0.2, 0.1, 0.5], 9, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance())
+    tree = core.compile(9, goal_leaves=["target"])
+    spaces = [d.space for d in tree.descs]
+    assert _native.SPACE_FRAME_EULER in spaces and _native.SPACE_FRAME_POSITION in spaces
+    assert tree.specialize(compile_only=True) is None
+    # an orientation leaf accepts only the two target policies
+    bad = ns.RmpCore()
+    bad.add_rmp(ns.JointDamping(accel_d_gain=1, metric_scalar=0.005, inertia=0.3))
+    bad.rmps["joint_damping"].taskmap = S.euler_taskmap(ns, fk, "tool")
+    with pytest.raises(NotImplementedError):
+        bad.compile(9)
+
+
+def test_step_argument_checks_need_no_gpu(native_lib):
+    """Everything rmp2_step refuses is refused before any CUDA call: misaligned sphere rows, missing goals, pair-set
+    mismatches; likewise the options, rmp2_tree_reserve and rmp2_pinv_solve argument checks."""
+    ns = S.product_namespace()
+    fk = ns.UrdfForwardKinematic(S.PANDA_WO_TOOL_URDF, S.PANDA_ORDER_7)
+    core = S.build_config4(ns, fk, [0.5, 0.0, 0.5], 7, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance())
+    tree = core.compile(7, goal_leaves=["attractor"])
+    io = _native.StepIO()
+    io.B, io.q, io.qd, io.qdd = 4, 0x1000, 0x2000, 0x3000          # never dereferenced: the call fails first
+    io.goals, io.n_goal_slots = 0x4000, 1
+    io.spheres, io.n_spheres = 0x5004, 8                           # 4-byte aligned only
+    assert native_lib.rmp2_step(tree.handle, ctypes.byref(io), None) == 1
+    assert b"16-byte aligned" in native_lib.rmp2_last_error()
+    io.spheres, io.goals = 0x5000, None
+    assert native_lib.rmp2_step(tree.handle, ctypes.byref(io), None) == 1
+    assert b"per-environment goals" in native_lib.rmp2_last_error()
+    io.goals, io.n_pair_sets = 0x4000, 2
+    assert native_lib.rmp2_step(tree.handle, ctypes.byref(io), None) == 1
+    assert b"n_pair_sets" in native_lib.rmp2_last_error()
+    assert native_lib.rmp2_rollout(tree.handle, None, 0x1000, 0x2000, 0.01, 10, 10, None) == 1   # NULL io: no crash
+    for option, value in ((_native.OPT_SPLIT_RESOLVE, 2), (_native.OPT_BLOCK_THREADS, 48), (_native.OPT_CHUNK_ENVS, -1), (99, 0)):
+        assert native_lib.rmp2_tree_set_option(tree.handle, option, value) == 1
+    for option, value in ((_native.OPT_SPLIT_RESOLVE, 0), (_native.OPT_BLOCK_THREADS, 64), (_native.OPT_TMA, 0),
+                          (_native.OPT_EARLY_OUT, 0), (_native.OPT_CHUNK_ENVS, 1 << 16)):
+        assert native_lib.rmp2_tree_set_option(tree.handle, option, value) == 0
+    assert native_lib.rmp2_tree_reserve(None, 16, 0, None) == 1
+    assert native_lib.rmp2_tree_reserve(tree.handle, -1, 0, None) == 1
+    assert native_lib.rmp2_pinv_solve(7, 4, None, 0x1000, 0x2000, 1, 0, None) == 1
+    assert native_lib.rmp2_pinv_solve(13, 4, 0x1000, 0x2000, 0x3000, 1, 0, None) == 1
+    assert native_lib.rmp2_pinv_solve(7, 4, 0x1000, 0x2000, 0x3000, 1, 2, None) == 1
+    assert native_lib.rmp2_obstacle_feed(fk._handle, np.zeros(1, np.int32).ctypes.data, None, 1, 4, 0x1000, 0x5004, 2, None, 0,
+                                         0x6000, None, None) == 1
+    assert b"16-byte aligned" in native_lib.rmp2_last_error()
+
+
+def test_oracle_sensitivity_yardstick():
+    """oracle/harness.config_sensitivity: deterministic per environment (independent of the batch around it), at the
+    eps32 scale for a well-conditioned tree, and kappa * eps32 for a nearly singular metric."""
+    import torch
+    from oracle import harness as H
+    q, qd, goal = S.sample_panda_state(6, 7, seed=3)
+    full = H.config_sensitivity(2, 7, q, qd, goal)
+    part = H.config_sensitivity(2, 7, q[2:4], qd[2:4], goal[2:4])
+    np.testing.assert_array_equal(full[2:4], part)
+    assert (full > 1e-8).all() and (full < 1e-4).all()
+    M = np.diag([1.0, 1e-3, 1e-9, 0, 0, 0, 0])[None]
+    np.testing.assert_allclose(H.metric_conditioning(M), [1e3 * H.EPS32])       # 1e-9 is below the pinv cutoff
