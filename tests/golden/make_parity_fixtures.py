@@ -46,11 +46,9 @@ def main():
         np.savez_compressed(out, B=B, ref32=ref32.astype(np.float32), ref64=ref64, s64=s64, sens=sens,
                             digest=np.array(input_digest(q, qd, goal, sph)))
         print("wrote", out)
-        if os.environ.get("RMP2_STUDY_DIR"):       # (M, f) in float32 for the solver study (tools/parity_study.py)
+        if config == 4:       # the float32 combined (M, f) of the same batch: input of the solver study (tools/parity_study.py)
             f32, M32 = H.combined_vmap(config, N, q, qd, goal, sph, dtype=torch.float32)
-            f64, _ = H.combined_vmap(config, N, q, qd, goal, sph, dtype=torch.float64)
-            np.savez_compressed(os.path.join(os.environ["RMP2_STUDY_DIR"], f"mf_config{config}.npz"),
-                                M32=M32, f32=f32, M64=M64, f64=f64)
+            np.savez_compressed(os.path.join(HERE, "mf_config4_f32.npz"), M32=M32.astype(np.float32), f32=f32.astype(np.float32))
 
 
 if __name__ == "__main__":

@@ -100,7 +100,7 @@ def pipeline(config, B=4096):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "parity_study.json"))
-    ap.add_argument("--mf", default=os.path.join(ROOT, "gpurun_in", "mf_config4.npz"))
+    ap.add_argument("--mf", default=os.path.join(ROOT, "tests", "golden", "mf_config4_f32.npz"))
     args = ap.parse_args()
     res = {"lib": os.environ.get("RMP2_B200_LIB", "default build")}
     if os.path.exists(args.mf):
