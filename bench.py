@@ -362,8 +362,15 @@ def other_config_lines(ns, S, fk, n, device, steps, torch):
         line["value"] = B / (ms * 1e-3)
         line["unit"] = UNIT
         tree.set_early_out(True)
-        if O_:
-            line["value_early_out"] = B / (time_steps(step, steps, torch) * 1e-3)
+        if O_:                                  # library default, same launch mode
+            if graphed:
+                step(0)
+                torch.cuda.synchronize()
+                graph_eo = graph_of(lambda: step(0), torch)
+                ms_eo = time_steps(lambda i: graph_eo.replay(), steps, torch)
+            else:
+                ms_eo = time_steps(step, steps, torch)
+            line["value_early_out"] = B / (ms_eo * 1e-3)
         line["parity"] = fixture_parity(ns, config, n)
         out[f"config{config}"] = line
         del tree, core, q, qd, goal, spheres, qdd
