@@ -157,7 +157,8 @@ int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* 
 
 /* qdd = pinv(sum_l J_l^T M_l J_l) * sum_l J_l^T M_l (xdd_l - Jdot_l qd) for B environments.
  * Stands in for RmpCore.evaluate (rmp.py:133-155).  All io pointers are device memory.
- * Launches up to five kernels on `stream` (frames -> spheres -> step [-> resolve] -> resolve fallback).  The
+ * Launches up to four kernels on `stream` (frames -> spheres -> step -> resolve fallback; five with
+ * RMP2_OPT_SPLIT_RESOLVE).  The
  * tree handle owns scratch buffers (per-(environment, obstacle leaf) records of 40 B, the combined metric, the
  * work list of the fallback resolve; at most 2^20 environments at a time).  They are sized by rmp2_tree_reserve,
  * or grown on demand with stream-ordered allocation on `stream` (no device-wide stall; refused while `stream`
@@ -238,8 +239,8 @@ int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_sphere
  * pair through the full arithmetic (used for the roofline measurement). */
 #define RMP2_OPT_EARLY_OUT 0
 /* RMP2_OPT_TMA (default 1): stage sphere rows through shared memory with TMA bulk copies (0: LDG.128).
- * RMP2_OPT_SPLIT_RESOLVE (default -1 = by batch size; 0 / 1): run the direct resolve inside the step kernel
- * or as its own kernel.  RMP2_OPT_BLOCK_THREADS (default 0 = by batch size; 32 / 64 / 128).
+ * RMP2_OPT_SPLIT_RESOLVE (default -1 = 0; 0 / 1): run the direct resolve inside the step kernel (measured faster
+ * or equal on every configuration) or as its own kernel behind the (M, f) scratch.  RMP2_OPT_BLOCK_THREADS (default 0 = by batch size; 32 / 64 / 128).
  * RMP2_OPT_CHUNK_ENVS (default 0 = 2^20): environments per internal chunk of a step (bounds the scratch). */
 #define RMP2_OPT_TMA 1
 #define RMP2_OPT_SPLIT_RESOLVE 2

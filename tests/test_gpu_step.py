@@ -285,6 +285,29 @@ def test_tma_and_direct_paths_agree(ns):
         tree.step(args[0], args[1], torch.empty(B, n, device=dev), goals=goals, spheres=shifted)
 
 
+@pytest.mark.parametrize("config", [2, 4, 5])
+def test_split_and_fused_resolve_agree(ns, config):
+    """RMP2_OPT_SPLIT_RESOLVE: the direct resolve inside the step kernel (default) or as its own kernel behind the
+    (M, f) scratch -- same arithmetic, same fallback list, bit-identical results."""
+    from riemannian_motion_policies_b200 import _native
+    n, B = 7, 3000
+    q, qd, goal, sph = make_inputs(config, n, B)
+    fk = product_fkine(ns, n)
+    core = product_core(ns, config, n, fk)
+    dev = torch.device("cuda")
+    tree = core.compile(n, goal_leaves=["target" if config == 2 else "attractor"])
+    tq, tqd = torch.as_tensor(q, device=dev), torch.as_tensor(qd, device=dev)
+    goals = torch.as_tensor(goal, device=dev).reshape(B, 1, 3).contiguous()
+    spheres = None if sph is None else torch.as_tensor(sph, device=dev)
+    out = {}
+    for split in (0, 1):
+        tree.set_option(_native.OPT_SPLIT_RESOLVE, split)
+        qdd = torch.empty(B, n, device=dev)
+        tree.step(tq, tqd, qdd, goals=goals, spheres=spheres)
+        out[split] = qdd.cpu().numpy()
+    np.testing.assert_array_equal(out[0], out[1])
+
+
 def test_early_out_is_exact(ns):
     """Skipping pairs beyond the metric radius (library default) changes nothing: they contribute
     exactly zero in the reference (rmp2.py:194)."""

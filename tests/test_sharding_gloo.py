@@ -57,8 +57,9 @@ def _worker(rank, world, port, B, out_dir):
         dist.destroy_process_group()
 
 
-def test_two_ranks_gloo_match_single_process(tmp_path):
-    B, world = 11, 2                      # odd batch: ranks hold 6 and 5 environments
+@pytest.mark.parametrize("B", [11, 12])   # odd batch: ranks hold 6 and 5 environments (padded gather); even: one direct collective
+def test_two_ranks_gloo_match_single_process(tmp_path, B):
+    world = 2
     port = _free_port()
     mp.spawn(_worker, args=(world, port, B, str(tmp_path)), nprocs=world, join=True)
     from oracle import harness as H
