@@ -71,7 +71,8 @@ def test_reference_source_vectors_v1(ns):
     assert_parity(np.stack(got), g["qdd_ref"], ref64, label="reference-source v1 CollisionAvoidance")
 
 
-@pytest.mark.parametrize("config,n,B", [(1, 2, 1000), (2, 7, 4096), (3, 7, 2048), (4, 7, 1024), (5, 7, 1024), (5, 9, 256), (6, 9, 512)])
+@pytest.mark.parametrize("config,n,B", [(1, 2, 1000), (2, 7, 4096), (3, 7, 2048), (4, 7, 1024), (4, 9, 512), (5, 7, 1024), (5, 9, 256),
+                                        (6, 9, 512)])
 def test_seeded_batches_against_oracle(ns, config, n, B):
     """Same seeded inputs through the oracle (vmap, f32 and f64) and the kernel."""
     q, qd, goal, sph = make_inputs(config, n, B)
