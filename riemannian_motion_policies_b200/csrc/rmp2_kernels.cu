@@ -336,14 +336,14 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       uint32_t me = 0u, mo = 0u;
       if (active) reach_masks_64(me, mo);
       const int steps = max(__popc(me), __popc(mo));            // 0 .. 32
-      if (t < 36) hist[t] = 0;
+      for (int i = t; i < 36; i += blockDim.x) hist[i] = 0;        // (a block may have as few as 32 threads)
       __syncthreads();
       const int rank = atomicAdd(&hist[steps], 1);
       __syncthreads();
-      if (t < 33) {                                               // heaviest owners first
+      for (int i = t; i < 33; i += blockDim.x) {                  // heaviest owners first
         int before = 0;
-        for (int s = t + 1; s <= 32; ++s) before += hist[s];
-        first[t] = before;
+        for (int s = i + 1; s <= 32; ++s) before += hist[s];
+        first[i] = before;
       }
       __syncthreads();
       {

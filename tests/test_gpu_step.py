@@ -331,6 +331,58 @@ def test_early_out_is_exact(ns):
     np.testing.assert_array_equal(out[True], out[False])
 
 
+@pytest.mark.parametrize("n_leaves", [1, 3])
+def test_early_out_with_few_obstacle_leaves(ns, n_leaves):
+    """One or three obstacle leaves instead of eight: the pair kernel's blocks shrink to 32 / 96 threads (32 environments
+    per tile); the re-dealing early-out must still be bit-identical to the all-pairs variant and match the oracle."""
+    n, B, O_ = 7, 1500, 64
+    q, qd, goal = S.sample_panda_state(B, n, seed=61)
+    fk = product_fkine(ns, n)
+    ofk = H.make_fkine(n, torch.float64)
+    frames = S.collision_frames(ofk)[-n_leaves:]
+    origins = torch.func.vmap(lambda qq: H.frame_origins(ofk, qq, frames))(torch.as_tensor(q).double()).numpy()
+    sph = S.sample_spheres(B, O_, 62, origins)
+
+    def build(ns_, fk_, g, tm_for):
+        core = ns_.RmpCore()
+        core.add_rmp(S.target_attractor(ns_, fk_, g))
+        core.add_rmp(ns_.JointDamping(accel_d_gain=1, metric_scalar=0.005, inertia=0.3))
+        for fr in frames:
+            core.add_rmp(S.obstacle_leaf(ns_, ns_.chain_taskmaps([ns_.TaskmapByForwardKinematic(fk_, fr), tm_for(fr)]), fr))
+        return core
+
+    dev = torch.device("cuda")
+    tree = build(ns, fk, goal[0], lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance()).compile(n, goal_leaves=["attractor"])
+    tq, tqd = torch.as_tensor(q, device=dev), torch.as_tensor(qd, device=dev)
+    goals = torch.as_tensor(goal, device=dev).reshape(B, 1, 3).contiguous()
+    spheres = torch.as_tensor(sph, device=dev)
+    out = {}
+    for flag in (True, False):
+        tree.set_early_out(flag)
+        qdd = torch.empty(B, n, device=dev)
+        tree.step(tq, tqd, qdd, goals=goals, spheres=spheres)
+        out[flag] = qdd.cpu().numpy()
+    np.testing.assert_array_equal(out[True], out[False])
+
+    def oracle(dtype, inputs=None):
+        ons, fko = H.namespace(dtype), H.make_fkine(n, dtype)
+        q_, qd_, goal_, sph_ = inputs if inputs is not None else (q, qd, goal, sph)
+
+        def one(q1, qd1, g1, s):
+            q1, qd1, g1, s = q1.to(dtype), qd1.to(dtype), g1.to(dtype), s.to(dtype)
+            org = H.frame_origins(fko, q1, frames)
+            r = org[:, None, :] - s[None, :, :3]
+            on_obst = s[None, :, :3] + s[None, :, 3:4] * r / torch.linalg.norm(r, dim=-1, keepdim=True)
+            on_link = org[:, None, :].expand_as(on_obst)
+            idx = {fr: i for i, fr in enumerate(frames)}
+            return build(ons, fko, g1, lambda fr: ons.TaskmapJointFrame4x4ToDistance(on_link[idx[fr]], on_obst[idx[fr]])).evaluate(q1, qd1)
+
+        return torch.func.vmap(one)(torch.as_tensor(q_), torch.as_tensor(qd_), torch.as_tensor(goal_), torch.as_tensor(sph_)).numpy()
+
+    sens = lambda idx: H.sensitivity(lambda *arrs: oracle(torch.float64, inputs=arrs), [q[idx], qd[idx], goal[idx], sph[idx]])
+    assert_parity(out[True], oracle(torch.float32), oracle(torch.float64), label=f"{n_leaves} obstacle leaves", sens=sens)
+
+
 def test_joint_subset_pads_the_kernel_width(ns):
     """n = 5 controllable joints of the 7-joint arm (kernel instantiated for 7): joints outside `order`
     read q = 0 like the reference (kinematics.py:197,218-219); padded rows/cols stay zero."""
