@@ -99,15 +99,17 @@ static void fill_sphere_row(const rmp2_leaf_desc& d, float* row) {
   row[SP_GT_B] = live ? -1.f : 0.f;
   row[SP_D1A] = (float)(R / ((double)r[9] * fold));
   row[SP_D1B] = (float)((double)r[10] / fold);
-  // the damping gain D divides den2: q = 1/(den1' den2/D (1 + e_v)) then carries it (w2 = q den1' = D (1-sig)/den2,
-  // w1 = q den2/D unchanged).  D == 0: a constant den2' = 2^60 makes the damping term vanish below float32 resolution
-  const double D = r[1];
+  // the damping gain D and the velocity scale k divide den2: q = 1/(den1' den2/(D k) (1 + e_v)) then carries them
+  // (w2 = q den1' = D k (1-sig)/den2, w1 = q den2/(D k) unchanged).  D == 0: a constant den2' = 2^60 makes the
+  // damping term vanish below float32 resolution.  The pair loop works with v' = k v (see obstacle_pair2).
+  const double D = r[1], kv = 1.4426950408889634 / (double)r[4];
   const bool damped = std::fabs(D) > 1e-30;
-  row[SP_D2A] = damped ? (float)(R / ((double)r[2] * D)) : 0.f;
-  row[SP_D2B] = damped ? (float)((double)r[3] / D) : 1152921504606846976.f;
-  row[SP_K_VEL] = (float)(1.4426950408889634 / (double)r[4]);
+  row[SP_D2A] = damped ? (float)(R / ((double)r[2] * D * kv)) : 0.f;
+  row[SP_D2B] = damped ? (float)((double)r[3] / (D * kv)) : 1152921504606846976.f;
+  row[SP_K_VEL] = (float)kv;
   row[SP_K_REP] = (float)(-1.4426950408889634 * R / (double)r[6]);
-  row[SP_RGAIN] = r[5];
+  row[SP_RGAIN] = (float)((double)r[5] * kv * kv);
+  row[SP_INV_K2] = (float)(1.0 / (kv * kv));
   row[SP_REACH] = (float)((rad + margin) * 1.00001);
 }
 

@@ -106,9 +106,6 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 #ifndef RMP2_SKIP_MIN_SPHERES
 #define RMP2_SKIP_MIN_SPHERES 32      // rows shorter than this run every pair even with RMP2_OPT_EARLY_OUT set
 #endif
-#ifndef RMP2_REACH_TOL
-#define RMP2_REACH_TOL 2e-6f          // k of the expanded reach test (reach_masks_64x): slack 2k (u^2 + r^2) on the squared distance
-#endif
 #ifndef RMP2_SKIP_UNROLL
 #define RMP2_SKIP_UNROLL 1            // packed steps per trip of the early-out pair loop (2: measured slower, 1.236 vs 1.170 ms/step)
 #endif
@@ -139,10 +136,9 @@ RMP2_DEV void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64
 // ones -- which thread does the work changes, the sums do not: bit-identical to the all-pairs variant
 // (tests/test_gpu_step.py::test_early_out_is_exact).
 struct SkipOwner {                  // what travels with an owner when it is re-dealt (phase 2)
-  float p[3], v[3], vv;
+  float p[3], v[3], a[3], vv;
   uint32_t mask_even, mask_odd;
   int32_t thread;                   // the owner's home thread: slot = thread / E, environment = thread % E
-  int32_t pad;                      // 11 words: an odd stride keeps owners[t] conflict free across a warp
 };
 
 template <bool kTma, bool kSkip>
@@ -188,10 +184,14 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
   float* rec = A.rec + (size_t)slot * A.B + env;
   const size_t fstride = (size_t)L * A.B;
   float px = 0.f, py = 0.f, pz = 0.f, vv = 0.f;
-  float v[3] = {0.f, 0.f, 0.f};
-  if (active) {                                     // (fields 6..8, a = Jdot qd of the frame origin: read at the end)
+  float v[3] = {0.f, 0.f, 0.f}, a[3] = {0.f, 0.f, 0.f};
+  if (active) {
     px = rec[0 * fstride], py = rec[1 * fstride], pz = rec[2 * fstride];
     v[0] = rec[3 * fstride], v[1] = rec[4 * fstride], v[2] = rec[5 * fstride];
+    // a = Jdot qd of the frame origin is only used after the pair loop.  The all-pairs variant reads it there (three
+    // registers less through the loop: 0.879 vs 0.885 ms); the early-out variant's threads are short-lived and
+    // latency bound, a load at their end costs more than it saves (1.075 vs 1.064 ms per step)
+    if (kSkip) a[0] = rec[6 * fstride], a[1] = rec[7 * fstride], a[2] = rec[8 * fstride];
     vv = rec[9 * fstride];
   }
   float p[SP_COUNT];
@@ -201,32 +201,19 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
     mbar_wait(bar, 0);
     // the sphere loads below are plain (non-volatile) asm so that the scheduler may hoist them over
     // arithmetic; making their address depend on this statement keeps them after the wait
-    asm volatile("" : "+r"(row), "+r"(tile) : : "memory");
-  }
-  // Early-out, staged rows of at most 64 spheres: one pass of the whole block leaves b_o = |c_o|^2 - (1 + 2k) r_o^2 of
-  // every sphere of the tile in shared memory -- the part of the expanded reach test (reach_masks_64) that the L
-  // obstacle leaves of an environment share.  Row pitch (O rounded up to 8) + 4 words: the LDS.128 of 8 consecutive
-  // lanes (environments) fall into 8 distinct 16-byte bank groups.
-  const bool expanded = kTma && sorted;
-  const uint32_t pitch_b = ((((uint32_t)O + 7u) & ~7u) + 4u) * 4u;
-  uint32_t brow = 0;
-  if (expanded) {
-    const uint32_t bsm = tile + (uint32_t)E * pitch + 16u;
-    const float infl = -(1.f + 2.f * RMP2_REACH_TOL);
-    for (int e = t >> 5; e < rows; e += blockDim.x >> 5)
-      for (int o = t & 31; o < O; o += 32) {
-        const float4 c = lds128(tile + (uint32_t)e * pitch + (uint32_t)o * 16u);
-        const float b = fmaf(c.x, c.x, fmaf(c.y, c.y, fmaf(c.z, c.z, infl * c.w * c.w)));
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bsm + (uint32_t)e * pitch_b + (uint32_t)o * 4u), "f"(b) : "memory");
-      }
-    __syncthreads();
-    brow = bsm + (uint32_t)e_local * pitch_b;
-    asm volatile("" : "+r"(brow) : : "memory");      // the b loads below stay behind the barrier
+    asm volatile("" : "+r"(row) : : "memory");
   }
   // Two spheres per step in packed f32x2 arithmetic: lane x of every accumulator takes the even
   // spheres of the environment, lane y the odd ones (fixed assignment -> the early-out variant adds
   // the same terms to the same accumulators in the same order and stays bit-identical).
   float2 S[6], g[3];
+  float vk[3] = {0.f, 0.f, 0.f}, vvk = 0.f;          // k v and |k v|^2 of this thread's owner (obstacle_pair2)
+  auto scale_velocity = [&]() {
+    const float k = p[SP_K_VEL];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) vk[i] = k * v[i];
+    vvk = (k * k) * vv;
+  };
 #pragma unroll
   for (int i = 0; i < 6; ++i) S[i] = make_float2(0.f, 0.f);
 #pragma unroll
@@ -252,11 +239,12 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
     const float2 sgn = make_float2(copysignf(inv_dc.x, sd.x), copysignf(inv_dc.y, sd.y));       // inside: normal flips
     const float2 d = make_float2(fabsf(sd.x) + 1e-12f, fabsf(sd.y) + 1e-12f);                   // > 0 (FADD, not FMNMX)
     const float2 inv_d = make_float2(fast_rcp(d.x), fast_rcp(d.y));
-    obstacle_pair2(p, __fmul2_rn(rx, sgn), __fmul2_rn(ry, sgn), __fmul2_rn(rz, sgn), d, inv_d, v, vv, S, g);
+    obstacle_pair2(p, __fmul2_rn(rx, sgn), __fmul2_rn(ry, sgn), __fmul2_rn(rz, sgn), d, inv_d, vk, vvk, S, g);
   };
   const float4* gs = reinterpret_cast<const float4*>(A.spheres) + (size_t)env * O;
   auto load_sphere = [&](int o) -> float4 { return kTma ? lds128(row + (uint32_t)o * 16u) : __ldg(gs + o); };
   if (!kSkip) {
+    scale_velocity();
     // a sphere that contributes exactly zero (beyond every metric radius; d ~ 1e15 keeps all terms finite)
     const float4 far_away = make_float4(px + 1e15f, py, pz, 0.f);
     constexpr int kStep = 2 * RMP2_SPHERES_STEPS_PER_TRIP;      // spheres per loop trip
@@ -324,52 +312,6 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       mask_even = __brev(acc_even);
       mask_odd = __brev(acc_odd);
     };
-    // The same decision from the EXPANDED squared distance (staged rows, O <= 64), 7.25 instructions per sphere:
-    //     |p - c|^2 - (reach + r)^2 = (|c|^2 - r^2) - 2 p.c - 2 reach r + (|p|^2 - reach^2)
-    // four FFMA on the scalars the LDS.128 delivers, seeded with the block-shared b_o (a quarter LDS.128), one FADD of
-    // the thread's constant, one funnel shift of the sign.  Cancellation makes this form less accurate than the
-    // direct one, so it carries its own rigorous slack: with u = 2|p| + reach, every term of the sum is bounded by
-    // (|p| + |c|)^2 + (reach + r)^2 <= 2 (u + r)^2 <= 4 (u^2 + r^2) for a pair inside the reach (|c| <= |p| + reach + r),
-    // seven roundings (b_o: 3, chain: 4, constant: ~1) give an error below 7 eps 4 (u^2 + r^2) = 1.7e-6 (u^2 + r^2);
-    // the test subtracts 2k (u^2 + r^2) with k = RMP2_REACH_TOL = 2e-6 (r^2 part inside b_o).  A pair kept without need
-    // contributes exactly zero (xs saturates), so only this direction matters.
-    auto reach_masks_64x = [&](uint32_t& mask_even, uint32_t& mask_odd) {
-      const float reach = p[SP_REACH];
-      const float m2x = -2.f * px, m2y = -2.f * py, m2z = -2.f * pz, m2r = -2.f * reach;
-      const float pp = fmaf(px, px, fmaf(py, py, pz * pz));
-      const float u = fmaf(2.f, sqrtf(pp), reach);
-      const float C = fmaf(-2.f * RMP2_REACH_TOL * u, u, fmaf(-reach, reach, pp));
-      uint32_t acc_even = 0u, acc_odd = 0u;                          // bit 31 - k <-> sphere pair k, reversed at the end
-      auto margin = [&](const float4 c, const float b) -> uint32_t {
-        return __float_as_uint(fmaf(c.x, m2x, fmaf(c.y, m2y, fmaf(c.z, m2z, fmaf(c.w, m2r, b)))) + C);   // < 0 inside
-      };
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {                                  // 8 spheres per chunk, one bounds check per chunk
-        if (8 * c < O) {
-          const float4 b0 = lds128(brow + 32u * c), b1 = lds128(brow + 32u * c + 16u);
-          const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          if (8 * c + 8 <= O) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              acc_even = __funnelshift_l(margin(load_sphere(8 * c + 2 * k), b[2 * k]), acc_even, 1);
-              acc_odd = __funnelshift_l(margin(load_sphere(8 * c + 2 * k + 1), b[2 * k + 1]), acc_odd, 1);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int o = 8 * c + 2 * k;
-              acc_even = __funnelshift_l((o < O) ? margin(load_sphere(o), b[2 * k]) : 0u, acc_even, 1);
-              acc_odd = __funnelshift_l((o + 1 < O) ? margin(load_sphere(o + 1), b[2 * k + 1]) : 0u, acc_odd, 1);
-            }
-          }
-        } else {
-          acc_even <<= 4;
-          acc_odd <<= 4;
-        }
-      }
-      mask_even = __brev(acc_even);
-      mask_odd = __brev(acc_odd);
-    };
     // phase 3: the pairs of the set bits, an even with an odd sphere per packed step; an exhausted list yields the
     // far-away sphere (staged rows: the pad slot, index O -- one select on the index instead of four on the data)
     auto masked_pairs = [&](int o0, uint32_t mask_even, uint32_t mask_odd) {
@@ -394,6 +336,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       }
     };
     if (!sorted) {
+      scale_velocity();
       for (int o0 = 0; o0 < O; o0 += 64) {
         uint32_t me, mo;
         reach_masks(o0, me, mo);
@@ -403,10 +346,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       __shared__ SkipOwner owners[RMP2_SPHERES_BLOCK];
       __shared__ int hist[36], first[36];
       uint32_t me = 0u, mo = 0u;
-      if (active) {
-        if (expanded) reach_masks_64x(me, mo);
-        else reach_masks_64(me, mo);
-      }
+      if (active) reach_masks_64(me, mo);
       const int steps = max(__popc(me), __popc(mo));            // 0 .. 32
       for (int i = t; i < 36; i += blockDim.x) hist[i] = 0;        // (a block may have as few as 32 threads)
       __syncthreads();
@@ -422,7 +362,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
         SkipOwner& w = owners[first[steps] + rank];
         w.p[0] = px, w.p[1] = py, w.p[2] = pz;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) w.v[i] = v[i];
+        for (int i = 0; i < 3; ++i) w.v[i] = v[i], w.a[i] = a[i];
         w.vv = vv;
         w.mask_even = me, w.mask_odd = mo;
         w.thread = active ? t : -1;
@@ -431,7 +371,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       const SkipOwner& r = owners[t];
       px = r.p[0], py = r.p[1], pz = r.p[2];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) v[i] = r.v[i];
+      for (int i = 0; i < 3; ++i) v[i] = r.v[i], a[i] = r.a[i];
       vv = r.vv;
       me = r.mask_even, mo = r.mask_odd;
       const int home = r.thread;
@@ -444,17 +384,21 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       if (kTma) row = tile + (uint32_t)e_local * pitch;
 #pragma unroll
       for (int i = 0; i < SP_COUNT; ++i) p[i] = ST.p[slot][i];
+      scale_velocity();
       masked_pairs(0, me, mo);
     }
   }
-  // The pair loop left the n.a part of the curvature term out of g (obstacle_pair2): sum_o m (n.a) n = S a, once here.
-  const float a0 = rec[6 * fstride], a1 = rec[7 * fstride], a2 = rec[8 * fstride];
+  // The pair loop left the n.a part of the curvature term out of g and accumulated k^2 g (obstacle_pair2):
+  // sum_o m (n.a) n = S a, once here.
+  if (!kSkip) a[0] = rec[6 * fstride], a[1] = rec[7 * fstride], a[2] = rec[8 * fstride];
+  const float a0 = a[0], a1 = a[1], a2 = a[2];
   float Ss[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) Ss[i] = S[i].x + S[i].y;
-  const float g0 = (g[0].x + g[0].y) - fmaf(Ss[0], a0, fmaf(Ss[1], a1, Ss[2] * a2));
-  const float g1 = (g[1].x + g[1].y) - fmaf(Ss[1], a0, fmaf(Ss[3], a1, Ss[4] * a2));
-  const float g2 = (g[2].x + g[2].y) - fmaf(Ss[2], a0, fmaf(Ss[4], a1, Ss[5] * a2));
+  const float ik2 = p[SP_INV_K2];
+  const float g0 = fmaf(g[0].x + g[0].y, ik2, -fmaf(Ss[0], a0, fmaf(Ss[1], a1, Ss[2] * a2)));
+  const float g1 = fmaf(g[1].x + g[1].y, ik2, -fmaf(Ss[1], a0, fmaf(Ss[3], a1, Ss[4] * a2)));
+  const float g2 = fmaf(g[2].x + g[2].y, ik2, -fmaf(Ss[2], a0, fmaf(Ss[4], a1, Ss[5] * a2)));
 #pragma unroll
   for (int i = 0; i < 6; ++i) rec[i * fstride] = Ss[i];                 // fields 0..5: S, 6..8: g (in place)
   rec[6 * fstride] = g0;
@@ -926,9 +870,7 @@ cudaError_t rmp2_launch_frames(const StepTables& T, const StepArgs& A, int block
 size_t rmp2_spheres_smem(const SphereTables& ST, int n_spheres, bool use_tma) {
   if (!use_tma) return 0;
   const size_t pitch = (size_t)n_spheres * 16 + 16;
-  // rows, the mbarrier (16 bytes), and for rows of at most 64 spheres the b_o array of the expanded reach test
-  const size_t pitch_b = n_spheres <= 64 ? ((((size_t)n_spheres + 7) & ~(size_t)7) + 4) * 4 : 0;
-  return 128 + (size_t)ST.envs_per_block * (pitch + pitch_b) + 16;
+  return 128 + (size_t)ST.envs_per_block * pitch + sizeof(uint64_t);
 }
 
 cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, bool use_tma, cudaStream_t stream) {

@@ -255,8 +255,12 @@ RMP2_DEV void obstacle_pair(const float* __restrict__ p, float nx, float ny, flo
 //        e_v = exp(xdot / l_v)): the damping gain D rides on the reciprocal for free;
 //   xdd - c' = G e_rep - (q den1') xdot - curv  as two FMAs, c' = c - n.a;
 //   the n.a term of the curvature c (three FMAs per pair) never enters the loop:
-//        sum_o m (n.a) n = (sum_o m n n^T) a = S a   -- the caller subtracts S a once per (environment, leaf).
-// 43 lane operations per pair (round 1: 61, then 49, then 47).
+//        sum_o m (n.a) n = (sum_o m n n^T) a = S a   -- the caller subtracts S a once per (environment, leaf);
+//   the velocity enters pre-scaled, v' = k v with k = log2(e)/l_v, so xdot' = n.v' is the exponent of e_v as it
+//        stands; everything downstream that is quadratic in the velocity carries k^2 (|v'|^2, the damping term through
+//        den2' = den2 / (D k), the repulsion through G' = G k^2) and the caller divides g by k^2 once;
+//   g += (xdd - c')(m n): the product with m is shared with the metric's m n.
+// 41 lane operations per pair (round 1: 61, then 49, 47, 43).
 // Sphere-row parameters, derived on the host in double (fill_sphere_row, rmp2_api.cu):
 #define SP_XA 0           // 1 / r
 #define SP_XB 1           // -margin / r
@@ -264,13 +268,14 @@ RMP2_DEV void obstacle_pair(const float* __restrict__ p, float nx, float ny, flo
 #define SP_GT_B 3         // -1           (0 when metric_scalar == 0)
 #define SP_D1A 4          // r / (metric_exploder_std_dev * metric_scalar)
 #define SP_D1B 5          // metric_exploder_eps / metric_scalar
-#define SP_D2A 6          // r / (damping_std_dev * damping_gain)      (0 when damping_gain == 0)
-#define SP_D2B 7          // damping_robustness_eps / damping_gain     (2^60 when damping_gain == 0: no damping term)
-#define SP_K_VEL 8        //  log2(e) / damping_velocity_gate_length_scale
+#define SP_D2A 6          // r / (damping_std_dev * damping_gain * k)      (0 when damping_gain == 0)
+#define SP_D2B 7          // damping_robustness_eps / (damping_gain * k)   (2^60 when damping_gain == 0: no damping term)
+#define SP_K_VEL 8        // k = log2(e) / damping_velocity_gate_length_scale
 #define SP_K_REP 9        // -log2(e) r / repulsion_std_dev
-#define SP_RGAIN 10
+#define SP_RGAIN 10       // repulsion_gain * k^2
 #define SP_REACH 11       // (r + margin) * (1 + 1e-5): conservative bound of the early-out test
-#define SP_COUNT 12
+#define SP_INV_K2 12      // 1 / k^2
+#define SP_COUNT 13
 
 RMP2_DEV float2 bc2(float s) { return make_float2(s, s); }
 RMP2_DEV float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
@@ -280,30 +285,28 @@ RMP2_DEV float fma_sat(float a, float b, float c) {                             
   return y;
 }
 
-// n = unit vectors obstacle -> link of the two pairs, d = distances, inv_d = 1/d; v = velocity of the frame origin,
-// vv = |v|^2.  S[i], g[i]: lane x accumulates the even spheres of the environment, lane y the odd ones.
-// g is accumulated WITHOUT the n.a part of the curvature term: the caller finishes with g -= S a.
+// n = unit vectors obstacle -> link of the two pairs, d = distances, inv_d = 1/d; vk = k v (velocity of the frame
+// origin, pre-scaled), vvk = |k v|^2.  S[i], g[i]: lane x accumulates the even spheres of the environment, lane y the
+// odd ones.  g is accumulated as k^2 (g + S a): the caller finishes with g = g / k^2 - S a.
 RMP2_DEV void obstacle_pair2(const float* __restrict__ p, float2 nx, float2 ny, float2 nz, float2 d, float2 inv_d,
-                             const float (&v)[3], float vv, float2 (&S)[6], float2 (&g)[3]) {
-  const float2 xdot = __ffma2_rn(nx, bc2(v[0]), __ffma2_rn(ny, bc2(v[1]), __fmul2_rn(nz, bc2(v[2]))));
-  const float2 curv = __fmul2_rn(__ffma2_rn(neg2(xdot), xdot, bc2(vv)), inv_d);   // (|v|^2 - xdot^2)/d  taskmap.py:120-138
+                             const float (&vk)[3], float vvk, float2 (&S)[6], float2 (&g)[3]) {
+  const float2 xdot = __ffma2_rn(nx, bc2(vk[0]), __ffma2_rn(ny, bc2(vk[1]), __fmul2_rn(nz, bc2(vk[2]))));   // k n.v
+  const float2 curv = __fmul2_rn(__ffma2_rn(neg2(xdot), xdot, bc2(vvk)), inv_d);  // k^2 (|v|^2 - xdot^2)/d  taskmap.py:120-138
   // xs = clamp((d - margin) / r, 0, 1)                                           rmp2.py:185-186, 170-174
   const float2 xs = make_float2(fma_sat(d.x, p[SP_XA], p[SP_XB]), fma_sat(d.y, p[SP_XA], p[SP_XB]));
   const float2 den1 = __ffma2_rn(xs, bc2(p[SP_D1A]), bc2(p[SP_D1B]));           // (x/s_e + eps_e) / scalar  rmp2.py:187
-  const float2 den2 = __ffma2_rn(xs, bc2(p[SP_D2A]), bc2(p[SP_D2B]));           // (x/s_d + eps_d) / D       rmp2.py:191
-  const float2 tv = __fmul2_rn(xdot, bc2(p[SP_K_VEL]));
-  const float2 ev = make_float2(fast_exp2(tv.x), fast_exp2(tv.y));               // 1/(1 - sigmoid) = 1 + ev  rmp2.py:190
+  const float2 den2 = __ffma2_rn(xs, bc2(p[SP_D2A]), bc2(p[SP_D2B]));           // (x/s_d + eps_d) / (D k)   rmp2.py:191
+  const float2 ev = make_float2(fast_exp2(xdot.x), fast_exp2(xdot.y));           // 1/(1 - sigmoid) = 1 + ev  rmp2.py:190
   const float2 den12 = __fmul2_rn(den1, den2);
   const float2 Q = __ffma2_rn(den12, ev, den12);
   const float2 q = make_float2(fast_rcp(Q.x), fast_rcp(Q.y));                    // 0 when ev overflowed: no metric, no force
   const float2 w1 = __fmul2_rn(q, den2);                                          // (1-sig) scalar / (x/s_e + eps_e)
-  const float2 w2 = __fmul2_rn(q, den1);                                          // (1-sig) D / (x/s_d + eps_d)
+  const float2 w2 = __fmul2_rn(q, den1);                                          // (1-sig) D k / (x/s_d + eps_d)
   const float2 gt = __ffma2_rn(xs, bc2(p[SP_GT_A]), bc2(p[SP_GT_B]));           // x/r - 1, 0 beyond the radius
   const float2 m = __fmul2_rn(w1, __fmul2_rn(gt, gt));                            // rmp2.py:172,194
   const float2 tr = __fmul2_rn(xs, bc2(p[SP_K_REP]));
   const float2 er = make_float2(fast_exp2(tr.x), fast_exp2(tr.y));               // rmp2.py:189
-  const float2 ac = __ffma2_rn(bc2(p[SP_RGAIN]), er, neg2(__ffma2_rn(w2, xdot, curv)));   // xdd - (c - n.a)
-  const float2 h = __fmul2_rn(m, ac);
+  const float2 ac = __ffma2_rn(bc2(p[SP_RGAIN]), er, neg2(__ffma2_rn(w2, xdot, curv)));   // k^2 (xdd - (c - n.a))
   const float2 mx = __fmul2_rn(m, nx), my = __fmul2_rn(m, ny), mz = __fmul2_rn(m, nz);
   S[0] = __ffma2_rn(mx, nx, S[0]);
   S[1] = __ffma2_rn(mx, ny, S[1]);
@@ -311,9 +314,9 @@ RMP2_DEV void obstacle_pair2(const float* __restrict__ p, float2 nx, float2 ny, 
   S[3] = __ffma2_rn(my, ny, S[3]);
   S[4] = __ffma2_rn(my, nz, S[4]);
   S[5] = __ffma2_rn(mz, nz, S[5]);
-  g[0] = __ffma2_rn(h, nx, g[0]);
-  g[1] = __ffma2_rn(h, ny, g[1]);
-  g[2] = __ffma2_rn(h, nz, g[2]);
+  g[0] = __ffma2_rn(ac, mx, g[0]);
+  g[1] = __ffma2_rn(ac, my, g[1]);
+  g[2] = __ffma2_rn(ac, mz, g[2]);
 }
 
 // scalar form used by rmp2_leaf_evaluate: x, xd -> xdd, M
