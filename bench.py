@@ -38,7 +38,7 @@ FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # analytic, at clocks.max
 # The pair loop's real bound (profiles/r1_pipe_peaks.json): FP32 and ALU-pipe instructions
 # share lane time on a B200 SM (128 lanes/clk), MUFU (16/clk/SM) runs underneath.  Thread-level operations
 # per (frame, sphere) pair, counted from the SASS of rmp2_spheres_kernel's unrolled loop:
-LANE_OPS_PER_PAIR = 49.0        # 46 FP32 (41 packed halves + 5 scalar) + 3 ALU
+LANE_OPS_PER_PAIR = 42.5        # 41 FP32 (35 packed halves + 6 scalar) + 1.5 ALU (copysign LOP3, loop overhead); round 1: 49
 MUFU_PER_PAIR = 5.0
 LANE_PEAK_TOPS = 148 * 128 * 1.965e9 / 1e12
 MUFU_PEAK_TOPS = 148 * 16 * 1.965e9 / 1e12
@@ -685,7 +685,7 @@ def run_b200_arm(args):
         total_kernel_ms = sum(v[0] for v in kernel_ms.values()) / args.steps
         # algorithmic bytes / flops of one launch of the dominant kernel
         if O_:
-            dom_bytes = B * (16.0 * O_ + 76.0 * n_slots)           # spheres in, 40 B frame record in, 36 B (S,g) out
+            dom_bytes = B * (16.0 * O_ + 76.0 * n_slots)           # spheres in, frame record in (40 B; 36 B since round 2), 36 B (S,g) out
             dom_flops = B * 76.0 * O_ * n_slots                    # SURVEY.md 8d term C
         else:
             dom_bytes = B * BYTES_PER_ENV[config]

@@ -136,7 +136,7 @@ RMP2_DEV void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64
 // ones -- which thread does the work changes, the sums do not: bit-identical to the all-pairs variant
 // (tests/test_gpu_step.py::test_early_out_is_exact).
 struct SkipOwner {                  // what travels with an owner when it is re-dealt (phase 2)
-  float p[3], v[3], a[3], vv;
+  float p[3], v[3], a[3], pad;       // (13 words: an odd stride keeps owners[t] conflict free across a warp)
   uint32_t mask_even, mask_odd;
   int32_t thread;                   // the owner's home thread: slot = thread / E, environment = thread % E
 };
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
   // this thread's frame record and leaf parameters (loads in flight while the rows land)
   float* rec = A.rec + (size_t)slot * A.B + env;
   const size_t fstride = (size_t)L * A.B;
-  float px = 0.f, py = 0.f, pz = 0.f, vv = 0.f;
+  float px = 0.f, py = 0.f, pz = 0.f;
   float v[3] = {0.f, 0.f, 0.f}, a[3] = {0.f, 0.f, 0.f};
   if (active) {
     px = rec[0 * fstride], py = rec[1 * fstride], pz = rec[2 * fstride];
@@ -192,7 +192,6 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
     // registers less through the loop: 0.879 vs 0.885 ms); the early-out variant's threads are short-lived and
     // latency bound, a load at their end costs more than it saves (1.075 vs 1.064 ms per step)
     if (kSkip) a[0] = rec[6 * fstride], a[1] = rec[7 * fstride], a[2] = rec[8 * fstride];
-    vv = rec[9 * fstride];
   }
   float p[SP_COUNT];
 #pragma unroll
@@ -212,7 +211,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
     const float k = p[SP_K_VEL];
 #pragma unroll
     for (int i = 0; i < 3; ++i) vk[i] = k * v[i];
-    vvk = (k * k) * vv;
+    vvk = fmaf(vk[0], vk[0], fmaf(vk[1], vk[1], vk[2] * vk[2]));
   };
 #pragma unroll
   for (int i = 0; i < 6; ++i) S[i] = make_float2(0.f, 0.f);
@@ -363,7 +362,6 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
         w.p[0] = px, w.p[1] = py, w.p[2] = pz;
 #pragma unroll
         for (int i = 0; i < 3; ++i) w.v[i] = v[i], w.a[i] = a[i];
-        w.vv = vv;
         w.mask_even = me, w.mask_odd = mo;
         w.thread = active ? t : -1;
       }
@@ -372,7 +370,6 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       px = r.p[0], py = r.p[1], pz = r.p[2];
 #pragma unroll
       for (int i = 0; i < 3; ++i) v[i] = r.v[i], a[i] = r.a[i];
-      vv = r.vv;
       me = r.mask_even, mo = r.mask_odd;
       const int home = r.thread;
       active = home >= 0;

@@ -10,7 +10,7 @@
 #define RMP2_SLOT_BASE (-2)       // restore_slot value meaning "start from the base link"
 #define RMP2_CHAIN_FLOATS 24      // R(9) p(3) w(3) v(3) alpha(3) a(3)
 #define RMP2_PAIR_FLOATS 8        // floats per explicit pair row (rmp2_step_io.pairs)
-#define RMP2_REC_FLOATS 10        // fields of one frame record (p, v, a, |v|^2); (S, g) reuse 9 of them
+#define RMP2_REC_FLOATS 9         // fields of one frame record (p, v, a); the (S, g) sums overwrite them in place
 
 struct FrameTab {
   float R[9];            // constant rotation  (reference: kinematics.py:202, R_x R_y R_z order)
@@ -93,7 +93,7 @@ struct StepArgs {
   const float* goals;
   const float* spheres;
   const float* pairs;
-  float* rec;            // [10][n_sphere_slots][B] scratch, field-major: frame records in, (S, g) sums out
+  float* rec;            // [9][n_sphere_slots][B] scratch, field-major: frame records in, (S, g) sums out
   float* mf;             // [N*N + N][B] scratch (N = kernel width): combined M and f between the step and the resolve
                          // kernel (split mode); in either mode the factorised problems handed to the fallback kernel
   int32_t* fb;           // fallback work list: [0] length, [1] block ticket, [2 ...] environment indices

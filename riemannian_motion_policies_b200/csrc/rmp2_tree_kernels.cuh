@@ -61,7 +61,7 @@ RMP2_DEV void visit_frame(const StepTables& T, int fi, const float (&q)[N], cons
 }
 
 // ------------------------------------------------------------------------------- frames kernel
-// rec[field][slot][env] = (p, v, a, |v|^2) for every sphere-obstacle leaf slot (fields 0..9).
+// rec[field][slot][env] = (p, v, a) for every sphere-obstacle leaf slot (fields 0..8).
 template <int N>
 RMP2_DEV void frames_body(const StepTables& T, const StepArgs& A) {
   extern __shared__ float slots[];
@@ -87,7 +87,6 @@ RMP2_DEV void frames_body(const StepTables& T, const StepArgs& A) {
     for (int li = F.leaf_begin; li < F.leaf_end; ++li) {
       const LeafTab& L = T.leaves[li];
       if (L.space != RMP2_SPACE_FRAME_DISTANCE_SPHERES) continue;
-      const float vv = fmaf(ch.v[0], ch.v[0], fmaf(ch.v[1], ch.v[1], ch.v[2] * ch.v[2]));
       float* r = rec + (size_t)L.sphere_slot * A.B;
       r[0 * fstride] = ch.p[0];
       r[1 * fstride] = ch.p[1];
@@ -98,7 +97,6 @@ RMP2_DEV void frames_body(const StepTables& T, const StepArgs& A) {
       r[6 * fstride] = ch.a[0];
       r[7 * fstride] = ch.a[1];
       r[8 * fstride] = ch.a[2];
-      r[9 * fstride] = vv;
     }
   }
 }
