@@ -75,6 +75,7 @@ struct rmp2_tree {
   int split_resolve = -1;                 // RMP2_OPT_SPLIT_RESOLVE: -1 by batch size, 0 fused, 1 split
   int force_block = 0;                    // RMP2_OPT_BLOCK_THREADS: 0 by batch size, else 32 / 64 / 128
   long long chunk_envs = 0;               // RMP2_OPT_CHUNK_ENVS: environments per internal chunk (0 = 2^20)
+  int spec_step_block = 0;                // tuning hook RMP2_SPEC_STEP_BLOCK: block size of the specialised step kernel for large batches (0: 256 for n <= 7)
   bool respecialize = false;              // rebuild the specialised kernels when a leaf changes
   KernelClock clock[RMP2_N_CLOCKS];       // frames, spheres, step, resolve, resolve fallback
   HostStage stage[3];
@@ -448,6 +449,10 @@ int rmp2_tree_create(const rmp2_robot* rb, const rmp2_leaf_desc* leaves, int32_t
     if (b == 32 || b == 64 || b == 128) tr->force_block = b;
   }
   if (const char* v = getenv("RMP2_CHUNK_ENVS")) tr->chunk_envs = std::max(0LL, atoll(v));
+  if (const char* v = getenv("RMP2_SPEC_STEP_BLOCK")) {
+    const int b = atoi(v);
+    if (b == 128 || b == 256) tr->spec_step_block = b;
+  }
   tr->sph.n_slots = T.n_sphere_slots;
   if (T.n_sphere_slots > 0) {
     // E environments per block: E * L threads <= 128, E <= 32 (box rows), shared memory bounded
@@ -643,10 +648,14 @@ int launch_chunk(rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
   }
   {
     ScopedClock clk(tree, 2, stream);
-    if (tree->spec)
-      e = rmp2_jit_launch(tree->spec, A.split ? 2 : 1, A, (unsigned)((A.B + block - 1) / block), block,
-                          rmp2_step_smem(T, block), stream, jit_err);
-    else
+    if (tree->spec) {
+      // large batches: 256-thread blocks (instruction fetch, see RMP2_SPEC_STEP_THREADS in rmp2_tree_kernels.cuh)
+      int sb = block;
+      if (block == 128 && A.B >= 148LL * 2 * 256 * 2 && rmp2_pick_width(T.n) <= 7)
+        sb = tree->spec_step_block ? tree->spec_step_block : 256;
+      e = rmp2_jit_launch(tree->spec, A.split ? 2 : 1, A, (unsigned)((A.B + sb - 1) / sb), sb,
+                          rmp2_step_smem(T, sb), stream, jit_err);
+    } else
       e = rmp2_launch_step(T, A, block, stream);
   }
   if (e != cudaSuccess) return cuda_fail(e, (std::string("rmp2_step_kernel launch") + (jit_err.empty() ? "" : ": " + jit_err)).c_str());

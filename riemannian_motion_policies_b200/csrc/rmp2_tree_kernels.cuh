@@ -190,6 +190,22 @@ RMP2_DEV void resolve_or_defer(const StepArgs& A, float (&M)[N][N], float (&f)[N
 #ifndef RMP2_STEP_MIN_BLOCKS
 #define RMP2_STEP_MIN_BLOCKS(N) ((N) <= 7 ? 4 : ((N) <= 9 ? 3 : 2))
 #endif
+// The tree-specialised step kernels are ~110 KB of straight-line code and their top stall is instruction fetch
+// (ncu: no_instruction 2.5 of 6.8 stalled warps per issue).  Warps of one block start together and stay close, so a
+// fetched line serves several of them: 256-thread blocks (two warps per SM sub-partition and block, two blocks per
+// SM -- the same 128-register budget as four blocks of 128) run the config-4 step kernel in 0.270 ms instead of
+// 0.303; 512-thread blocks 0.283 (one block per SM: no latency diversity), block barriers between the frames
+// (forced lock step) cost more than they save (0.283 at 256, 0.311 at 512).  Upper bound of the launch only: small
+// batches still launch 32 / 64 / 128 threads.  N > 7 keeps 128 (its register budget needs 3 or 2 blocks per SM).
+#ifndef RMP2_SPEC_STEP_THREADS
+#define RMP2_SPEC_STEP_THREADS(N) ((N) <= 7 ? 256 : RMP2_BLOCK_THREADS)
+#endif
+#ifndef RMP2_SPEC_STEP_MIN_BLOCKS
+#define RMP2_SPEC_STEP_MIN_BLOCKS(N) ((N) <= 7 ? 2 : RMP2_STEP_MIN_BLOCKS(N))
+#endif
+#ifndef RMP2_SPEC_SPLIT_MIN_BLOCKS
+#define RMP2_SPEC_SPLIT_MIN_BLOCKS(N) ((N) <= 7 ? 2 : RMP2_SPLIT_MIN_BLOCKS(N))
+#endif
 // kSplit: stop after the combined (M, f) and hand them to rmp2_resolve_kernel through A.mf
 // (field-major [N*N + N][B]); used for large batches, where two small kernels beat one big one.
 template <int N, bool kSplit>
