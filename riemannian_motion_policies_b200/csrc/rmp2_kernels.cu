@@ -145,8 +145,14 @@ template <bool kTma, bool kSkip>
 __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP_MIN_BLOCKS : RMP2_SPHERES_MIN_BLOCKS) * 128 / RMP2_SPHERES_BLOCK)
     rmp2_spheres_kernel(const __grid_constant__ SphereTables ST, const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ SkipOwner owners[kSkip ? RMP2_SPHERES_BLOCK : 1];   // re-deal of the early-out variant (phase 2)
+  __shared__ int hist[kSkip ? 33 : 1];
   const int L = ST.n_slots, E = ST.envs_per_block;
   const int t = threadIdx.x;
+  if (kSkip) {                                      // zeroed ahead of the barrier(s) every thread passes before phase 2
+    for (int i = t; i < 33; i += blockDim.x) hist[i] = 0;
+    if (!kTma) __syncthreads();
+  }
   int slot = t / E, e_local = t - slot * E;         // consecutive lanes = consecutive environments
   const long long env0 = (long long)blockIdx.x * E;
   long long env = env0 + e_local;
@@ -342,23 +348,25 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
         masked_pairs(o0, me, mo);
       }
     } else {
-      __shared__ SkipOwner owners[RMP2_SPHERES_BLOCK];
-      __shared__ int hist[36], first[36];
       uint32_t me = 0u, mo = 0u;
       if (active) reach_masks_64(me, mo);
       const int steps = max(__popc(me), __popc(mo));            // 0 .. 32
-      for (int i = t; i < 36; i += blockDim.x) hist[i] = 0;        // (a block may have as few as 32 threads)
-      __syncthreads();
       const int rank = atomicAdd(&hist[steps], 1);
       __syncthreads();
-      for (int i = t; i < 33; i += blockDim.x) {                  // heaviest owners first
-        int before = 0;
-        for (int s = i + 1; s <= 32; ++s) before += hist[s];
-        first[i] = before;
+      // heaviest owners first: position = (owners with more steps) + rank.  Every warp forms the suffix sums of the
+      // histogram on its own lanes (no third barrier, no serial loop): lane l holds sum_{s >= l, s < 32} hist[s]
+      const int lane = t & 31;
+      int suffix = hist[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int up = __shfl_down_sync(0xffffffffu, suffix, d);
+        if (lane + d < 32) suffix += up;
       }
-      __syncthreads();
+      const int above31 = hist[32];
+      const int more = __shfl_sync(0xffffffffu, suffix, min(steps + 1, 31));   // sum_{s > steps, s < 32} (steps <= 30)
+      const int before = (steps >= 32) ? 0 : above31 + ((steps >= 31) ? 0 : more);
       {
-        SkipOwner& w = owners[first[steps] + rank];
+        SkipOwner& w = owners[before + rank];
         w.p[0] = px, w.p[1] = py, w.p[2] = pz;
 #pragma unroll
         for (int i = 0; i < 3; ++i) w.v[i] = v[i], w.a[i] = a[i];
