@@ -9,10 +9,11 @@ d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('$1', 'all-pairs ms', round(d['ms_per_step'],4), 'spheres', round(d['kernel_ms']['spheres']['ms_per_step'],4), '| early-out ms', round(d['early_out']['ms_per_step'],4), 'speedup', round(d['early_out']['speedup_over_all_pairs'],3))"
 }
 {
-run pf0 "-DRMP2_SKIP_PREFETCH=0"
-run pf1_mb7 ""
-run pf1_mb6 "-DRMP2_SPHERES_SKIP_MIN_BLOCKS=6"
-run pf1_mb5 "-DRMP2_SPHERES_SKIP_MIN_BLOCKS=5"
+run base ""
+run scalar "-DRMP2_REACH_SCALAR=1"
+run scalar_mb8 "-DRMP2_REACH_SCALAR=1 -DRMP2_SPHERES_SKIP_MIN_BLOCKS=8"
+run mb8 "-DRMP2_SPHERES_SKIP_MIN_BLOCKS=8"
+run mb6 "-DRMP2_SPHERES_SKIP_MIN_BLOCKS=6"
 } > gpurun_out/r2l_variants.txt 2>&1
 cat gpurun_out/r2l_variants.txt
 [ -n "$NO_NCU" ] && exit 0
