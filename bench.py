@@ -342,6 +342,7 @@ def other_config_lines(ns, S, fk, n, device, steps, torch):
         core, tree, spec = build_tree(ns, S, fk, config, n)
         O_ = S.N_SPHERES[config]
         tree.set_early_out(False)
+        tree.set_merge_coincident(False)
         nb = 2 if O_ else 1
         q, qd, goal, spheres = S.synth_inputs_device(fk, n, B, O_, nb, seed=S.SEEDS[config], device=device)
         goals = goal.reshape(B, 1, 3).contiguous()
@@ -361,16 +362,19 @@ def other_config_lines(ns, S, fk, n, device, steps, torch):
         line["ms_per_step"] = ms
         line["value"] = B / (ms * 1e-3)
         line["unit"] = UNIT
-        tree.set_early_out(True)
-        if O_:                                  # library default, same launch mode
-            if graphed:
-                step(0)
-                torch.cuda.synchronize()
-                graph_eo = graph_of(lambda: step(0), torch)
-                ms_eo = time_steps(lambda i: graph_eo.replay(), steps, torch)
-            else:
-                ms_eo = time_steps(step, steps, torch)
-            line["value_early_out"] = B / (ms_eo * 1e-3)
+        if O_:                                  # the exact early-out alone, then the library default; same launch mode
+            for key, merged in (("value_early_out", False), ("value_library_default", True)):
+                tree.set_early_out(True)
+                tree.set_merge_coincident(merged)
+                if graphed:
+                    step(0)
+                    torch.cuda.synchronize()
+                    graph_eo = graph_of(lambda: step(0), torch)
+                    ms_eo = time_steps(lambda i: graph_eo.replay(), steps, torch)
+                else:
+                    ms_eo = time_steps(step, steps, torch)
+                line[key] = B / (ms_eo * 1e-3)
+            line["obstacle_leaves_and_pair_loops"] = list(tree.obstacle_slots())
         line["parity"] = fixture_parity(ns, config, n)
         out[f"config{config}"] = line
         del tree, core, q, qd, goal, spheres, qdd
@@ -515,9 +519,11 @@ def run_b200_arm(args):
     # the product's path for large batches: frames / step kernels rebuilt for this tree by NVRTC (one-off,
     # outside the timed region like any warm-up); --no-specialize times the generic table-driven kernels
     core, tree, specialized = build_tree(ns, S, fk, config, n, specialize=not args.no_specialize)
-    # Headline and roofline: every (frame, sphere) pair goes through the full arithmetic.  The exact
-    # early-out of the obstacle kernel (library default) is measured separately below.
+    # Headline and roofline: every (frame, sphere) pair of every obstacle leaf goes through the full arithmetic.  The
+    # library defaults -- the exact early-out of the obstacle kernel, one pair loop for obstacle leaves that share their
+    # control point -- are measured separately below.
     tree.set_early_out(False)
+    tree.set_merge_coincident(False)
 
     n_buffers = 4 if O_ else 1
     q, qd, goal, spheres = S.synth_inputs_device(fk, n, B, O_, n_buffers, seed=S.SEEDS[config] + 17 * rank, device=device)
@@ -563,19 +569,28 @@ def run_b200_arm(args):
     per_gpu = B / (ms_per_step * 1e-3)
 
     # ---- same workload with the library default (exact early-out of pairs beyond the metric radius)
-    early = None
-    if O_ and not args.skip_early_out:
-        tree.set_early_out(True)
+    def timed_mode(early_out, merged):
+        """ms per step (max over ranks) and per-kernel CUDA-event times of the same workload in another mode."""
+        tree.set_early_out(early_out)
+        tree.set_merge_coincident(merged)
         for i in range(3):
             step(i)
         barrier()
+        tree.profile(True)
+        tree.profile_read()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):
             step(i)
         e1.record()
         barrier()
-        ems = max_over_ranks(e0.elapsed_time(e1))
+        kms = tree.profile_read()
+        tree.profile(False)
+        return max_over_ranks(e0.elapsed_time(e1)), {k: v[0] / max(v[1], 1) for k, v in kms.items() if v[1]}
+
+    early = library_default = None
+    if O_ and not args.skip_early_out:
+        ems, _ = timed_mode(True, False)
         sub = slice(0, min(B, 8192))
         frames = S.collision_frames(fk)
         origins = torch.stack([fk.forward(q[sub], fr)[:, :3, 3] for fr in frames], dim=1)          # [b,K,3]
@@ -586,7 +601,23 @@ def run_b200_arm(args):
                  "active_pair_fraction": float((dist_s.abs() <= 0.5).float().mean()),
                  "note": "library default: pairs beyond metric_modulation_radius contribute exactly zero "
                          "(reference rmp2.py:194) and are skipped; results are identical"}
+        # ---- the library default: early-out and one pair loop per group of obstacle leaves with a common control point
+        dms, dk = timed_mode(True, True)
+        mms, mk = timed_mode(False, True)
+        n_leaves, n_loops = tree.obstacle_slots()
+        library_default = {
+            "value": world * B / (dms / args.steps * 1e-3), "unit": UNIT, "ms_per_step": dms / args.steps,
+            "speedup_over_all_pairs": ms_per_step / (dms / args.steps), "kernel_ms": dk,
+            "obstacle_leaves": n_leaves, "pair_loops": n_loops,
+            "all_pairs_merged": {"value": world * B / (mms / args.steps * 1e-3), "ms_per_step": mms / args.steps,
+                                 "kernel_ms": mk},
+            "note": "what rmp2_step does when no option is set: RMP2_OPT_EARLY_OUT and RMP2_OPT_MERGE_COINCIDENT on.  "
+                    "Obstacle leaves with equal parameters on frames whose origins coincide for every q (Panda: joint2 "
+                    "on joint1, joint6 on joint5) have identical pulled-back (M, f) -- the distance map differentiates "
+                    "through the frame origin only (taskmap.py:124-128) -- so one of them runs the pair loop and its "
+                    "sums are doubled; `value` and the roofline above run every leaf's loop"}
         tree.set_early_out(False)
+        tree.set_merge_coincident(False)
 
     # ---- result collection (north star: "NCCL allgather only for result collection"): not part of the step
     collect = None
@@ -750,7 +781,7 @@ def run_b200_arm(args):
             "kernel_ms": {k: {"ms_per_step": v[0] / args.steps, "launches": int(v[1])} for k, v in kernel_ms.items()},
             "per_gpu_value": per_gpu, "gpu_launches": int(launches), "kernel": info, "specialized": specialized,
             "clocks": clocks.summary(),
-            "early_out": early, "e2e": e2e, "collect": collect, "cpu_baseline": cpu_baseline,
+            "early_out": early, "library_default": library_default, "e2e": e2e, "collect": collect, "cpu_baseline": cpu_baseline,
             "cpu_baseline_vectorised": cpu_vec, "parity": parity, "other_configs": others, "rollout": rollout,
             "latency_b1_us": latency,
         }

@@ -246,7 +246,19 @@ int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_sphere
 #define RMP2_OPT_SPLIT_RESOLVE 2
 #define RMP2_OPT_BLOCK_THREADS 3
 #define RMP2_OPT_CHUNK_ENVS 4
+/* RMP2_OPT_MERGE_COINCIDENT (default 1): ObstacleAvoidance leaves on the sphere path whose parameters are equal and
+ * whose frame origins coincide for every q (a frame with zero constant translation and a revolute or fixed joint sits
+ * on its parent's origin; Panda: joint2 on joint1, joint6 on joint5) have the same x, xd, c and the same Jacobian up to a
+ * zero column (the reference differentiates the distance through the frame origin only, taskmap.py:124-128), hence the
+ * same pulled-back (M, f).  One leaf of the group runs the pair loop and the pullback, its sums are multiplied by the
+ * size of the group.  Results equal the unmerged tree's up to rounding (M1 + M1 = 2 M1 is exact; the sum over leaves
+ * is formed in another order).  0: every leaf on its own (used for the roofline measurement).  Changing the option
+ * recompiles the tree's tables (and its specialised kernels, when loaded). */
+#define RMP2_OPT_MERGE_COINCIDENT 5
 int rmp2_tree_set_option(rmp2_tree* tree, int32_t option, int32_t value);
+/* Sphere-path ObstacleAvoidance leaves of the tree (*n_leaves) and the pair loops that run for them per environment
+ * (*n_slots = n_leaves minus the leaves merged under RMP2_OPT_MERGE_COINCIDENT).  Either pointer may be NULL. */
+int rmp2_tree_obstacle_slots(const rmp2_tree* tree, int32_t* n_leaves, int32_t* n_slots);
 
 /* Tree-specialised kernels.  The frames and step kernels interpret the tree's tables at run time; for a
  * large batch that shares one tree that interpretation is pure overhead.  rmp2_tree_specialize rebuilds

@@ -43,6 +43,7 @@ OPT_TMA = 1
 OPT_SPLIT_RESOLVE = 2
 OPT_BLOCK_THREADS = 3
 OPT_CHUNK_ENVS = 4
+OPT_MERGE_COINCIDENT = 5
 PROFILE_KERNELS = 5
 SPECIALIZE_COMPILE_ONLY = 1
 
@@ -53,6 +54,7 @@ EXPORTS = [
     "rmp2_leaf_evaluate", "rmp2_obstacle_feed", "rmp2_last_error", "rmp2_version", "rmp2_launch_count",
     "rmp2_tree_kernel_info", "rmp2_tree_profile", "rmp2_tree_profile_read", "rmp2_tree_set_option",
     "rmp2_tree_specialize", "rmp2_tree_is_specialized", "rmp2_tree_reserve", "rmp2_pinv_solve",
+    "rmp2_tree_obstacle_slots",
 ]
 
 
@@ -134,6 +136,8 @@ def lib():
     L.rmp2_tree_kernel_info.restype = ctypes.c_int
     L.rmp2_tree_set_option.argtypes = [vp, i32, i32]
     L.rmp2_tree_set_option.restype = ctypes.c_int
+    L.rmp2_tree_obstacle_slots.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    L.rmp2_tree_obstacle_slots.restype = ctypes.c_int
     L.rmp2_tree_specialize.argtypes = [vp, i32]
     L.rmp2_tree_specialize.restype = ctypes.c_int
     L.rmp2_tree_is_specialized.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]

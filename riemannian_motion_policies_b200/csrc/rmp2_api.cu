@@ -56,8 +56,11 @@ struct KernelClock {              // optional per-kernel timing (rmp2_tree_profi
 
 struct rmp2_tree {
   StepTables tab;
+  rmp2_robot robot;                       // copy of the kinematics the tables were compiled from (recompiled on demand)
   std::vector<rmp2_leaf_desc> leaves;     // as given, tree order
-  std::vector<int> table_index;           // tree order -> index in tab.leaves
+  std::vector<int> table_index;           // tree order -> index in tab.leaves (a merged leaf: its representative's)
+  bool merge_coincident = true;           // RMP2_OPT_MERGE_COINCIDENT
+  int n_merged = 0;                       // sphere-obstacle leaves represented by another leaf's record slot
   int n_pair_sets = 0;
   int n_goal_slots_used = 0;
   SphereTables sph;                       // parameters of the sphere-obstacle leaves, by record slot
@@ -294,6 +297,186 @@ static uint32_t prismatic_mask(const rmp2_robot& rb) {
   return m;
 }
 
+// Kernel tables of a tree from its robot and leaf descriptors (rmp2_tree_create; again whenever a leaf or the
+// merge option changes).  The tree's tables are only replaced when the whole compilation succeeds.
+static int compile_tables_into(rmp2_tree* tr);
+static int compile_tables(rmp2_tree* tr) {
+  const StepTables tab = tr->tab;
+  const SphereTables sph = tr->sph;
+  const std::vector<int> table_index = tr->table_index;
+  const int n_pair_sets = tr->n_pair_sets, n_goal_slots_used = tr->n_goal_slots_used, n_merged = tr->n_merged;
+  const int rc = compile_tables_into(tr);
+  if (rc != RMP2_OK) {
+    tr->tab = tab, tr->sph = sph, tr->table_index = table_index;
+    tr->n_pair_sets = n_pair_sets, tr->n_goal_slots_used = n_goal_slots_used, tr->n_merged = n_merged;
+  }
+  return rc;
+}
+
+static int compile_tables_into(rmp2_tree* tr) {
+  const rmp2_robot& rb = tr->robot;
+  const rmp2_leaf_desc* leaves = tr->leaves.data();
+  const int n_leaves = (int)tr->leaves.size();
+  memset(&tr->tab, 0, sizeof(StepTables));
+  StepTables& T = tr->tab;
+  T.n = rb.n;
+  T.rcond = (float)(10.0 * rb.n * 1.1920928955078125e-07);   // 10 * max(rows, cols) * eps(float32)
+  T.prismatic_mask = prismatic_mask(rb);
+  tr->table_index.assign(n_leaves, -1);
+
+  // Sphere-obstacle leaves that share their control point.  The distance map differentiates through the frame origin
+  // only (taskmap.py:124-128) and the sphere path takes the frame origin as pos_on_link, so two ObstacleAvoidance
+  // leaves with equal parameters whose frame origins coincide for every q -- frame k has a zero constant translation
+  // and a revolute or fixed joint, so its origin is its parent's (Panda: joint2 on joint1, joint6 on joint5) -- yield
+  // the same (M, f): same x, xd, c, and Jacobians that differ by a zero column.  One leaf of such a group (the one on
+  // the shallowest frame) runs the pair loop and the pullback; its sums carry the size of the group as a weight.
+  std::vector<int> rep(n_leaves), weight(n_leaves, 1);     // representative of leaf i (i itself when not merged)
+  for (int i = 0; i < n_leaves; ++i) rep[i] = i;
+  tr->n_merged = 0;
+  if (tr->merge_coincident) {
+    auto origin_root = [&](int k) {
+      while (rb.parent[k] >= 0 && rb.jtype[k] != RMP2_JOINT_PRISMATIC && rb.T_const[16 * k + 3] == 0.f &&
+             rb.T_const[16 * k + 7] == 0.f && rb.T_const[16 * k + 11] == 0.f)
+        k = rb.parent[k];
+      return k;
+    };
+    auto same_policy = [&](const rmp2_leaf_desc& a, const rmp2_leaf_desc& b) {
+      return a.type == b.type && memcmp(a.params, b.params, sizeof(a.params)) == 0;
+    };
+    for (int i = 0; i < n_leaves; ++i) {
+      if (leaves[i].space != RMP2_SPACE_FRAME_DISTANCE_SPHERES) continue;
+      for (int j = 0; j < i; ++j) {
+        if (leaves[j].space != RMP2_SPACE_FRAME_DISTANCE_SPHERES || rep[j] != j) continue;
+        if (origin_root(leaves[j].frame) != origin_root(leaves[i].frame) || !same_policy(leaves[i], leaves[j])) continue;
+        rep[i] = j;
+        break;
+      }
+    }
+    // the member on the shallowest frame (smallest index: parents precede children) represents its group
+    std::vector<int> group = rep;                            // first member in tree order
+    for (int j = 0; j < n_leaves; ++j) {
+      if (group[j] != j) continue;
+      int best = j, members = 0;
+      for (int i = j; i < n_leaves; ++i)
+        if (group[i] == j) {
+          ++members;
+          if (leaves[i].frame < leaves[best].frame) best = i;
+        }
+      if (members == 1) continue;
+      for (int i = j; i < n_leaves; ++i)
+        if (group[i] == j) rep[i] = best, weight[i] = 0;
+      weight[best] = members;
+      tr->n_merged += members - 1;
+    }
+  }
+
+  // frames that carry a leaf, and everything between them and the base
+  std::vector<char> needed(rb.F, 0);
+  for (int i = 0; i < n_leaves; ++i)
+    if (leaves[i].space != RMP2_SPACE_CONFIG && rep[i] == i)
+      for (int k = leaves[i].frame; k >= 0; k = rb.parent[k]) needed[k] = 1;
+  std::vector<std::vector<int>> children(rb.F + 1);          // index F = base
+  for (int k = 0; k < rb.F; ++k)
+    if (needed[k]) children[rb.parent[k] < 0 ? rb.F : rb.parent[k]].push_back(k);
+
+  // leaf bookkeeping shared by frame-attached and configuration-space leaves
+  int leaf_cursor = 0, pair_sets = 0, goal_slots = 0, vec_cursor = 0;
+  std::vector<int> pair_set_of(n_leaves, -1);
+  for (int i = 0; i < n_leaves; ++i) {
+    if (leaves[i].space == RMP2_SPACE_FRAME_DISTANCE_PAIRS || leaves[i].space == RMP2_SPACE_FRAME_POINTS)
+      pair_set_of[i] = pair_sets++;
+    if (leaves[i].goal_slot >= 0) goal_slots = std::max(goal_slots, leaves[i].goal_slot + 1);
+    if (leaves[i].space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) T.uses_spheres = 1;
+  }
+  memset(&tr->sph, 0, sizeof(SphereTables));
+  if (pair_sets > RMP2_MAX_PAIR_SETS) { return fail(RMP2_ERR_UNSUPPORTED, "too many explicit-pair leaves"); }
+  tr->n_pair_sets = pair_sets;
+  tr->n_goal_slots_used = goal_slots;
+  auto add_leaf = [&](int i) -> int {
+    LeafTab& L = T.leaves[leaf_cursor];
+    L.type = leaves[i].type;
+    L.space = leaves[i].space;
+    L.goal_slot = leaves[i].goal_slot;
+    L.pair_set = pair_set_of[i];
+    L.sphere_slot = -1;
+    float vec[3 * RMP2_MAX_JOINTS];
+    int vlen = 0;
+    int rc = derive_leaf_params(leaves[i], rb.n, L, vec, &vlen);
+    if (rc != RMP2_OK) return rc;
+    if (L.space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) {
+      L.sphere_slot = T.n_sphere_slots++;
+      fill_sphere_row(leaves[i], tr->sph.p[L.sphere_slot]);
+      tr->sph.p[L.sphere_slot][SP_WEIGHT] = (float)weight[i];
+    }
+    if (vec_cursor + vlen > RMP2_VECPOOL) return fail(RMP2_ERR_UNSUPPORTED, "vector-parameter pool exhausted");
+    L.vec_off = vec_cursor;
+    for (int j = 0; j < vlen; ++j) T.vecpool[vec_cursor + j] = vec[j];
+    vec_cursor += vlen;
+    tr->table_index[i] = leaf_cursor++;
+    return RMP2_OK;
+  };
+
+  // depth-first execution order.  A frame with several needed children saves its chain state in
+  // slot `depth` (stack discipline: its descendants only use deeper slots); the first child
+  // continues from the live state, later children reload the slot.
+  int n_slots = 0;
+  std::function<int(int, int, int)> visit = [&](int k, int restore, int depth) -> int {
+    if (T.n_frames >= RMP2_MAX_FRAMES) return fail(RMP2_ERR_UNSUPPORTED, "too many frames");
+    FrameTab& ft = T.frames[T.n_frames++];
+    fill_frame(rb, k, ft);
+    ft.anc_mask = ancestor_mask(rb, k);
+    ft.restore_slot = restore;
+    ft.leaf_begin = leaf_cursor;
+    for (int i = 0; i < n_leaves; ++i)
+      if (leaves[i].space != RMP2_SPACE_CONFIG && leaves[i].frame == k && rep[i] == i) {
+        int rc = add_leaf(i);
+        if (rc != RMP2_OK) return rc;
+      }
+    ft.leaf_end = leaf_cursor;
+    const std::vector<int>& ch = children[k];
+    if (ch.size() > 1) {
+      if (depth >= RMP2_MAX_SLOTS) return fail(RMP2_ERR_UNSUPPORTED, "kinematic tree branches too deeply");
+      ft.save_slot = depth;
+      n_slots = std::max(n_slots, depth + 1);
+      for (size_t ci = 0; ci < ch.size(); ++ci) {
+        int rc = visit(ch[ci], ci == 0 ? -1 : depth, depth + 1);
+        if (rc != RMP2_OK) return rc;
+      }
+    } else if (ch.size() == 1) {
+      return visit(ch[0], -1, depth);
+    }
+    return RMP2_OK;
+  };
+  for (int k : children[rb.F]) {
+    int rc = visit(k, RMP2_SLOT_BASE, 0);
+    if (rc != RMP2_OK) return rc;
+  }
+  T.n_slots = n_slots;
+  T.n_frame_leaves = leaf_cursor;
+  for (int i = 0; i < n_leaves; ++i)
+    if (leaves[i].space == RMP2_SPACE_CONFIG) {
+      int rc = add_leaf(i);
+      if (rc != RMP2_OK) return rc;
+    }
+  T.n_leaves = leaf_cursor;
+  for (int i = 0; i < n_leaves; ++i)
+    if (rep[i] != i) tr->table_index[i] = tr->table_index[rep[i]];
+  // leaves whose metric is a positive multiple of the identity keep M well conditioned
+  T.precondition = 1;
+  for (int i = 0; i < n_leaves; ++i) {
+    const int t = leaves[i].type;
+    if (t == RMP2_LEAF_CONFIG_BIASING || t == RMP2_LEAF_JOINT_DAMPING || t == RMP2_LEAF_CSPACE_BIASING) T.precondition = 0;
+  }
+  tr->sph.n_slots = T.n_sphere_slots;
+  if (T.n_sphere_slots > 0) {
+    // E environments per block: E * L threads <= 128, E <= 32 (box rows), shared memory bounded
+    int E = RMP2_SPHERES_BLOCK / T.n_sphere_slots;
+    E = std::max(1, std::min(E, 32));
+    tr->sph.envs_per_block = E;
+  }
+  return RMP2_OK;
+}
+
 extern "C" {
 
 const char* rmp2_last_error(void) { return g_last_error.c_str(); }
@@ -339,108 +522,8 @@ int rmp2_tree_create(const rmp2_robot* rb, const rmp2_leaf_desc* leaves, int32_t
     if (rc != RMP2_OK) return rc;
   }
   rmp2_tree* tr = new rmp2_tree;
-  memset(&tr->tab, 0, sizeof(StepTables));
-  StepTables& T = tr->tab;
-  T.n = rb->n;
-  T.rcond = (float)(10.0 * rb->n * 1.1920928955078125e-07);   // 10 * max(rows, cols) * eps(float32)
-  T.prismatic_mask = prismatic_mask(*rb);
+  tr->robot = *rb;
   tr->leaves.assign(leaves, leaves + n_leaves);
-  tr->table_index.assign(n_leaves, -1);
-
-  // frames that carry a leaf, and everything between them and the base
-  std::vector<char> needed(rb->F, 0);
-  for (int i = 0; i < n_leaves; ++i)
-    if (leaves[i].space != RMP2_SPACE_CONFIG)
-      for (int k = leaves[i].frame; k >= 0; k = rb->parent[k]) needed[k] = 1;
-  std::vector<std::vector<int>> children(rb->F + 1);          // index F = base
-  for (int k = 0; k < rb->F; ++k)
-    if (needed[k]) children[rb->parent[k] < 0 ? rb->F : rb->parent[k]].push_back(k);
-
-  // leaf bookkeeping shared by frame-attached and configuration-space leaves
-  int leaf_cursor = 0, pair_sets = 0, goal_slots = 0, vec_cursor = 0;
-  std::vector<int> pair_set_of(n_leaves, -1);
-  for (int i = 0; i < n_leaves; ++i) {
-    if (leaves[i].space == RMP2_SPACE_FRAME_DISTANCE_PAIRS || leaves[i].space == RMP2_SPACE_FRAME_POINTS)
-      pair_set_of[i] = pair_sets++;
-    if (leaves[i].goal_slot >= 0) goal_slots = std::max(goal_slots, leaves[i].goal_slot + 1);
-    if (leaves[i].space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) T.uses_spheres = 1;
-  }
-  memset(&tr->sph, 0, sizeof(SphereTables));
-  if (pair_sets > RMP2_MAX_PAIR_SETS) { delete tr; return fail(RMP2_ERR_UNSUPPORTED, "too many explicit-pair leaves"); }
-  tr->n_pair_sets = pair_sets;
-  tr->n_goal_slots_used = goal_slots;
-  auto add_leaf = [&](int i) -> int {
-    LeafTab& L = T.leaves[leaf_cursor];
-    L.type = leaves[i].type;
-    L.space = leaves[i].space;
-    L.goal_slot = leaves[i].goal_slot;
-    L.pair_set = pair_set_of[i];
-    L.sphere_slot = -1;
-    float vec[3 * RMP2_MAX_JOINTS];
-    int vlen = 0;
-    int rc = derive_leaf_params(leaves[i], rb->n, L, vec, &vlen);
-    if (rc != RMP2_OK) return rc;
-    if (L.space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) {
-      L.sphere_slot = T.n_sphere_slots++;
-      fill_sphere_row(leaves[i], tr->sph.p[L.sphere_slot]);
-    }
-    if (vec_cursor + vlen > RMP2_VECPOOL) return fail(RMP2_ERR_UNSUPPORTED, "vector-parameter pool exhausted");
-    L.vec_off = vec_cursor;
-    for (int j = 0; j < vlen; ++j) T.vecpool[vec_cursor + j] = vec[j];
-    vec_cursor += vlen;
-    tr->table_index[i] = leaf_cursor++;
-    return RMP2_OK;
-  };
-
-  // depth-first execution order.  A frame with several needed children saves its chain state in
-  // slot `depth` (stack discipline: its descendants only use deeper slots); the first child
-  // continues from the live state, later children reload the slot.
-  int n_slots = 0;
-  std::function<int(int, int, int)> visit = [&](int k, int restore, int depth) -> int {
-    if (T.n_frames >= RMP2_MAX_FRAMES) return fail(RMP2_ERR_UNSUPPORTED, "too many frames");
-    FrameTab& ft = T.frames[T.n_frames++];
-    fill_frame(*rb, k, ft);
-    ft.anc_mask = ancestor_mask(*rb, k);
-    ft.restore_slot = restore;
-    ft.leaf_begin = leaf_cursor;
-    for (int i = 0; i < n_leaves; ++i)
-      if (leaves[i].space != RMP2_SPACE_CONFIG && leaves[i].frame == k) {
-        int rc = add_leaf(i);
-        if (rc != RMP2_OK) return rc;
-      }
-    ft.leaf_end = leaf_cursor;
-    const std::vector<int>& ch = children[k];
-    if (ch.size() > 1) {
-      if (depth >= RMP2_MAX_SLOTS) return fail(RMP2_ERR_UNSUPPORTED, "kinematic tree branches too deeply");
-      ft.save_slot = depth;
-      n_slots = std::max(n_slots, depth + 1);
-      for (size_t ci = 0; ci < ch.size(); ++ci) {
-        int rc = visit(ch[ci], ci == 0 ? -1 : depth, depth + 1);
-        if (rc != RMP2_OK) return rc;
-      }
-    } else if (ch.size() == 1) {
-      return visit(ch[0], -1, depth);
-    }
-    return RMP2_OK;
-  };
-  for (int k : children[rb->F]) {
-    int rc = visit(k, RMP2_SLOT_BASE, 0);
-    if (rc != RMP2_OK) { delete tr; return rc; }
-  }
-  T.n_slots = n_slots;
-  T.n_frame_leaves = leaf_cursor;
-  for (int i = 0; i < n_leaves; ++i)
-    if (leaves[i].space == RMP2_SPACE_CONFIG) {
-      int rc = add_leaf(i);
-      if (rc != RMP2_OK) { delete tr; return rc; }
-    }
-  T.n_leaves = leaf_cursor;
-  // leaves whose metric is a positive multiple of the identity keep M well conditioned
-  T.precondition = 1;
-  for (int i = 0; i < n_leaves; ++i) {
-    const int t = leaves[i].type;
-    if (t == RMP2_LEAF_CONFIG_BIASING || t == RMP2_LEAF_JOINT_DAMPING || t == RMP2_LEAF_CSPACE_BIASING) T.precondition = 0;
-  }
   // tuning hooks, read once per tree (never on the step path); rmp2_tree_set_option overrides them
   if (getenv("RMP2_DISABLE_TMA")) tr->use_tma = false;
   if (const char* v = getenv("RMP2_SPLIT_RESOLVE")) tr->split_resolve = (v[0] == '1') ? 1 : 0;
@@ -453,13 +536,9 @@ int rmp2_tree_create(const rmp2_robot* rb, const rmp2_leaf_desc* leaves, int32_t
     const int b = atoi(v);
     if (b == 128 || b == 256) tr->spec_step_block = b;
   }
-  tr->sph.n_slots = T.n_sphere_slots;
-  if (T.n_sphere_slots > 0) {
-    // E environments per block: E * L threads <= 128, E <= 32 (box rows), shared memory bounded
-    int E = RMP2_SPHERES_BLOCK / T.n_sphere_slots;
-    E = std::max(1, std::min(E, 32));
-    tr->sph.envs_per_block = E;
-  }
+  if (const char* v = getenv("RMP2_MERGE_COINCIDENT")) tr->merge_coincident = (v[0] != '0');
+  int rc = compile_tables(tr);
+  if (rc != RMP2_OK) { delete tr; return rc; }
   *out = tr;
   return RMP2_OK;
 }
@@ -507,15 +586,15 @@ int rmp2_tree_update_leaf(rmp2_tree* tree, int32_t index, const rmp2_leaf_desc* 
   const rmp2_leaf_desc& old = tree->leaves[index];
   if (old.type != leaf->type || old.space != leaf->space || old.frame != leaf->frame || old.goal_slot != leaf->goal_slot)
     return fail(RMP2_ERR_INVALID, "update_leaf may change params/vec only; rebuild the tree to change its structure");
-  LeafTab& L = tree->tab.leaves[tree->table_index[index]];
-  float vec[3 * RMP2_MAX_JOINTS];
-  int vlen = 0;
-  int rc = derive_leaf_params(*leaf, tree->tab.n, L, vec, &vlen);
-  if (rc != RMP2_OK) return rc;
-  for (int j = 0; j < vlen; ++j) tree->tab.vecpool[L.vec_off + j] = vec[j];
-  if (L.sphere_slot >= 0)
-    fill_sphere_row(*leaf, tree->sph.p[L.sphere_slot]);
+  // the tables are recompiled as a whole (host work of microseconds): a changed obstacle leaf may leave or join a group
+  // of merged leaves.  On failure the tree keeps its previous tables and descriptor.
+  const rmp2_leaf_desc previous = old;
   tree->leaves[index] = *leaf;
+  const int rc = compile_tables(tree);
+  if (rc != RMP2_OK) {
+    tree->leaves[index] = previous;
+    return rc;
+  }
   if (tree->spec) {
     // The tables are compile-time constants of the specialised kernels: rebuild them for the new values (NVRTC,
     // tens of milliseconds once the compiler library is loaded), so that the reference idiom
@@ -964,7 +1043,11 @@ int rmp2_obstacle_feed(const rmp2_robot* rb, const int32_t* frames, const float*
   }
   rmp2_tree* tmp = nullptr;
   int rc = rmp2_tree_create(rb, marks.data(), n_frames, &tmp);
-  if (rc != RMP2_OK) return rc;
+  if (rc == RMP2_OK) rc = rmp2_tree_set_option(tmp, RMP2_OPT_MERGE_COINCIDENT, 0);   // every listed frame keeps its own rows
+  if (rc != RMP2_OK) {
+    rmp2_tree_destroy(tmp);
+    return rc;
+  }
   for (int i = 0; i < n_frames; ++i) tmp->tab.leaves[tmp->table_index[i]].pair_set = i;
   FeedArgs A;
   A.B = B;
@@ -1067,9 +1150,35 @@ int rmp2_tree_set_option(rmp2_tree* tree, int32_t option, int32_t value) {
       if (value < 0) return fail(RMP2_ERR_INVALID, "RMP2_OPT_CHUNK_ENVS must be >= 0");
       tree->chunk_envs = value;
       return RMP2_OK;
+    case RMP2_OPT_MERGE_COINCIDENT: {
+      const bool on = value != 0;
+      if (on == tree->merge_coincident) return RMP2_OK;
+      tree->merge_coincident = on;
+      const int rc = compile_tables(tree);
+      if (rc != RMP2_OK) {
+        tree->merge_coincident = !on;
+        return rc;
+      }
+      if (tree->spec) {                       // the tables are compile-time constants of the specialised kernels
+        SpecModule* m = nullptr;
+        std::string err;
+        const int jrc = rmp2_jit_build(tree->tab, rmp2_pick_width(tree->tab.n), false, &m, err);
+        cudaDeviceSynchronize();              // steps queued with the old module finish before it is unloaded
+        rmp2_jit_destroy(tree->spec);
+        tree->spec = (jrc == 0) ? m : nullptr;
+      }
+      return RMP2_OK;
+    }
     default:
       return fail(RMP2_ERR_INVALID, "unknown option " + std::to_string(option));
   }
+}
+
+int rmp2_tree_obstacle_slots(const rmp2_tree* tree, int32_t* n_leaves, int32_t* n_slots) {
+  if (!tree) return fail(RMP2_ERR_INVALID, "null argument");
+  if (n_leaves) *n_leaves = tree->tab.n_sphere_slots + tree->n_merged;
+  if (n_slots) *n_slots = tree->tab.n_sphere_slots;
+  return RMP2_OK;
 }
 
 int rmp2_tree_profile(rmp2_tree* tree, int32_t enable) {

@@ -397,10 +397,13 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
   // sum_o m (n.a) n = S a, once here.
   if (!kSkip) a[0] = rec[6 * fstride], a[1] = rec[7 * fstride], a[2] = rec[8 * fstride];
   const float a0 = a[0], a1 = a[1], a2 = a[2];
+  // SP_WEIGHT: this leaf stands for a group of obstacle leaves that share its control point (rmp2_tree_create); the
+  // group's sums are the weight times its own (1 for an ordinary leaf: the products below are exact)
+  const float wgt = ST.p[slot][SP_WEIGHT];
   float Ss[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) Ss[i] = S[i].x + S[i].y;
-  const float ik2 = p[SP_INV_K2];
+  for (int i = 0; i < 6; ++i) Ss[i] = (S[i].x + S[i].y) * wgt;
+  const float ik2 = p[SP_INV_K2] * wgt;
   const float g0 = fmaf(g[0].x + g[0].y, ik2, -fmaf(Ss[0], a0, fmaf(Ss[1], a1, Ss[2] * a2)));
   const float g1 = fmaf(g[1].x + g[1].y, ik2, -fmaf(Ss[1], a0, fmaf(Ss[3], a1, Ss[4] * a2)));
   const float g2 = fmaf(g[2].x + g[2].y, ik2, -fmaf(Ss[2], a0, fmaf(Ss[4], a1, Ss[5] * a2)));

@@ -275,7 +275,8 @@ RMP2_DEV void obstacle_pair(const float* __restrict__ p, float nx, float ny, flo
 #define SP_RGAIN 10       // repulsion_gain * k^2
 #define SP_REACH 11       // (r + margin) * (1 + 1e-5): conservative bound of the early-out test
 #define SP_INV_K2 12      // 1 / k^2
-#define SP_COUNT 13
+#define SP_COUNT 13        // parameters the pair loop keeps in registers
+#define SP_WEIGHT 13       // number of obstacle leaves this row stands for (coincident control points merged), read once at the end
 
 RMP2_DEV float2 bc2(float s) { return make_float2(s, s); }
 RMP2_DEV float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }

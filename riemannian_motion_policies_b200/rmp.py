@@ -320,6 +320,17 @@ class CompiledTree:
         """Skip (frame, sphere) pairs beyond the metric radius in the obstacle kernel (exact; default on)."""
         _native.check(_native.lib().rmp2_tree_set_option(self.handle, _native.OPT_EARLY_OUT, 1 if enable else 0))
 
+    def set_merge_coincident(self, enable=True):
+        """Run one pair loop for obstacle leaves that share their control point (equal parameters, frame origins that
+        coincide for every q; exact up to rounding; default on).  Off: every leaf on its own."""
+        _native.check(_native.lib().rmp2_tree_set_option(self.handle, _native.OPT_MERGE_COINCIDENT, 1 if enable else 0))
+
+    def obstacle_slots(self):
+        """-> (sphere-path obstacle leaves of the tree, pair loops that run for them per environment)."""
+        leaves, slots = ctypes.c_int32(), ctypes.c_int32()
+        _native.check(_native.lib().rmp2_tree_obstacle_slots(self.handle, ctypes.byref(leaves), ctypes.byref(slots)))
+        return leaves.value, slots.value
+
     def profile(self, enable=True):
         """Bracket every kernel launch of this tree with CUDA events (see ``profile_read``)."""
         _native.check(_native.lib().rmp2_tree_profile(self.handle, 1 if enable else 0))

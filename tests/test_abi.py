@@ -182,6 +182,32 @@ def test_step_argument_checks_need_no_gpu(native_lib):
     assert b"16-byte aligned" in native_lib.rmp2_last_error()
 
 
+def test_coincident_obstacle_leaves_are_merged(native_lib):
+    """RMP2_OPT_MERGE_COINCIDENT: obstacle leaves with equal parameters on frames whose origins coincide for every q run
+    one pair loop (Panda: joint2 sits on joint1, joint6 on joint5; the finger joints are prismatic and stay).  A leaf
+    whose parameters differ leaves its group; switching the option off gives every leaf its own loop again."""
+    ns = S.product_namespace()
+    dist = lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance()
+    fk7 = ns.UrdfForwardKinematic(S.PANDA_WO_TOOL_URDF, S.PANDA_ORDER_7)
+    core = S.build_config4(ns, fk7, [0.5, 0.0, 0.5], 7, dist)
+    tree = core.compile(7)
+    assert tree.obstacle_slots() == (8, 6)
+    assert tree.specialize(compile_only=True) is None           # the merged tables still compile under NVRTC
+    tree.set_merge_coincident(False)
+    assert tree.obstacle_slots() == (8, 8)
+    tree.set_merge_coincident(True)
+    assert tree.obstacle_slots() == (8, 6)
+    # the reference idiom `leaf.attr = value`, picked up at the next step: joint2's leaf leaves joint1's group
+    core.rmps["collision_avoidance_for_panda_joint2"].repulsion_gain = 700.
+    tree = core.compile(7)
+    assert tree.obstacle_slots() == (8, 7)
+    core.rmps["collision_avoidance_for_panda_joint2"].repulsion_gain = 800.
+    assert core.compile(7).obstacle_slots() == (8, 6)
+    fk9 = ns.UrdfForwardKinematic(S.PANDA_URDF, S.PANDA_ORDER_9)
+    assert S.build_config4(ns, fk9, [0.5, 0.0, 0.5], 9, dist).compile(9).obstacle_slots() == (10, 8)
+    assert native_lib.rmp2_tree_obstacle_slots(None, None, None) == 1
+
+
 def test_oracle_sensitivity_yardstick():
     """oracle/harness.config_sensitivity: deterministic per environment (independent of the batch around it), at the
     eps32 scale for a well-conditioned tree, and kappa * eps32 for a nearly singular metric."""
