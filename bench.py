@@ -762,7 +762,10 @@ def run_b200_arm(args):
                        "kernels": "frames/step rebuilt for this tree by NVRTC (rmp2_tree_specialize)" if specialized["on"]
                                   else "generic table-driven frames/step kernels",
                        "l2_policy": f"inputs larger than L2: {n_buffers} rotating sphere buffers of "
-                                    f"{B * O_ * 16 / 1e6:.0f} MB each" if O_ else "q/qd/goal re-read each step"},
+                                    f"{B * O_ * 16 / 1e6:.0f} MB each" if O_ else "q/qd/goal re-read each step",
+                       "pairs": "every (obstacle leaf, sphere) pair through the full arithmetic: RMP2_OPT_EARLY_OUT and "
+                                "RMP2_OPT_MERGE_COINCIDENT off for value / roofline / e2e; the library defaults are "
+                                "timed under early_out and library_default" if O_ else "no obstacle leaves"},
             "roofline": {"bound": "hbm", "kernel": f"rmp2_{dom}_kernel", "achieved": dom_gbs, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": dom_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_kind,

@@ -28,6 +28,17 @@ class RiemannianMotionPolicy:
         self.name = name
         self.taskmap = taskmap
 
+    def __setattr__(self, key, value):
+        # Every attribute assignment (the reference idiom ``leaf.goal = ...``, ``leaf.repulsion_gain = ...``) bumps a
+        # version counter; a compiled tree re-derives a leaf's kernel parameters only when it moved (or when the leaf
+        # holds vector parameters, which may also be mutated in place).
+        object.__setattr__(self, key, value)
+        object.__setattr__(self, "_version", self.__dict__.get("_version", 0) + 1)
+
+    @classmethod
+    def _has_vector_parameters(cls):
+        return cls._vec is not RiemannianMotionPolicy._vec
+
     # -- description handed to the C ABI --------------------------------------------------------
     def _params(self):
         """Constructor arguments in the order documented in include/rmp2_b200.h."""

@@ -13,7 +13,7 @@ import torch
 
 from . import _native
 from ._leaf import RiemannianMotionPolicy, as_float_list
-from ._tensor import current_stream_ptr, is_device_tensor, require_cuda, to_device, unwrap
+from ._tensor import current_stream_ptr, is_device_tensor, require_cuda, stage_host_inputs, to_device, unwrap
 from .taskmap import (IdentityTaskmap, TaskmapByForwardKinematic, TaskmapByFunction, TaskmapFrom4x4ToEuler,
                       TaskmapFrom4x4ToPosition, TaskmapJointFrame4x4ToDistance, TaskmapJointFrame4x4ToSphereDistance,
                       TaskmapRelative4x4)
@@ -197,17 +197,38 @@ class CompiledTree:
             return torch.cat([rel, data, torch.zeros(rel.shape[0], 1)], dim=1)
         return rows
 
+    def _make_desc(self, i):
+        leaf, space, frame, goal_slot, _ = self.entries[i]
+        return leaf.leaf_desc(self.n if space == _native.SPACE_CONFIG else 3, space, frame, goal_slot)
+
     def _make_descs(self):
-        return [leaf.leaf_desc(self.n if space == _native.SPACE_CONFIG else 3, space, frame, goal_slot)
-                for leaf, space, frame, goal_slot, _ in self.entries]
+        # (version read BEFORE the parameters: a concurrent assignment is then picked up by the next refresh)
+        self._versions = [e[0].__dict__.get("_version", 0) for e in self.entries]
+        self._vecs = {}                  # vector parameters as last seen by refresh (leaf index -> list of floats)
+        return [self._make_desc(i) for i in range(len(self.entries))]
 
     def signature(self):
         return tuple((type(e[0]).__name__, e[1], e[2], e[3]) for e in self.entries)
 
     def refresh(self):
         """Push parameters the caller changed since the last step (e.g. ``target_rmp.goal = ...``,
-        reference: experiments/franka_panda/06_cluttered_environment.py:142)."""
-        for i, d in enumerate(self._make_descs()):
+        reference: experiments/franka_panda/06_cluttered_environment.py:142).  A leaf is looked at again when one of
+        its attributes was assigned since (``_version``) or when it holds a vector parameter that is not fed per
+        environment (goal / q0 / limits: arrays can be changed in place)."""
+        for i, e in enumerate(self.entries):
+            leaf = e[0]
+            version = leaf.__dict__.get("_version", 0)
+            if version == self._versions[i]:
+                if e[3] >= 0 or not leaf._has_vector_parameters():
+                    continue
+                vec = leaf._vec(self.n if e[1] == _native.SPACE_CONFIG else 3)
+                if vec == self._vecs.get(i):
+                    continue
+                self._vecs[i] = vec
+            else:
+                self._vecs.pop(i, None)
+            d = self._make_desc(i)
+            self._versions[i] = version
             if bytes(d) != bytes(self.descs[i]):
                 _native.check(_native.lib().rmp2_tree_update_leaf(self.handle, i, d))
                 self.descs[i] = d
@@ -393,6 +414,9 @@ class RmpCore:
         dev = require_cuda()
         q_in = unwrap(q)
         single = (np.ndim(q_in) == 1) if not isinstance(q_in, torch.Tensor) else (q_in.dim() == 1)
+        if not isinstance(goals, dict) and not any(is_device_tensor(unwrap(a)) for a in (q, qd, goals, spheres)):
+            # all inputs live on the host (the reference's call): one staging copy for all of them
+            q, qd, goals, spheres = stage_host_inputs((q, qd, goals, spheres), dev)
         qt = to_device(q, dev)
         qdt = to_device(qd, dev)
         qt = qt.reshape(1, -1) if single else qt

@@ -208,6 +208,36 @@ def test_coincident_obstacle_leaves_are_merged(native_lib):
     assert native_lib.rmp2_tree_obstacle_slots(None, None, None) == 1
 
 
+def test_refresh_picks_up_leaf_changes(native_lib):
+    """The reference's callers change leaf parameters by assignment (``target_rmp.goal = ...``,
+    06_cluttered_environment.py:142) or mutate a goal array in place; a compiled tree re-derives exactly the leaves that
+    moved (attribute version counter; vector parameters compared by value) and pushes them with rmp2_tree_update_leaf."""
+    ns = S.product_namespace()
+    fk = ns.UrdfForwardKinematic(S.PANDA_WO_TOOL_URDF, S.PANDA_ORDER_7)
+    core = S.build_config4(ns, fk, [0.5, 0.0, 0.5], 7, lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance())
+    tree = core.compile(7)
+    names = list(core.rmps)
+    before = [bytes(d) for d in tree.descs]
+    assert core.compile(7) is tree and [bytes(d) for d in tree.descs] == before        # nothing changed
+    goal = np.array([0.5, 0.0, 0.5])
+    core.rmps["attractor"].goal = goal                                                 # same values: no update
+    core.compile(7)
+    assert [bytes(d) for d in tree.descs] == before
+    goal[1] = 0.25                                                                     # in place
+    core.compile(7)
+    i = names.index("attractor")
+    assert list(tree.descs[i].vec[:3]) == [0.5, 0.25, 0.5]
+    core.rmps["joint_limit_avoidance"].gamma_p = 0.4                                   # scalar by assignment
+    core.compile(7)
+    j = names.index("joint_limit_avoidance")
+    assert abs(tree.descs[j].params[0] - 0.4) < 1e-7
+    changed = [k for k, d in enumerate(tree.descs) if bytes(d) != before[k]]
+    assert sorted(changed) == sorted([i, j])
+    core.rmps["attractor"].goal = [0.5, 0.0]                                           # wrong length is refused
+    with pytest.raises(ValueError):
+        core.compile(7)
+
+
 def test_oracle_sensitivity_yardstick():
     """oracle/harness.config_sensitivity: deterministic per environment (independent of the batch around it), at the
     eps32 scale for a well-conditioned tree, and kappa * eps32 for a nearly singular metric."""
