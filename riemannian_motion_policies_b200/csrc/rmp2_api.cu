@@ -473,6 +473,7 @@ static int compile_tables_into(rmp2_tree* tr) {
     int E = RMP2_SPHERES_BLOCK / T.n_sphere_slots;
     E = std::max(1, std::min(E, 32));
     tr->sph.envs_per_block = E;
+    tr->sph.div_magic = 65536 / E + 1;
   }
   return RMP2_OK;
 }
@@ -623,7 +624,7 @@ int pick_block(const rmp2_tree* tree, long long B) {
 bool tma_eligible(const rmp2_tree* tree, const StepArgs& A) {
   const int O = A.n_spheres;
   if (!tree->use_tma || O <= 0 || A.spheres == nullptr) return false;
-  return rmp2_spheres_smem(tree->sph, O, true) <= 96 * 1024;
+  return rmp2_spheres_smem(tree->sph, O, true, true) <= 96 * 1024;
 }
 
 struct ScopedClock {               // brackets one launch with events when profiling is on
@@ -1109,9 +1110,9 @@ int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_sphere
   bool use_tma = false;
   if (which == 1) {
     if (tree->tab.n_sphere_slots == 0) return fail(RMP2_ERR_INVALID, "tree has no sphere-obstacle leaves");
-    use_tma = n_spheres > 0 && rmp2_spheres_smem(tree->sph, n_spheres, true) <= 96 * 1024;
+    use_tma = n_spheres > 0 && rmp2_spheres_smem(tree->sph, n_spheres, true, true) <= 96 * 1024;
     block = ((tree->sph.envs_per_block * tree->sph.n_slots + 31) / 32) * 32;
-    smem = rmp2_spheres_smem(tree->sph, n_spheres, use_tma);
+    smem = rmp2_spheres_smem(tree->sph, n_spheres, use_tma, tree->early_out);
   }
   int r = 0, bps = 0;
   cudaError_t e = rmp2_kernel_attributes(tree->tab.n, which, use_tma, block, smem, &r, &bps);

@@ -116,6 +116,13 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 #define RMP2_SPHERES_STEPS_PER_TRIP 4 // packed (two-sphere) steps per loop trip
 #endif
 
+// Shared-memory pitch of one staged sphere row.  16 O + 16: an odd number of 16-byte units spreads the LDS.128 of 8
+// consecutive lanes over all bank groups, and the unit behind the row holds the far-away sphere.  The sorted early-out
+// (O <= 64) uses 67 units whatever O is: its sentinel spheres sit at the fixed slots 64 and 65.
+__host__ __device__ inline uint32_t rmp2_spheres_pitch(int O, bool skip_variant) {
+  return (skip_variant && RMP2_SKIP_SORT && O <= 64) ? 67u * 16u : (uint32_t)O * 16u + 16u;
+}
+
 RMP2_DEV void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -153,7 +160,8 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
     for (int i = t; i < 33; i += blockDim.x) hist[i] = 0;
     if (!kTma) __syncthreads();
   }
-  int slot = t / E, e_local = t - slot * E;         // consecutive lanes = consecutive environments
+  int slot = (t * ST.div_magic) >> 16;              // = t / E without the integer-division sequence
+  int e_local = t - slot * E;                       // consecutive lanes = consecutive environments
   const long long env0 = (long long)blockIdx.x * E;
   long long env = env0 + e_local;
   const int O = A.n_spheres;
@@ -163,7 +171,9 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
   uint32_t row = 0;                                 // shared-memory address of this thread's sphere row
   uint32_t tile = 0;                                // ... of the tile's first row
   uint64_t* bar = nullptr;
-  const uint32_t pitch = (uint32_t)O * 16u + 16u;
+  // row pitch in shared memory (rmp2_spheres_pitch, shared with the host): 16 O + 16, or 67 x 16 bytes for the sorted
+  // early-out, whose exhausted lists read the two sentinel slots behind sphere 63 (see masked_pairs_rev)
+  const uint32_t pitch = rmp2_spheres_pitch(O, kSkip);
   const long long rows = (A.B - env0 < E) ? (A.B - env0) : E;
   if (kTma) {
     const uint32_t row_bytes = (uint32_t)O * 16u;
@@ -181,8 +191,14 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
     row = tile + (uint32_t)e_local * pitch;
     // the 16 pad bytes behind every row hold a sphere that contributes exactly zero (beyond every metric radius;
     // 1e15 m away keeps all terms finite): index O of a row, what an exhausted list of the early-out loop yields
-    if (kSkip && slot == 0 && e_local < E)
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %2, %2};" ::"r"(row + (uint32_t)O * 16u), "f"(1e15f), "f"(0.f) : "memory");
+    if (kSkip && slot == 0 && e_local < E) {
+      if (sorted) {     // slots 64 and 65: where index 62 + parity - 2 pos lands for pos = -1 (masked_pairs_rev)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %2, %2};" ::"r"(row + 64u * 16u), "f"(1e15f), "f"(0.f) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %2, %2};" ::"r"(row + 65u * 16u), "f"(1e15f), "f"(0.f) : "memory");
+      } else {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %2, %2};" ::"r"(row + (uint32_t)O * 16u), "f"(1e15f), "f"(0.f) : "memory");
+      }
+    }
   }
   if (!sorted && !active) return;                   // (the sorted variant keeps every thread for its barriers)
 
@@ -285,7 +301,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
     // w = |r|^2 - (reach + radius)^2, and one funnel shift that pushes the SIGN of w into the mask: 9 instructions
     // where the generic loop needs 15.  (w = +0 exactly on the boundary counts as outside: the reach carries a
     // 1e-5 relative margin, and a pair wrongly kept would contribute exactly zero anyway.)
-    auto reach_masks_64 = [&](uint32_t& mask_even, uint32_t& mask_odd) {
+    auto reach_masks_64 = [&](uint32_t& mask_even, uint32_t& mask_odd, bool reversed) {
       const float2 pxy = make_float2(px, py), pzr = make_float2(pz, p[SP_REACH]);
       const float2 mm = make_float2(-1.f, -1.f), mp = make_float2(-1.f, 1.f);
       uint32_t acc_even = 0u, acc_odd = 0u;                          // bit 31 - k <-> sphere pair k, reversed at the end
@@ -314,8 +330,8 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
           acc_odd <<= 4;
         }
       }
-      mask_even = __brev(acc_even);
-      mask_odd = __brev(acc_odd);
+      mask_even = reversed ? acc_even : __brev(acc_even);
+      mask_odd = reversed ? acc_odd : __brev(acc_odd);
     };
     // phase 3: the pairs of the set bits, an even with an odd sphere per packed step; an exhausted list yields the
     // far-away sphere (staged rows: the pad slot, index O -- one select on the index instead of four on the data)
@@ -340,6 +356,22 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
 #endif
       }
     };
+    // The same on staged rows with the masks in REVERSED bit order (bit 31 - k <-> sphere pair k, the order the reach
+    // test's funnel shifts produce): the leading one (one FLO) is the next pair in increasing sphere order, the
+    // sphere's address is base - 32 pos, and an exhausted list (pos = -1) lands on the sentinel slots 64 / 65 of the
+    // row by itself -- 5 instructions per list and step (FLO, IMAD, LDS, SHF, LOP3) where the forward order needs 9
+    // (BREV, FLO, ISETP, 2 k (+1), SEL, LEA, LDS, mask & (mask - 1)).
+    auto masked_pairs_rev = [&](uint32_t rev_even, uint32_t rev_odd) {
+      const uint32_t base_even = row + 62u * 16u, base_odd = row + 63u * 16u;
+      while (rev_even | rev_odd) {
+        uint32_t pe, po;                                   // bfind = FLO: position of the leading one, 0xffffffff for 0
+        asm("bfind.u32 %0, %1;" : "=r"(pe) : "r"(rev_even));
+        asm("bfind.u32 %0, %1;" : "=r"(po) : "r"(rev_odd));
+        rev_even &= ~(1u << (pe & 31u));
+        rev_odd &= ~(1u << (po & 31u));
+        two_spheres(lds128(base_even - 32u * pe), lds128(base_odd - 32u * po));
+      }
+    };
     if (!sorted) {
       scale_velocity();
       for (int o0 = 0; o0 < O; o0 += 64) {
@@ -349,7 +381,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       }
     } else {
       uint32_t me = 0u, mo = 0u;
-      if (active) reach_masks_64(me, mo);
+      if (active) reach_masks_64(me, mo, kTma);
       const int steps = max(__popc(me), __popc(mo));            // 0 .. 32
       const int rank = atomicAdd(&hist[steps], 1);
       __syncthreads();
@@ -382,7 +414,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       const int home = r.thread;
       active = home >= 0;
       if (!active) return;                                        // no barrier below this line
-      slot = home / E, e_local = home - slot * E;
+      slot = (home * ST.div_magic) >> 16, e_local = home - slot * E;
       env = env0 + e_local;
       rec = A.rec + (size_t)slot * A.B + env;
       gs = reinterpret_cast<const float4*>(A.spheres) + (size_t)env * O;
@@ -390,7 +422,8 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
 #pragma unroll
       for (int i = 0; i < SP_COUNT; ++i) p[i] = ST.p[slot][i];
       scale_velocity();
-      masked_pairs(0, me, mo);
+      if (kTma) masked_pairs_rev(me, mo);
+      else masked_pairs(0, me, mo);
     }
   }
   // The pair loop left the n.a part of the curvature term out of g and accumulated k^2 g (obstacle_pair2):
@@ -875,9 +908,9 @@ cudaError_t rmp2_launch_frames(const StepTables& T, const StepArgs& A, int block
   return cudaGetLastError();
 }
 
-size_t rmp2_spheres_smem(const SphereTables& ST, int n_spheres, bool use_tma) {
+size_t rmp2_spheres_smem(const SphereTables& ST, int n_spheres, bool use_tma, bool early_out) {
   if (!use_tma) return 0;
-  const size_t pitch = (size_t)n_spheres * 16 + 16;
+  const size_t pitch = rmp2_spheres_pitch(n_spheres, early_out && n_spheres >= RMP2_SKIP_MIN_SPHERES);
   return 128 + (size_t)ST.envs_per_block * pitch + sizeof(uint64_t);
 }
 
@@ -886,7 +919,7 @@ cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, bool 
   if (blocks <= 0) return cudaSuccess;
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
   const int threads = ((ST.envs_per_block * ST.n_slots + 31) / 32) * 32;
-  const size_t smem = rmp2_spheres_smem(ST, A.n_spheres, use_tma);
+  const size_t smem = rmp2_spheres_smem(ST, A.n_spheres, use_tma, A.early_out != 0);
   const unsigned nb = (unsigned)blocks;
   // the early-out variant pays a reach test per pair and a re-deal of the block's work: below ~32 spheres per
   // environment that costs more than the skipped pairs save (measured, config 3 with 16 spheres: 0.8x), so short

@@ -21,7 +21,7 @@ int rmp2_pick_width(int n);
 size_t rmp2_step_smem(const StepTables& T, int block);
 
 cudaError_t rmp2_launch_frames(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);
-size_t rmp2_spheres_smem(const SphereTables& ST, int n_spheres, bool use_tma);
+size_t rmp2_spheres_smem(const SphereTables& ST, int n_spheres, bool use_tma, bool early_out);
 cudaError_t rmp2_launch_spheres(const SphereTables& ST, const StepArgs& A, bool use_tma, cudaStream_t stream);
 cudaError_t rmp2_launch_step(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);
 cudaError_t rmp2_launch_resolve(const StepTables& T, const StepArgs& A, int block, cudaStream_t stream);

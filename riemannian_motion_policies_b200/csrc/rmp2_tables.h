@@ -60,6 +60,7 @@ struct StepTables {
 struct SphereTables {
   int32_t n_slots;              // L
   int32_t envs_per_block;       // E: environments per thread block (E * L <= 128)
+  int32_t div_magic;            // 65536 / E + 1: t / E == (t * div_magic) >> 16 for every thread index t < 512
   float p[RMP2_MAX_LEAVES][RMP2_LEAF_PARAMS];
 };
 
