@@ -733,8 +733,10 @@ int launch_chunk(rmp2_tree* tree, const StepArgs& A, cudaStream_t stream) {
       int sb = block;
       if (block == 128 && A.B >= 148LL * 2 * 256 * 2 && rmp2_pick_width(T.n) <= 7)
         sb = tree->spec_step_block ? tree->spec_step_block : 256;
-      e = rmp2_jit_launch(tree->spec, A.split ? 2 : 1, A, (unsigned)((A.B + sb - 1) / sb), sb,
-                          rmp2_step_smem(T, sb), stream, jit_err);
+      // which: 1 fused / 2 split at the launch's block size; 3 = the fused instance compiled for exactly
+      // RMP2_SPEC_STEP_THREADS threads (shared-memory offsets as immediates)
+      const int which = A.split ? 2 : ((sb == rmp2_jit_big_block(tree->spec, rmp2_pick_width(T.n))) ? 3 : 1);
+      e = rmp2_jit_launch(tree->spec, which, A, (unsigned)((A.B + sb - 1) / sb), sb, rmp2_step_smem(T, sb), stream, jit_err);
     } else
       e = rmp2_launch_step(T, A, block, stream);
   }
@@ -775,7 +777,8 @@ size_t fb_ints_for(long long B) { return (size_t)B + 4; }
 
 size_t rec_floats_for(const rmp2_tree* tree, long long B, int n_spheres) {
   if (tree->tab.n_sphere_slots == 0 || n_spheres <= 0) return 0;
-  return (size_t)B * tree->tab.n_sphere_slots * RMP2_REC_FLOATS;
+  const size_t tiles = (size_t)((B + RMP2_REC_TILE - 1) / RMP2_REC_TILE);        // tiled over environments: rmp2_rec_base
+  return tiles * RMP2_REC_TILE * tree->tab.n_sphere_slots * RMP2_REC_FLOATS;
 }
 
 // Size the tree's scratch for chunks of `chunk` environments.  Stream-ordered (cudaMallocAsync / cudaFreeAsync

@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
   if (!sorted && !active) return;                   // (the sorted variant keeps every thread for its barriers)
 
   // this thread's frame record and leaf parameters (loads in flight while the rows land)
-  float* rec = A.rec + (size_t)slot * A.B + env;
-  const size_t fstride = (size_t)L * A.B;
+  float* rec = A.rec + rmp2_rec_base(env, L) + slot * RMP2_REC_TILE;      // tiled record scratch, see rmp2_tables.h
+  const int fstride = L * RMP2_REC_TILE;
   float px = 0.f, py = 0.f, pz = 0.f;
   float v[3] = {0.f, 0.f, 0.f}, a[3] = {0.f, 0.f, 0.f};
   if (active) {
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       if (!active) return;                                        // no barrier below this line
       slot = (home * ST.div_magic) >> 16, e_local = home - slot * E;
       env = env0 + e_local;
-      rec = A.rec + (size_t)slot * A.B + env;
+      rec = A.rec + rmp2_rec_base(env, L) + slot * RMP2_REC_TILE;
       gs = reinterpret_cast<const float4*>(A.spheres) + (size_t)env * O;
       if (kTma) row = tile + (uint32_t)e_local * pitch;
 #pragma unroll

@@ -11,6 +11,20 @@
 #define RMP2_CHAIN_FLOATS 24      // R(9) p(3) w(3) v(3) alpha(3) a(3)
 #define RMP2_PAIR_FLOATS 8        // floats per explicit pair row (rmp2_step_io.pairs)
 #define RMP2_REC_FLOATS 9         // fields of one frame record (p, v, a); the (S, g) sums overwrite them in place
+#define RMP2_REC_TILE 128         // environments per tile of the record scratch (see rmp2_rec_base)
+
+// The record scratch is tiled over the environment axis: rec[env / TILE][field * L + slot][env % TILE] (L = record
+// slots per environment).  Consecutive environments stay consecutive floats (full 128-byte lines per warp access), and
+// the distance between two fields of one environment is (L * TILE) floats -- a compile-time constant in the
+// tree-specialised kernels, so every record access there is base + immediate instead of a 64-bit add per field (the
+// field-major layout [field][slot][B] cost ~2 address instructions per access in the step kernel).
+// -> offset of (field 0, slot 0) of environment `env`; field f / slot s add (f * L + s) * RMP2_REC_TILE.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline size_t rmp2_rec_base(long long env, int L) {
+  return (size_t)(env / RMP2_REC_TILE) * ((size_t)RMP2_REC_FLOATS * L * RMP2_REC_TILE) + (size_t)(env % RMP2_REC_TILE);
+}
 
 struct FrameTab {
   float R[9];            // constant rotation  (reference: kinematics.py:202, R_x R_y R_z order)
@@ -94,7 +108,7 @@ struct StepArgs {
   const float* goals;
   const float* spheres;
   const float* pairs;
-  float* rec;            // [9][n_sphere_slots][B] scratch, field-major: frame records in, (S, g) sums out
+  float* rec;            // [ceil(B / TILE)][9 * n_sphere_slots][TILE] scratch (rmp2_rec_base): frame records in, (S, g) sums out
   float* mf;             // [N*N + N][B] scratch (N = kernel width): combined M and f between the step and the resolve
                          // kernel (split mode); in either mode the factorised problems handed to the fallback kernel
   int32_t* fb;           // fallback work list: [0] length, [1] block ticket, [2 ...] environment indices

@@ -14,6 +14,11 @@
 #define RMP2_BLOCK_THREADS 128
 #endif
 
+// Threads per block as a kernel body sees it: the launch's own value (kBlock = 0), or a compile-time constant when a
+// specialised kernel is built for one block size -- the shared-memory offsets of the chain-state slots and joint columns
+// are immediates then (config 4: 6090 -> 5710 instructions in the specialised step kernel).
+#define RMP2_BLOCKDIM (kBlock ? kBlock : (int)blockDim.x)
+
 #ifdef RMP2_JIT
 #define RMP2_UNROLL_SPEC _Pragma("unroll")
 #else
@@ -23,17 +28,17 @@
 // ------------------------------------------------------------------------------ chain walking
 // Visit frame `fi` of the depth-first execution list: restore / advance / save the chain state and,
 // when kCols, record the world axis and origin of the joint column the frame drives.
-template <int N, bool kCols>
+template <int N, bool kCols, int kBlock = 0>
 RMP2_DEV void visit_frame(const StepTables& T, int fi, const float (&q)[N], const float (&qd)[N], Chain& ch,
                           float* cols, float* slots) {
   const FrameTab& F = T.frames[fi];
   if (F.restore_slot == RMP2_SLOT_BASE) {
     chain_reset(ch);
   } else if (F.restore_slot >= 0) {
-    const float* s = slots + (size_t)F.restore_slot * RMP2_CHAIN_FLOATS * blockDim.x + threadIdx.x;
+    const float* s = slots + (size_t)F.restore_slot * RMP2_CHAIN_FLOATS * RMP2_BLOCKDIM + threadIdx.x;
     float* cf = reinterpret_cast<float*>(&ch);
 #pragma unroll
-    for (int i = 0; i < RMP2_CHAIN_FLOATS; ++i) cf[i] = s[i * blockDim.x];
+    for (int i = 0; i < RMP2_CHAIN_FLOATS; ++i) cf[i] = s[i * RMP2_BLOCKDIM];
   }
   float qi = 0.f, qdi = 0.f;
 #pragma unroll
@@ -45,27 +50,27 @@ RMP2_DEV void visit_frame(const StepTables& T, int fi, const float (&q)[N], cons
   float z[3];
   chain_advance(ch, F, qi, qdi, z);
   if (kCols && F.qidx >= 0) {                    // joint column -> shared memory (see pullback)
-    float* c = cols + (size_t)F.qidx * 6 * blockDim.x;
+    float* c = cols + (size_t)F.qidx * 6 * RMP2_BLOCKDIM;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      c[i * blockDim.x] = z[i];
-      c[(3 + i) * blockDim.x] = ch.p[i];
+      c[i * RMP2_BLOCKDIM] = z[i];
+      c[(3 + i) * RMP2_BLOCKDIM] = ch.p[i];
     }
   }
   if (F.save_slot >= 0) {
-    float* s = slots + (size_t)F.save_slot * RMP2_CHAIN_FLOATS * blockDim.x + threadIdx.x;
+    float* s = slots + (size_t)F.save_slot * RMP2_CHAIN_FLOATS * RMP2_BLOCKDIM + threadIdx.x;
     const float* cf = reinterpret_cast<const float*>(&ch);
 #pragma unroll
-    for (int i = 0; i < RMP2_CHAIN_FLOATS; ++i) s[i * blockDim.x] = cf[i];
+    for (int i = 0; i < RMP2_CHAIN_FLOATS; ++i) s[i * RMP2_BLOCKDIM] = cf[i];
   }
 }
 
 // ------------------------------------------------------------------------------- frames kernel
 // rec[field][slot][env] = (p, v, a) for every sphere-obstacle leaf slot (fields 0..8).
-template <int N>
+template <int N, int kBlock = 0>
 RMP2_DEV void frames_body(const StepTables& T, const StepArgs& A) {
   extern __shared__ float slots[];
-  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long env = (long long)blockIdx.x * RMP2_BLOCKDIM + threadIdx.x;
   if (env >= A.B) return;
   const int n = T.n;
   float q[N], qd[N];
@@ -76,18 +81,19 @@ RMP2_DEV void frames_body(const StepTables& T, const StepArgs& A) {
   }
   Chain ch;
   chain_reset(ch);
-  // records are field-major: rec[(field * L + slot) * B + env] -> every store below is one full line
-  float* rec = A.rec + env;
-  const size_t fstride = (size_t)T.n_sphere_slots * A.B;
+  // tiled record scratch (rmp2_rec_base): consecutive environments are consecutive floats -> every store below is
+  // one full line per warp, at an immediate offset from one base pointer in the specialised kernel
+  float* rec = A.rec + rmp2_rec_base(env, T.n_sphere_slots);
+  const int fstride = T.n_sphere_slots * RMP2_REC_TILE;
   RMP2_UNROLL_SPEC
   for (int fi = 0; fi < T.n_frames; ++fi) {
-    visit_frame<N, false>(T, fi, q, qd, ch, nullptr, slots);
+    visit_frame<N, false, kBlock>(T, fi, q, qd, ch, nullptr, slots);
     const FrameTab& F = T.frames[fi];
     RMP2_UNROLL_SPEC
     for (int li = F.leaf_begin; li < F.leaf_end; ++li) {
       const LeafTab& L = T.leaves[li];
       if (L.space != RMP2_SPACE_FRAME_DISTANCE_SPHERES) continue;
-      float* r = rec + (size_t)L.sphere_slot * A.B;
+      float* r = rec + L.sphere_slot * RMP2_REC_TILE;
       r[0 * fstride] = ch.p[0];
       r[1 * fstride] = ch.p[1];
       r[2 * fstride] = ch.p[2];
@@ -208,10 +214,10 @@ RMP2_DEV void resolve_or_defer(const StepArgs& A, float (&M)[N][N], float (&f)[N
 #endif
 // kSplit: stop after the combined (M, f) and hand them to rmp2_resolve_kernel through A.mf
 // (field-major [N*N + N][B]); used for large batches, where two small kernels beat one big one.
-template <int N, bool kSplit>
+template <int N, bool kSplit, int kBlock = 0>
 RMP2_DEV void step_body(const StepTables& T, const StepArgs& A) {
   extern __shared__ float slots[];
-  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long env = (long long)blockIdx.x * RMP2_BLOCKDIM + threadIdx.x;
   // no early return: the resolve uses full-warp votes; out-of-range lanes redo the last environment
   const bool active = env < A.B;
   const long long e = active ? env : A.B - 1;
@@ -235,8 +241,8 @@ RMP2_DEV void step_body(const StepTables& T, const StepArgs& A) {
 
   {
     // shared memory: [chain-state slots | joint columns (6 N floats per thread)]
-    float* cols = slots + (size_t)T.n_slots * RMP2_CHAIN_FLOATS * blockDim.x + threadIdx.x;
-    const int cstride = blockDim.x;
+    float* cols = slots + (size_t)T.n_slots * RMP2_CHAIN_FLOATS * RMP2_BLOCKDIM + threadIdx.x;
+    const int cstride = RMP2_BLOCKDIM;
     Chain ch;
     chain_reset(ch);
 #ifdef RMP2_JIT
@@ -248,8 +254,8 @@ RMP2_DEV void step_body(const StepTables& T, const StepArgs& A) {
       RMP2_UNROLL_SPEC
       for (int li = T.frames[fn].leaf_begin; li < T.frames[fn].leaf_end; ++li)
         if (T.leaves[li].space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) {
-          const float* r = A.rec + (size_t)T.leaves[li].sphere_slot * A.B + e;
-          const size_t fs = (size_t)T.n_sphere_slots * A.B;
+          const float* r = A.rec + rmp2_rec_base(e, T.n_sphere_slots) + T.leaves[li].sphere_slot * RMP2_REC_TILE;
+          const int fs = T.n_sphere_slots * RMP2_REC_TILE;
 #pragma unroll
           for (int i = 0; i < 9; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(r + i * fs));
         }
@@ -261,7 +267,7 @@ RMP2_DEV void step_body(const StepTables& T, const StepArgs& A) {
 #ifdef RMP2_JIT
       prefetch_sums(fi + 1);
 #endif
-      visit_frame<N, true>(T, fi, q, qd, ch, cols, slots);
+      visit_frame<N, true, kBlock>(T, fi, q, qd, ch, cols, slots);
       const FrameTab& F = T.frames[fi];
       if (F.leaf_begin >= F.leaf_end) continue;
 
@@ -329,8 +335,8 @@ RMP2_DEV void step_body(const StepTables& T, const StepArgs& A) {
         } else if (L.space == RMP2_SPACE_FRAME_DISTANCE_SPHERES) {
           if (A.n_spheres <= 0) continue;
           // sums over this leaf's spheres, produced by rmp2_spheres_kernel
-          const float* r = A.rec + (size_t)L.sphere_slot * A.B + e;
-          const size_t fstride = (size_t)T.n_sphere_slots * A.B;
+          const float* r = A.rec + rmp2_rec_base(e, T.n_sphere_slots) + L.sphere_slot * RMP2_REC_TILE;
+          const int fstride = T.n_sphere_slots * RMP2_REC_TILE;
 #pragma unroll
           for (int i = 0; i < 6; ++i) S[i] += __ldg(r + i * fstride);
 #pragma unroll
