@@ -770,7 +770,9 @@ long long chunk_envs(const rmp2_tree* tree) { return tree->chunk_envs > 0 ? tree
 
 size_t mf_floats_for(const rmp2_tree* tree, long long B) {
   const int N = rmp2_pick_width(tree->tab.n);
-  return (size_t)B * (N * N + N);
+  // split mode: the combined (M, f), field-major; fused mode: the fallback's rows (RMP2_HANDOFF_ROW(N) floats each)
+  const int handoff_row = (N * (N + 1) / 2 + 2 * N + 3) / 4 * 4;
+  return (size_t)B * std::max(N * N + N, handoff_row);
 }
 
 size_t fb_ints_for(long long B) { return (size_t)B + 4; }

@@ -503,16 +503,28 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_FALLBACK_MIN_BLOCKS(N
     const long long e = A.fb[2 + (valid ? i : count - 1)];
     float G[N][N], y[N], xs[N], qdd[N];
     int perm[N];
-    const float* in = A.mf + e;
+    float row[RMP2_HANDOFF_ROW(N)];                // [R upper triangle | Q^T f | perm], see defer_to_fallback
+    if (!A.split) {
+      const float4* in4 = reinterpret_cast<const float4*>(A.mf + (size_t)e * RMP2_HANDOFF_ROW(N));
+#pragma unroll
+      for (int i = 0; i < RMP2_HANDOFF_ROW(N) / 4; ++i) {
+        const float4 v = in4[i];
+        row[4 * i] = v.x, row[4 * i + 1] = v.y, row[4 * i + 2] = v.z, row[4 * i + 3] = v.w;
+      }
+    } else {
+      const float* in = A.mf + e;
+#pragma unroll
+      for (int i = 0; i < RMP2_HANDOFF_FIELDS(N); ++i) row[i] = in[(size_t)i * A.B];
+    }
     int k = 0;
 #pragma unroll
     for (int r = 0; r < N; ++r)
 #pragma unroll
-      for (int c = 0; c < N; ++c) G[r][c] = (c >= r) ? in[(size_t)(k++) * A.B] : 0.f;
+      for (int c = 0; c < N; ++c) G[r][c] = (c >= r) ? row[k++] : 0.f;
 #pragma unroll
-    for (int r = 0; r < N; ++r) y[r] = in[(size_t)(k++) * A.B];
+    for (int r = 0; r < N; ++r) y[r] = row[k++];
 #pragma unroll
-    for (int r = 0; r < N; ++r) perm[r] = __float_as_int(in[(size_t)(k++) * A.B]);
+    for (int r = 0; r < N; ++r) perm[r] = __float_as_int(row[k++]);
 #pragma unroll
     for (int r = 0; r < N; ++r) xs[r] = 0.f;
     resolve_jacobi<N, kQr>(G, y, perm, !valid, xs, R.rcond, qdd);

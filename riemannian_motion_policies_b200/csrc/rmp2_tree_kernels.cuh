@@ -148,6 +148,13 @@ RMP2_DEV void finish_step(const StepArgs& A, int n, long long e, bool active, bo
 // its registers and its warp divergence stay out of the kernels every environment passes through.
 //   A.fb: [0] = list length, [1] = block ticket of the fallback kernel, [2 ...] = environment indices
 #define RMP2_HANDOFF_FIELDS(N) ((N) * ((N) + 1) / 2 + 2 * (N))
+// Fused step kernel (A.split == 0): the mf scratch holds nothing else, and an environment's problem is ONE contiguous,
+// 16-byte aligned row of RMP2_HANDOFF_ROW(N) floats at mf + e * ROW -- a handful of 128-bit stores here, and a handful
+// of lines (one or two pages) per environment in the fallback kernel, whose lanes gather scattered environments: with
+// the field-major layout its 42 loads per lane each touched another 4 MB plane of the scratch and took 40 % of that
+// kernel's time (ncu: long_scoreboard at its head).  Split mode keeps the field-major layout [k][B] written over the
+// environment's own column: there the scratch still holds other environments' unread (M, f).
+#define RMP2_HANDOFF_ROW(N) ((RMP2_HANDOFF_FIELDS(N) + 3) / 4 * 4)
 
 template <int N>
 RMP2_DEV void defer_to_fallback(const StepArgs& A, long long e, bool need, const float (&G)[N][N],
@@ -161,6 +168,24 @@ RMP2_DEV void defer_to_fallback(const StepArgs& A, long long e, bool need, const
   base = __shfl_sync(0xffffffffu, base, leader);
   if (!need) return;
   A.fb[2 + base + __popc(ballot & ((1u << lane) - 1u))] = (int)e;
+  if (!A.split) {
+    float row[RMP2_HANDOFF_ROW(N)];
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = i; j < N; ++j) row[k++] = G[i][j];
+#pragma unroll
+    for (int i = 0; i < N; ++i) row[k++] = y[i];
+#pragma unroll
+    for (int i = 0; i < N; ++i) row[k++] = __int_as_float(perm[i]);
+#pragma unroll
+    for (; k < RMP2_HANDOFF_ROW(N); ++k) row[k] = 0.f;
+    float4* o4 = reinterpret_cast<float4*>(A.mf + (size_t)e * RMP2_HANDOFF_ROW(N));
+#pragma unroll
+    for (int i = 0; i < RMP2_HANDOFF_ROW(N) / 4; ++i) o4[i] = make_float4(row[4 * i], row[4 * i + 1], row[4 * i + 2], row[4 * i + 3]);
+    return;
+  }
   float* o = A.mf + e;
   int k = 0;
 #pragma unroll
