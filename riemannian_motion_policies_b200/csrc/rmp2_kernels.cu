@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 #define RMP2_SKIP_SORT 1              // re-deal the owners of a block by work before the early-out pair loop
 #endif
 #ifndef RMP2_SKIP_TRANSPOSED
-#define RMP2_SKIP_TRANSPOSED 1        // reach test of the sorted early-out by (environment, sphere chunk) threads, see below
+#define RMP2_SKIP_TRANSPOSED 0        // (being measured; 1 =) reach test of the sorted early-out by (environment, sphere chunk) threads, see below
 #endif
 #ifndef RMP2_SPHERES_STEPS_PER_TRIP
 #define RMP2_SPHERES_STEPS_PER_TRIP 4 // packed (two-sphere) steps per loop trip
