@@ -474,9 +474,6 @@ static int compile_tables_into(rmp2_tree* tr) {
     E = std::max(1, std::min(E, 32));
     tr->sph.envs_per_block = E;
     tr->sph.div_magic = 65536 / E + 1;
-    tr->sph.uniform_reach = 1;
-    for (int k = 1; k < T.n_sphere_slots; ++k)
-      if (memcmp(&tr->sph.p[k][SP_REACH], &tr->sph.p[0][SP_REACH], sizeof(float)) != 0) tr->sph.uniform_reach = 0;
   }
   return RMP2_OK;
 }

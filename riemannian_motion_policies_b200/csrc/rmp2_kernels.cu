@@ -112,9 +112,6 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 #ifndef RMP2_SKIP_SORT
 #define RMP2_SKIP_SORT 1              // re-deal the owners of a block by work before the early-out pair loop
 #endif
-#ifndef RMP2_SKIP_TRANSPOSED
-#define RMP2_SKIP_TRANSPOSED 0        // (being measured; 1 =) reach test of the sorted early-out by (environment, sphere chunk) threads, see below
-#endif
 #ifndef RMP2_SPHERES_STEPS_PER_TRIP
 #define RMP2_SPHERES_STEPS_PER_TRIP 4 // packed (two-sphere) steps per loop trip
 #endif
@@ -155,7 +152,7 @@ template <bool kTma, bool kSkip>
 __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP_MIN_BLOCKS : RMP2_SPHERES_MIN_BLOCKS) * 128 / RMP2_SPHERES_BLOCK)
     rmp2_spheres_kernel(const __grid_constant__ SphereTables ST, const __grid_constant__ StepArgs A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(16) SkipOwner owners[kSkip ? RMP2_SPHERES_BLOCK : 1];   // re-deal of the early-out variant (phase 2)
+  __shared__ SkipOwner owners[kSkip ? RMP2_SPHERES_BLOCK : 1];   // re-deal of the early-out variant (phase 2)
   __shared__ int hist[kSkip ? 33 : 1];
   const int L = ST.n_slots, E = ST.envs_per_block;
   const int t = threadIdx.x;
@@ -170,17 +167,6 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
   const int O = A.n_spheres;
   bool active = (slot < L) && (env < A.B);
   const bool sorted = kSkip && RMP2_SKIP_SORT && O <= 64;   // one mask word per parity: owners can be re-dealt
-  // Transposed reach test (staged rows, 6..9 obstacle slots with one common reach): the L threads of an environment
-  // split its spheres between them and each tests ITS spheres against all L control points, instead of every thread
-  // testing all spheres against its own control point.  What that buys: |c|^2 - (reach + r)^2 is formed once per
-  // sphere instead of once per pair (5 instead of 9 instructions per test), and a thread reads 2 * ceil(32 / L)
-  // sphere rows from shared memory instead of 64 -- the per-owner test moved 1 KB per thread through the shared-memory
-  // pipe, which was as busy as the issue slots in that phase.  Control points travel through shared memory
-  // (ctrl[slot][env] = (-2 p, |p|^2)), the c-bit fields of the masks come back the same way (fields[slot][env][chunk]);
-  // both live in the storage of `owners`, which is not in use before the re-deal.  One more block barrier.
-  const bool transposed = sorted && kTma && RMP2_SKIP_TRANSPOSED && L >= 6 && L <= 9 && ST.uniform_reach != 0;
-  float4* const ctrl = reinterpret_cast<float4*>(owners);                     // [L][E]
-  uint32_t* const fields = reinterpret_cast<uint32_t*>(ctrl + L * E);           // [L][E][L]
 
   uint32_t row = 0;                                 // shared-memory address of this thread's sphere row
   uint32_t tile = 0;                                // ... of the tile's first row
@@ -197,11 +183,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       mbar_init(bar, 1);
       mbar_expect_tx(bar, (uint32_t)rows * row_bytes);
     }
-    // barrier initialised before anyone copies or polls.  The copying threads (t < rows <= 32) all sit in warp 0 with
-    // the initialising thread: the transposed variant orders them with a warp barrier and lets its block barrier wait
-    // until the control points are in shared memory as well (one barrier for both).
-    if (transposed) __syncwarp();
-    else __syncthreads();
+    __syncthreads();                              // barrier initialised before anyone copies or polls
     for (int e = t; e < rows; e += blockDim.x)    // lane e copies row e (one warp's worth for E <= 32)
       bulk_load_1d(smem_u32(base) + (uint32_t)e * pitch,
                    reinterpret_cast<const unsigned char*>(A.spheres) + (size_t)(env0 + e) * row_bytes, row_bytes, bar);
@@ -236,14 +218,6 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
   float p[SP_COUNT];
 #pragma unroll
   for (int i = 0; i < SP_COUNT; ++i) p[i] = ST.p[active ? slot : 0][i];
-  // eta = 2^-20 = 16 eps32 bounds the rounding of the expanded test w = |c|^2 - R^2 + |p|^2 - 2 p.c (a dozen
-  // operations on terms no larger than 2 |c|^2 + 2 |p|^2 + R^2): the test is made on w - eta (2 |c|^2 + 2 |p|^2 + R^2),
-  // folded into the two constants, so a pair within reach is never dropped (a pair kept in excess adds exactly zero)
-  constexpr float kShrink = 1.f - 0x1p-19f, kGrow = 1.f + 0x1p-20f;
-  if (kSkip && transposed) {
-    if (active) ctrl[slot * E + e_local] = make_float4(-2.f * px, -2.f * py, -2.f * pz, kShrink * fmaf(px, px, fmaf(py, py, pz * pz)));
-    __syncthreads();                                // control points visible; mbarrier initialised (see above)
-  }
   if (kTma) {
     mbar_wait(bar, 0);
     // the sphere loads below are plain (non-volatile) asm so that the scheduler may hoist them over
@@ -407,52 +381,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       }
     } else {
       uint32_t me = 0u, mo = 0u;
-      if (kTma && transposed) {
-        // thread (chunk j = slot, environment e): sphere pairs k in [j c, j c + c), c = ceil(32 / L) <= 6
-        const int c = (32 + L - 1) / L;
-        const int k0 = slot * c, nk = min(c, 32 - k0);
-        if (active && nk > 0) {
-          const float reach = ST.p[0][SP_REACH];
-          float sx[12], sy[12], sz[12], sk[12];
-#pragma unroll
-          for (int i = 0; i < 12; ++i) {             // i even: even sphere of pair k0 + i / 2, i odd: the odd one
-            const int o = 2 * k0 + i;
-            if (i < 2 * nk && o < O) {
-              const float4 sp = load_sphere(o);
-              const float R = sp.w + reach;
-              sx[i] = sp.x, sy[i] = sp.y, sz[i] = sp.z;
-              sk[i] = fmaf(-kGrow * R, R, kShrink * fmaf(sp.x, sp.x, fmaf(sp.y, sp.y, sp.z * sp.z)));
-            } else {
-              sx[i] = 0.f, sy[i] = 0.f, sz[i] = 0.f, sk[i] = 1e30f;      // no such sphere: never within reach
-            }
-          }
-          for (int l = 0; l < L; ++l) {
-            const float4 cp = ctrl[l * E + e_local];
-            uint32_t fe = 0u, fo = 0u;
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-              if (i < nk) {
-                const float we = fmaf(sx[2 * i], cp.x, fmaf(sy[2 * i], cp.y, fmaf(sz[2 * i], cp.z, sk[2 * i] + cp.w)));
-                const float wo = fmaf(sx[2 * i + 1], cp.x, fmaf(sy[2 * i + 1], cp.y, fmaf(sz[2 * i + 1], cp.z, sk[2 * i + 1] + cp.w)));
-                fe = __funnelshift_l(__float_as_uint(we), fe, 1);        // sign bit: < 0 within reach
-                fo = __funnelshift_l(__float_as_uint(wo), fo, 1);
-              }
-            fields[(l * E + e_local) * L + slot] = fe | (fo << 16);
-          }
-        }
-        __syncthreads();                              // every chunk's fields are in
-        if (active) {
-          for (int j = 0; j < L; ++j) {
-            const int kj = j * c, nj = min(c, 32 - kj);
-            if (nj <= 0) break;
-            const uint32_t f = fields[(slot * E + e_local) * L + j];
-            me |= (f & 0xffffu) << (32 - kj - nj);    // reversed bit order: pair k <-> bit 31 - k (masked_pairs_rev)
-            mo |= (f >> 16) << (32 - kj - nj);
-          }
-        }
-      } else if (active) {
-        reach_masks_64(me, mo, kTma);
-      }
+      if (active) reach_masks_64(me, mo, kTma);
       const int steps = max(__popc(me), __popc(mo));            // 0 .. 32
       const int rank = atomicAdd(&hist[steps], 1);
       __syncthreads();

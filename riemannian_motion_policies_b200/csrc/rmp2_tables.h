@@ -75,7 +75,6 @@ struct SphereTables {
   int32_t n_slots;              // L
   int32_t envs_per_block;       // E: environments per thread block (E * L <= 128)
   int32_t div_magic;            // 65536 / E + 1: t / E == (t * div_magic) >> 16 for every thread index t < 512
-  int32_t uniform_reach;        // every slot has the same early-out reach (SP_REACH): the transposed reach test applies
   float p[RMP2_MAX_LEAVES][RMP2_LEAF_PARAMS];
 };
 
