@@ -407,6 +407,7 @@ static int compile_tables_into(rmp2_tree* tr) {
       L.sphere_slot = T.n_sphere_slots++;
       fill_sphere_row(leaves[i], tr->sph.p[L.sphere_slot]);
       tr->sph.p[L.sphere_slot][SP_WEIGHT] = (float)weight[i];
+      L.p[OA_G_SCALE] = tr->sph.p[L.sphere_slot][SP_INV_K2] * (float)weight[i];
     }
     if (vec_cursor + vlen > RMP2_VECPOOL) return fail(RMP2_ERR_UNSUPPORTED, "vector-parameter pool exhausted");
     L.vec_off = vec_cursor;

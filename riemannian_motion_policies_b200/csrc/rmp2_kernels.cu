@@ -146,7 +146,7 @@ RMP2_DEV void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64
 // ones -- which thread does the work changes, the sums do not: bit-identical to the all-pairs variant
 // (tests/test_gpu_step.py::test_early_out_is_exact).
 struct SkipOwner {                  // what travels with an owner when it is re-dealt (phase 2)
-  float p[3], v[3], a[3], pad;       // (13 words: an odd stride keeps owners[t] conflict free across a warp)
+  float p[3], v[3];                  // (9 words: an odd stride keeps owners[t] conflict free across a warp)
   uint32_t mask_even, mask_odd;
   int32_t thread;                   // the owner's home thread: slot = thread / E, environment = thread % E
 };
@@ -220,14 +220,10 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
   float* rec = A.rec + rmp2_rec_base(env, L) + slot * RMP2_REC_TILE;      // tiled record scratch, see rmp2_tables.h
   const int fstride = L * RMP2_REC_TILE;
   float px = 0.f, py = 0.f, pz = 0.f;
-  float v[3] = {0.f, 0.f, 0.f}, a[3] = {0.f, 0.f, 0.f};
+  float v[3] = {0.f, 0.f, 0.f};
   if (active) {
     px = rec[0 * fstride], py = rec[1 * fstride], pz = rec[2 * fstride];
     v[0] = rec[3 * fstride], v[1] = rec[4 * fstride], v[2] = rec[5 * fstride];
-    // a = Jdot qd of the frame origin is only used after the pair loop.  The all-pairs variant reads it there (three
-    // registers less through the loop: 0.879 vs 0.885 ms); the early-out variant's threads are short-lived and
-    // latency bound, a load at their end costs more than it saves (1.075 vs 1.064 ms per step)
-    if (kSkip) a[0] = rec[6 * fstride], a[1] = rec[7 * fstride], a[2] = rec[8 * fstride];
   }
   float p[SP_COUNT];
 #pragma unroll
@@ -415,7 +411,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
         SkipOwner& w = owners[before + rank];
         w.p[0] = px, w.p[1] = py, w.p[2] = pz;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) w.v[i] = v[i], w.a[i] = a[i];
+        for (int i = 0; i < 3; ++i) w.v[i] = v[i];
         w.mask_even = me, w.mask_odd = mo;
         w.thread = active ? t : -1;
       }
@@ -423,7 +419,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       const SkipOwner& r = owners[t];
       px = r.p[0], py = r.p[1], pz = r.p[2];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) v[i] = r.v[i], a[i] = r.a[i];
+      for (int i = 0; i < 3; ++i) v[i] = r.v[i];
       me = r.mask_even, mo = r.mask_odd;
       const int home = r.thread;
       active = home >= 0;
@@ -440,25 +436,15 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       else masked_pairs(0, me, mo);
     }
   }
-  // The pair loop left the n.a part of the curvature term out of g and accumulated k^2 g (obstacle_pair2):
-  // sum_o m (n.a) n = S a, once here.
-  if (!kSkip) a[0] = rec[6 * fstride], a[1] = rec[7 * fstride], a[2] = rec[8 * fstride];
-  const float a0 = a[0], a1 = a[1], a2 = a[2];
+  // The pair loop left the n.a part of the curvature term out of g and accumulated k^2 g (obstacle_pair2): the step
+  // kernel finishes with g = g_sum * weight / k^2 - S a (a = Jdot qd of the frame origin is at hand there).
   // SP_WEIGHT: this leaf stands for a group of obstacle leaves that share its control point (rmp2_tree_create); the
-  // group's sums are the weight times its own (1 for an ordinary leaf: the products below are exact)
+  // group's S is the weight times its own (1 for an ordinary leaf: the product is exact)
   const float wgt = ST.p[slot][SP_WEIGHT];
-  float Ss[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) Ss[i] = (S[i].x + S[i].y) * wgt;
-  const float ik2 = p[SP_INV_K2] * wgt;
-  const float g0 = fmaf(g[0].x + g[0].y, ik2, -fmaf(Ss[0], a0, fmaf(Ss[1], a1, Ss[2] * a2)));
-  const float g1 = fmaf(g[1].x + g[1].y, ik2, -fmaf(Ss[1], a0, fmaf(Ss[3], a1, Ss[4] * a2)));
-  const float g2 = fmaf(g[2].x + g[2].y, ik2, -fmaf(Ss[2], a0, fmaf(Ss[4], a1, Ss[5] * a2)));
+  for (int i = 0; i < 6; ++i) rec[i * fstride] = (S[i].x + S[i].y) * wgt;       // fields 0..5: S, 6..8: raw g sums (in place)
 #pragma unroll
-  for (int i = 0; i < 6; ++i) rec[i * fstride] = Ss[i];                 // fields 0..5: S, 6..8: g (in place)
-  rec[6 * fstride] = g0;
-  rec[7 * fstride] = g1;
-  rec[8 * fstride] = g2;
+  for (int i = 0; i < 3; ++i) rec[(6 + i) * fstride] = g[i].x + g[i].y;
 }
 
 // --------------------------------------------------------------------------------- step kernel

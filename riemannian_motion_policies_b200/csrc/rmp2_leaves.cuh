@@ -62,6 +62,7 @@
 #define OA_DEPS 11
 #define OA_K_REP 12       // -log2(e) / repulsion_std_dev
 #define OA_K_VEL 13       //  log2(e) / damping_velocity_gate_length_scale
+#define OA_G_SCALE 14     // sphere path: what the step kernel multiplies the pair kernel's raw force sums by: weight / k^2
 // CSPACE_BIASING
 #define CS_METRIC 0
 #define CS_PGAIN 1

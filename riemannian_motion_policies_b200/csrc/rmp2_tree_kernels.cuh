@@ -66,7 +66,9 @@ RMP2_DEV void visit_frame(const StepTables& T, int fi, const float (&q)[N], cons
 }
 
 // ------------------------------------------------------------------------------- frames kernel
-// rec[field][slot][env] = (p, v, a) for every sphere-obstacle leaf slot (fields 0..8).
+// rec[field][slot][env] = (p, v) of the frame origin for every sphere-obstacle leaf slot (fields 0..5; the pair kernel
+// overwrites fields 0..8 with its sums).  a = Jdot qd of the origin is not stored: only the step kernel needs it (for
+// the S a part of the curvature term), and it walks the chain itself.
 template <int N, int kBlock = 0>
 RMP2_DEV void frames_body(const StepTables& T, const StepArgs& A) {
   extern __shared__ float slots[];
@@ -100,9 +102,6 @@ RMP2_DEV void frames_body(const StepTables& T, const StepArgs& A) {
       r[3 * fstride] = ch.v[0];
       r[4 * fstride] = ch.v[1];
       r[5 * fstride] = ch.v[2];
-      r[6 * fstride] = ch.a[0];
-      r[7 * fstride] = ch.a[1];
-      r[8 * fstride] = ch.a[2];
     }
   }
 }
@@ -362,10 +361,20 @@ RMP2_DEV void step_body(const StepTables& T, const StepArgs& A) {
           // sums over this leaf's spheres, produced by rmp2_spheres_kernel
           const float* r = A.rec + rmp2_rec_base(e, T.n_sphere_slots) + L.sphere_slot * RMP2_REC_TILE;
           const int fstride = T.n_sphere_slots * RMP2_REC_TILE;
+          // fields 0..5: S = weight * sum_o m n n^T; 6..8: the raw force sums k^2 (g + S a)/weight (obstacle_pair2 leaves
+          // the n.a part of the curvature term out of its loop: sum_o m (n.a) n = S a, subtracted here, where a = Jdot qd
+          // of this frame's origin is at hand)
+          float Ss[6], gs[3];
 #pragma unroll
-          for (int i = 0; i < 6; ++i) S[i] += __ldg(r + i * fstride);
+          for (int i = 0; i < 6; ++i) Ss[i] = __ldg(r + i * fstride);
 #pragma unroll
-          for (int i = 0; i < 3; ++i) g[i] += __ldg(r + (6 + i) * fstride);
+          for (int i = 0; i < 3; ++i) gs[i] = __ldg(r + (6 + i) * fstride);
+          const float sc = L.p[OA_G_SCALE];
+          g[0] += fmaf(gs[0], sc, -fmaf(Ss[0], ch.a[0], fmaf(Ss[1], ch.a[1], Ss[2] * ch.a[2])));
+          g[1] += fmaf(gs[1], sc, -fmaf(Ss[1], ch.a[0], fmaf(Ss[3], ch.a[1], Ss[4] * ch.a[2])));
+          g[2] += fmaf(gs[2], sc, -fmaf(Ss[2], ch.a[0], fmaf(Ss[4], ch.a[1], Ss[5] * ch.a[2])));
+#pragma unroll
+          for (int i = 0; i < 6; ++i) S[i] += Ss[i];
           contrib = true;
         } else if (L.space == RMP2_SPACE_FRAME_DISTANCE_PAIRS) {  // explicit (pos_on_link, pos_on_obstacle)
           const int k0 = A.pair_off[L.pair_set], k1 = A.pair_off[L.pair_set + 1];
