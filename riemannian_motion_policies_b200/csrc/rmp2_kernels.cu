@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS, RMP2_RESOLVE_MIN_BLOCKS(N)
     q[j] = (rollout && j < n) ? A.q_rw[e * n + j] : 0.f;
     qd[j] = (rollout && j < n) ? A.qd_rw[e * n + j] : 0.f;
   }
-  resolve_or_defer<N, kQr>(A, M, f, n, R.rcond, e, active, rollout, q, qd);
+  resolve_or_defer<N, kQr, true>(A, M, f, n, R.rcond, e, active, rollout, q, qd);
 }
 
 // Stage 2: truncated SVD by one-sided Jacobi for the environments on the work list, starting from the

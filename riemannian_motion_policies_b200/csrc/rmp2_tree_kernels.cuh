@@ -155,7 +155,7 @@ RMP2_DEV void finish_step(const StepArgs& A, int n, long long e, bool active, bo
 // environment's own column: there the scratch still holds other environments' unread (M, f).
 #define RMP2_HANDOFF_ROW(N) ((RMP2_HANDOFF_FIELDS(N) + 3) / 4 * 4)
 
-template <int N>
+template <int N, bool kFieldMajor>     // kFieldMajor: called from the stand-alone resolve kernel (split mode, A.split == 1)
 RMP2_DEV void defer_to_fallback(const StepArgs& A, long long e, bool need, const float (&G)[N][N],
                                 const float (&y)[N], const int (&perm)[N]) {
   const unsigned ballot = __ballot_sync(0xffffffffu, need);
@@ -167,7 +167,7 @@ RMP2_DEV void defer_to_fallback(const StepArgs& A, long long e, bool need, const
   base = __shfl_sync(0xffffffffu, base, leader);
   if (!need) return;
   A.fb[2 + base + __popc(ballot & ((1u << lane) - 1u))] = (int)e;
-  if (!A.split) {
+  if (!kFieldMajor) {
     float row[RMP2_HANDOFF_ROW(N)];
     int k = 0;
 #pragma unroll
@@ -197,13 +197,13 @@ RMP2_DEV void defer_to_fallback(const StepArgs& A, long long e, bool need, const
   for (int i = 0; i < N; ++i) o[(size_t)(k++) * A.B] = __int_as_float(perm[i]);
 }
 
-template <int N, bool kQr>
+template <int N, bool kQr, bool kFieldMajor = false>
 RMP2_DEV void resolve_or_defer(const StepArgs& A, float (&M)[N][N], float (&f)[N], int n, float rcond, long long e,
                                bool active, bool rollout, float (&q)[N], float (&qd)[N]) {
   int perm[N];
   float qdd[N];
   const bool solved = resolve_direct<N, kQr>(M, f, perm, n, rcond, qdd);
-  defer_to_fallback<N>(A, e, active && !solved, M, f, perm);
+  defer_to_fallback<N, kFieldMajor>(A, e, active && !solved, M, f, perm);
   finish_step<N>(A, n, e, active && solved, rollout, q, qd, qdd);
 }
 
