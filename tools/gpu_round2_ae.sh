@@ -1,5 +1,5 @@
 #!/bin/bash
-# records without a = Jdot qd (the step kernel subtracts S a itself): full GPU tests + timing
+# full GPU tests, then two timing runs of the bench (all pairs / early-out / library default with per-kernel times)
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2ae_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2ae_tests.log
 tail -2 gpurun_out/r2ae_tests.log
