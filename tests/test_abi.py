@@ -238,6 +238,24 @@ def test_refresh_picks_up_leaf_changes(native_lib):
         core.compile(7)
 
 
+def test_host_inputs_travel_in_one_staging_buffer():
+    """_tensor.stage_host_inputs: every host argument of a call becomes a float32 view of ONE buffer (one host-to-device
+    copy), sections on 16-byte boundaries (sphere rows are read as float4), values rounded exactly like to_device."""
+    import torch
+    from riemannian_motion_policies_b200._tensor import stage_host_inputs
+    q = np.linspace(-1, 1, 7)                                   # float64 ndarray
+    qd = [0.1 * i for i in range(7)]                            # list
+    sph = torch.arange(24, dtype=torch.float64).reshape(2, 3, 4) / 7
+    out = stage_host_inputs((q, qd, None, sph), torch.device("cpu"))
+    assert out[2] is None and [tuple(o.shape) for o in out if o is not None] == [(7,), (7,), (2, 3, 4)]
+    assert all(o.dtype == torch.float32 and o.is_contiguous() for o in out if o is not None)
+    base = out[0].data_ptr()
+    assert [(o.data_ptr() - base) % 16 for o in out if o is not None] == [0, 0, 0]
+    assert (out[1].data_ptr() - base, out[3].data_ptr() - base) == (32, 64)      # 7 floats padded to 8
+    np.testing.assert_array_equal(out[0].numpy(), q.astype(np.float32))
+    np.testing.assert_array_equal(out[3].numpy(), sph.to(torch.float32).numpy())
+
+
 def test_oracle_sensitivity_yardstick():
     """oracle/harness.config_sensitivity: deterministic per environment (independent of the batch around it), at the
     eps32 scale for a well-conditioned tree, and kappa * eps32 for a nearly singular metric."""
