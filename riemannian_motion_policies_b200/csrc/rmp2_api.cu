@@ -475,6 +475,10 @@ static int compile_tables_into(rmp2_tree* tr) {
     E = std::max(1, std::min(E, 32));
     tr->sph.envs_per_block = E;
     tr->sph.div_magic = 65536 / E + 1;
+    tr->sph.div_magic_slots = 65536 / T.n_sphere_slots + 1;
+    // the slot-fastest order pays when the environment-fastest one misaligns its quarter-warps with the slots
+    // (measured: E = 21 gains 7 % on the early-out pair kernel, E = 16 loses 0.5 %)
+    tr->sph.slot_fastest = (E % 8 != 0) ? 1 : 0;
   }
   return RMP2_OK;
 }

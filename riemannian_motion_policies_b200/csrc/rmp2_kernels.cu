@@ -112,6 +112,9 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 #ifndef RMP2_SKIP_SORT
 #define RMP2_SKIP_SORT 1              // re-deal the owners of a block by work before the early-out pair loop
 #endif
+#ifndef RMP2_SLOT_FASTEST
+#define RMP2_SLOT_FASTEST (-1)        // early-out variant, thread <-> (slot, environment) with the slot fastest: -1 as the host decides, 0 / 1 forced
+#endif
 #ifndef RMP2_TMA_SPREAD
 #define RMP2_TMA_SPREAD 2             // issue the row copies of a tile from all warps: bit 0 all-pairs variant, bit 1 early-out variant
 #endif
@@ -148,7 +151,7 @@ RMP2_DEV void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint64
 struct SkipOwner {                  // what travels with an owner when it is re-dealt (phase 2)
   float p[3], v[3];                  // (9 words: an odd stride keeps owners[t] conflict free across a warp)
   uint32_t mask_even, mask_odd;
-  int32_t thread;                   // the owner's home thread: slot = thread / E, environment = thread % E
+  int32_t thread;                   // the owner's home thread (-> slot, environment: decode() in the kernel)
 };
 
 template <bool kTma, bool kSkip>
@@ -163,12 +166,30 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
     for (int i = t; i < 33; i += blockDim.x) hist[i] = 0;
     if (!kTma) __syncthreads();
   }
-  int slot = (t * ST.div_magic) >> 16;              // = t / E without the integer-division sequence
-  int e_local = t - slot * E;                       // consecutive lanes = consecutive environments
+  // thread <-> (slot, local environment).  Environment-fastest (t = slot * E + e): consecutive lanes are consecutive
+  // environments of one slot.  Slot-fastest (t = e * L + slot; early-out variant when the host asks for it,
+  // SphereTables::slot_fastest): the L threads of an environment sit in adjacent lanes and read the SAME sphere in the
+  // same instruction, so a warp's LDS.128 of the reach test touches 5-6 rows instead of 32 -- that kernel runs the
+  // shared-memory data pipe at 91 % of its peak (ncu), a third of it bank conflicts of the reach test when E is not a
+  // multiple of 8.  Measured (pair kernel, ms): L = 6 / E = 21 (Panda, merged control points) 0.4745 -> 0.4404;
+  // L = 8 / E = 16 0.6183 -> 0.6232 (stays environment-fastest); the all-pairs variant does not care (0.849 either way).
+  // (Divisions as multiply-shift: t / E = (t * magic) >> 16.)
+  const bool slot_fastest = kSkip && (RMP2_SLOT_FASTEST >= 0 ? RMP2_SLOT_FASTEST != 0 : ST.slot_fastest != 0);
+  auto decode = [&](int thr, int& s, int& e) {
+    if (slot_fastest) {
+      e = (thr * ST.div_magic_slots) >> 16;
+      s = thr - e * L;
+    } else {
+      s = (thr * ST.div_magic) >> 16;
+      e = thr - s * E;
+    }
+  };
+  int slot, e_local;
+  decode(t, slot, e_local);
   const long long env0 = (long long)blockIdx.x * E;
   long long env = env0 + e_local;
   const int O = A.n_spheres;
-  bool active = (slot < L) && (env < A.B);
+  bool active = (slot < L) && (e_local < E) && (env < A.B);
   const bool sorted = kSkip && RMP2_SKIP_SORT && O <= 64;   // one mask word per parity: owners can be re-dealt
 
   uint32_t row = 0;                                 // shared-memory address of this thread's sphere row
@@ -424,7 +445,7 @@ __global__ void __launch_bounds__(RMP2_SPHERES_BLOCK, (kSkip ? RMP2_SPHERES_SKIP
       const int home = r.thread;
       active = home >= 0;
       if (!active) return;                                        // no barrier below this line
-      slot = (home * ST.div_magic) >> 16, e_local = home - slot * E;
+      decode(home, slot, e_local);
       env = env0 + e_local;
       rec = A.rec + rmp2_rec_base(env, L) + slot * RMP2_REC_TILE;
       gs = reinterpret_cast<const float4*>(A.spheres) + (size_t)env * O;

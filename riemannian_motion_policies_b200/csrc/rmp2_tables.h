@@ -75,6 +75,8 @@ struct SphereTables {
   int32_t n_slots;              // L
   int32_t envs_per_block;       // E: environments per thread block (E * L <= 128)
   int32_t div_magic;            // 65536 / E + 1: t / E == (t * div_magic) >> 16 for every thread index t < 512
+  int32_t div_magic_slots;      // 65536 / L + 1: t / L likewise
+  int32_t slot_fastest;         // early-out variant: threads ordered (environment, slot) instead of (slot, environment)
   float p[RMP2_MAX_LEAVES][RMP2_LEAF_PARAMS];
 };
 
