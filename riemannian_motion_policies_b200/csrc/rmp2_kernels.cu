@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(RMP2_BLOCK_THREADS)
 
 // ------------------------------------------------------------------------------ spheres kernel
 // Thread t of a block <-> (obstacle-leaf slot t / E, local environment t % E); the block owns a tile of
-// E consecutive environments, so record loads/stores are contiguous across lanes.
+// E consecutive environments, so record loads/stores are contiguous across lanes.  (The early-out variant uses the
+// order (environment t / L, slot t % L) when E is not a multiple of 8: see `slot_fastest` in the kernel.)
 //
 // Staging (kTma): the spheres of one environment are one contiguous row of 16*O bytes in HBM; lane e < E
 // copies row e of the tile with one 1-D bulk copy (cp.async.bulk -- the TMA unit, completion on an
