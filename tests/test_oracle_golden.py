@@ -42,3 +42,41 @@ def test_pinv_cutoff_is_float32_in_both_modes():
     assert P[2, 2] == pytest.approx(2e5) and P[3, 3] == 0.0     # cutoff = 10*4*eps32 = 4.8e-6
     P32 = O.tf_pinv(M.float())
     assert P32[2, 2].item() == pytest.approx(2e5, rel=1e-5) and P32[3, 3].item() == 0.0
+
+
+@pytest.mark.parametrize("n,groups", [(7, [("panda_joint1", "panda_joint2"), ("panda_joint5", "panda_joint6")]),
+                                      (9, [("panda_joint1", "panda_joint2"), ("panda_joint5", "panda_joint6")])])
+def test_obstacle_leaves_on_coincident_frame_origins_pull_back_identically(n, groups):
+    """What RMP2_OPT_MERGE_COINCIDENT rests on, checked on the restated reference (float64, autodiff derivatives): the
+    distance map differentiates through the frame origin only (taskmap.py:124-128), so ObstacleAvoidance leaves with
+    equal gains on frames whose origins coincide for every q (a zero constant translation behind a revolute joint:
+    Panda joint2 on joint1, joint6 on joint5) contribute the same pulled-back (f, M) -- the reference computes it twice
+    and adds; the CUDA tree compiler runs one pair loop and doubles its sums.  Frames that do not coincide differ."""
+    from riemannian_motion_policies_b200 import scenarios as S
+    dtype = torch.float64
+    ns, fk = H.namespace(dtype), H.make_fkine(n, dtype)
+    frames = S.collision_frames(fk)
+    q, qd, goal = S.sample_panda_state(3, n, seed=11)
+    rng = np.random.RandomState(12)
+    for e in range(3):
+        sph = torch.as_tensor(np.concatenate([rng.uniform([-0.6, -0.6, 0.1], [0.6, 0.6, 1.0], size=(6, 3)),
+                                              rng.uniform(0.03, 0.08, size=(6, 1))], -1), dtype=dtype)
+        qe, qde = torch.as_tensor(q[e], dtype=dtype), torch.as_tensor(qd[e], dtype=dtype)
+        origins = H.frame_origins(fk, qe, frames)
+        r = origins[:, None, :] - sph[None, :, :3]
+        on_obst = sph[None, :, :3] + sph[None, :, 3:4] * r / torch.linalg.norm(r, dim=-1, keepdim=True)
+        on_link = origins[:, None, :].expand_as(on_obst)
+        idx = {fr: i for i, fr in enumerate(frames)}
+        core = S.build_config4(ns, fk, torch.as_tensor(goal[e], dtype=dtype), n,
+                               lambda fr: ns.TaskmapJointFrame4x4ToDistance(on_link[idx[fr]], on_obst[idx[fr]]))
+        pulled = {}
+        for fr in frames:
+            f, M = core._calculate_rmp(core.rmps[f"collision_avoidance_for_{fr}"], qe, qde)
+            pulled[fr] = (f.sum(0).numpy(), M.sum(0).numpy())
+        scale = max(np.abs(M).max() for _, M in pulled.values()) + 1e-30
+        for a, b in groups:
+            np.testing.assert_allclose(pulled[a][0], pulled[b][0], rtol=0, atol=1e-12 * max(1.0, np.abs(pulled[a][0]).max()))
+            np.testing.assert_allclose(pulled[a][1], pulled[b][1], rtol=0, atol=1e-12 * scale)
+        # ... and it is the coincidence that does it: joint3 sits 0.316 m away from joint2
+        assert np.abs(pulled["panda_joint3"][1] - pulled["panda_joint2"][1]).max() > 1e-6 * scale \
+            or np.abs(pulled["panda_joint3"][1]).max() == 0.0
