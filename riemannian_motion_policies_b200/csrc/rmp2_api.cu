@@ -368,6 +368,19 @@ static int compile_tables_into(rmp2_tree* tr) {
       weight[best] = members;
       tr->n_merged += members - 1;
     }
+    // A control point that cannot move -- its origin frame hangs on the base through fixed joints only and is not
+    // prismatic itself (Panda: joint1, and joint2 on top of it) -- has J = 0 identically: the leaf's pulled-back
+    // (M, f) is exactly zero in the reference as well (rmp.py:165-167 with J = 0).  Such a group runs no pair loop.
+    for (int i = 0; i < n_leaves; ++i) {
+      if (leaves[i].space != RMP2_SPACE_FRAME_DISTANCE_SPHERES || rep[i] != i) continue;
+      const int r = origin_root(leaves[i].frame);
+      bool immobile = rb.jtype[r] != RMP2_JOINT_PRISMATIC;
+      for (int a = rb.parent[r]; a >= 0 && immobile; a = rb.parent[a]) immobile = rb.jtype[a] == RMP2_JOINT_FIXED;
+      if (!immobile) continue;
+      tr->n_merged += 1;                              // (its merged companions are counted above)
+      for (int j = 0; j < n_leaves; ++j)
+        if (rep[j] == i) rep[j] = -2, weight[j] = 0;  // no representative: dropped from the tables (rep[i] itself included)
+    }
   }
 
   // frames that carry a leaf, and everything between them and the base
@@ -461,7 +474,7 @@ static int compile_tables_into(rmp2_tree* tr) {
     }
   T.n_leaves = leaf_cursor;
   for (int i = 0; i < n_leaves; ++i)
-    if (rep[i] != i) tr->table_index[i] = tr->table_index[rep[i]];
+    if (rep[i] >= 0 && rep[i] != i) tr->table_index[i] = tr->table_index[rep[i]];
   // leaves whose metric is a positive multiple of the identity keep M well conditioned
   T.precondition = 1;
   for (int i = 0; i < n_leaves; ++i) {

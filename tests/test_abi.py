@@ -184,27 +184,29 @@ def test_step_argument_checks_need_no_gpu(native_lib):
 
 def test_coincident_obstacle_leaves_are_merged(native_lib):
     """RMP2_OPT_MERGE_COINCIDENT: obstacle leaves with equal parameters on frames whose origins coincide for every q run
-    one pair loop (Panda: joint2 sits on joint1, joint6 on joint5; the finger joints are prismatic and stay).  A leaf
-    whose parameters differ leaves its group; switching the option off gives every leaf its own loop again."""
+    one pair loop (Panda: joint6 sits on joint5; the finger joints are prismatic and stay), and leaves whose control
+    point cannot move at all (joint1 on the base axis, joint2 on top of it: J = 0, their pulled-back (M, f) is exactly
+    zero in the reference too) run none.  A leaf whose parameters differ leaves its group; switching the option off
+    gives every leaf its own loop again."""
     ns = S.product_namespace()
     dist = lambda fr: ns.TaskmapJointFrame4x4ToSphereDistance()
     fk7 = ns.UrdfForwardKinematic(S.PANDA_WO_TOOL_URDF, S.PANDA_ORDER_7)
     core = S.build_config4(ns, fk7, [0.5, 0.0, 0.5], 7, dist)
     tree = core.compile(7)
-    assert tree.obstacle_slots() == (8, 6)
+    assert tree.obstacle_slots() == (8, 5)                      # {joint1, joint2} inert, {joint5, joint6} merged
     assert tree.specialize(compile_only=True) is None           # the merged tables still compile under NVRTC
     tree.set_merge_coincident(False)
     assert tree.obstacle_slots() == (8, 8)
     tree.set_merge_coincident(True)
-    assert tree.obstacle_slots() == (8, 6)
-    # the reference idiom `leaf.attr = value`, picked up at the next step: joint2's leaf leaves joint1's group
-    core.rmps["collision_avoidance_for_panda_joint2"].repulsion_gain = 700.
+    assert tree.obstacle_slots() == (8, 5)
+    # the reference idiom `leaf.attr = value`, picked up at the next step: joint6's leaf leaves joint5's group
+    core.rmps["collision_avoidance_for_panda_joint6"].repulsion_gain = 700.
     tree = core.compile(7)
-    assert tree.obstacle_slots() == (8, 7)
-    core.rmps["collision_avoidance_for_panda_joint2"].repulsion_gain = 800.
-    assert core.compile(7).obstacle_slots() == (8, 6)
+    assert tree.obstacle_slots() == (8, 6)
+    core.rmps["collision_avoidance_for_panda_joint6"].repulsion_gain = 800.
+    assert core.compile(7).obstacle_slots() == (8, 5)
     fk9 = ns.UrdfForwardKinematic(S.PANDA_URDF, S.PANDA_ORDER_9)
-    assert S.build_config4(ns, fk9, [0.5, 0.0, 0.5], 9, dist).compile(9).obstacle_slots() == (10, 8)
+    assert S.build_config4(ns, fk9, [0.5, 0.0, 0.5], 9, dist).compile(9).obstacle_slots() == (10, 7)
     assert native_lib.rmp2_tree_obstacle_slots(None, None, None) == 1
 
 
