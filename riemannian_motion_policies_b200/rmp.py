@@ -305,8 +305,8 @@ class CompiledTree:
         """registers / shared memory / resident blocks per SM of the kernels one step can launch."""
         out = {}
         for which, name in enumerate(("frames", "spheres", "step_fused", "step", "resolve", "resolve_fallback")):
-            if name in ("frames", "spheres") and not self.uses_spheres:
-                continue
+            if name in ("frames", "spheres") and (not self.uses_spheres or self.obstacle_slots()[1] == 0):
+                continue                     # no pair loop runs (no obstacle leaves, or every one of them is inert)
             regs, smem, bps, block = (ctypes.c_int32() for _ in range(4))
             _native.check(_native.lib().rmp2_tree_kernel_info(self.handle, which, n_spheres, ctypes.byref(regs),
                                                               ctypes.byref(smem), ctypes.byref(bps), ctypes.byref(block)))
