@@ -208,6 +208,13 @@ def test_coincident_obstacle_leaves_are_merged(native_lib):
     fk9 = ns.UrdfForwardKinematic(S.PANDA_URDF, S.PANDA_ORDER_9)
     assert S.build_config4(ns, fk9, [0.5, 0.0, 0.5], 9, dist).compile(9).obstacle_slots() == (10, 7)
     assert native_lib.rmp2_tree_obstacle_slots(None, None, None) == 1
+    # a tree whose only obstacle leaves are inert still compiles (no pair loop at all)
+    inert = ns.RmpCore()
+    inert.add_rmp(S.target_attractor(ns, fk7, [0.5, 0.0, 0.5]))
+    for fr in ("panda_joint1", "panda_joint2"):
+        inert.add_rmp(S.obstacle_leaf(ns, ns.chain_taskmaps([ns.TaskmapByForwardKinematic(fk7, fr), dist(fr)]), fr))
+    tree = inert.compile(7)
+    assert tree.obstacle_slots() == (2, 0) and tree.specialize(compile_only=True) is None
 
 
 def test_refresh_picks_up_leaf_changes(native_lib):
