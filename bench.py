@@ -615,7 +615,8 @@ def run_b200_arm(args):
                     "Obstacle leaves with equal parameters on frames whose origins coincide for every q (Panda: joint2 "
                     "on joint1, joint6 on joint5) have identical pulled-back (M, f) -- the distance map differentiates "
                     "through the frame origin only (taskmap.py:124-128) -- so one of them runs the pair loop and its "
-                    "sums are doubled; `value` and the roofline above run every leaf's loop"}
+                    "sums are doubled; leaves whose control point cannot move (joint1 / joint2: J = 0, exactly zero "
+                    "contribution in the reference as well) run none; `value` and the roofline above run every leaf's loop"}
         tree.set_early_out(False)
         tree.set_merge_coincident(False)
 

@@ -252,7 +252,9 @@ int rmp2_tree_kernel_info(const rmp2_tree* tree, int32_t which, int32_t n_sphere
  * zero column (the reference differentiates the distance through the frame origin only, taskmap.py:124-128), hence the
  * same pulled-back (M, f).  One leaf of the group runs the pair loop and the pullback, its sums are multiplied by the
  * size of the group.  Results equal the unmerged tree's up to rounding (M1 + M1 = 2 M1 is exact; the sum over leaves
- * is formed in another order).  0: every leaf on its own (used for the roofline measurement).  Changing the option
+ * is formed in another order).  A group whose control point cannot move at all (its origin frame hangs on the base
+ * through fixed joints only and is not prismatic; Panda: joint1, joint2) has J = 0 and a pulled-back (M, f) of exactly
+ * zero in the reference too: it runs no pair loop.  0: every leaf on its own (used for the roofline measurement).  Changing the option
  * recompiles the tree's tables (and its specialised kernels, when loaded). */
 #define RMP2_OPT_MERGE_COINCIDENT 5
 int rmp2_tree_set_option(rmp2_tree* tree, int32_t option, int32_t value);
